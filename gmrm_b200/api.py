@@ -1,0 +1,228 @@
+"""ctypes mirror of include/gmrm_b200.h.
+
+This is the binding a host language would write against the C ABI (INTEGRATION.md shows the C++
+one for the reference itself).  It holds no numerics: every method is one call into
+libgmrm_b200.so, which runs the sm_100a kernels.  There is no CPU fallback -- if the library is
+missing or there is no B200, loading / creating an engine raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgmrm_b200.so")
+
+
+class GmrmError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("N", C.c_int32), ("Mt", C.c_int32), ("T", C.c_int32),
+                ("G", C.c_int32), ("K", C.c_int32), ("world_size", C.c_int32), ("world_rank", C.c_int32),
+                ("vranks", C.c_int32), ("sync_rate", C.c_int32), ("shuffle", C.c_int32), ("seed", C.c_uint32),
+                ("nsm", C.c_int32), ("flags", C.c_int32)]
+
+
+_DP = C.POINTER(C.c_double)
+_IP = C.POINTER(C.c_int32)
+_BP = C.POINTER(C.c_uint8)
+
+
+class Replay(C.Structure):
+    _fields_ = [("perm", _IP), ("u", _DP), ("z", _DP), ("mu_draw", _DP), ("sigg_unit", _DP),
+                ("pi_unit", _DP), ("sige_unit", _DP)]
+
+
+class State(C.Structure):
+    _fields_ = [("sigmag", _DP), ("sigmae", _DP), ("pi", _DP), ("mu", _DP), ("m0", _IP), ("cass", _IP)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("marker_loop_ms", C.c_double), ("iteration_ms", C.c_double), ("dot_kernel_ms", C.c_double),
+                ("launches", C.c_int64), ("steps", C.c_int64), ("published", C.c_int64)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libgmrm_b200.so (built by gmrm_b200/csrc/Makefile).  Raises if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GmrmError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no Python/CPU fallback for the Gibbs path)")
+        L = C.CDLL(LIB_PATH)
+        L.gmrm_last_error.restype = C.c_char_p
+        L.gmrm_version.restype = C.c_char_p
+        L.gmrm_destroy.restype = None
+        L.gmrm_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise GmrmError(f"gmrm_b200 error {rc}: {lib().gmrm_last_error().decode()}")
+
+
+def _dp(a):
+    return a.ctypes.data_as(_DP) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(_IP) if a is not None else None
+
+
+def _bp(a):
+    return a.ctypes.data_as(_BP)
+
+
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(lib().gmrm_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Engine:
+    """One GPU's shard of the Gibbs chain (gmrm_engine)."""
+
+    def __init__(self, *, N, Mt, T=1, G=1, K=4, vranks=1, world_size=1, world_rank=0, sync_rate=1,
+                 shuffle=True, seed=0, device=0, nsm=0):
+        self.cfg = Config(device, N, Mt, T, G, K, world_size, world_rank, vranks, sync_rate, int(shuffle), seed, nsm, 0)
+        self._h = C.c_void_p()
+        _check(lib().gmrm_create(C.byref(self.cfg), C.byref(self._h)))
+        mb, mc, cs, ipl, tiles = C.c_int32(), C.c_int32(), C.c_int64(), C.c_int32(), C.c_int32()
+        _check(lib().gmrm_shard_info(self._h, C.byref(mb), C.byref(mc), C.byref(cs), C.byref(ipl), C.byref(tiles)))
+        self.marker_begin, self.marker_count = mb.value, mc.value
+        self.column_stride, self.individuals_per_lane, self.tiles = cs.value, ipl.value, tiles.value
+        self.N, self.Mt, self.T, self.G, self.K, self.R = N, Mt, T, G, K, vranks
+        self.mbytes = (N + 3) // 4
+        self.Mm = (Mt + vranks - 1) // vranks
+
+    def close(self):
+        if self._h:
+            lib().gmrm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- genotypes
+    def upload_bed(self, bed: np.ndarray, marker_begin: int | None = None):
+        bed = np.ascontiguousarray(bed, dtype=np.uint8)
+        assert bed.ndim == 2 and bed.shape[1] == self.mbytes
+        mb = self.marker_begin if marker_begin is None else marker_begin
+        _check(lib().gmrm_upload_bed(self._h, _bp(bed), mb, bed.shape[0]))
+
+    def generate_bed(self, seed=1, maf_lo=0.05, maf_hi=0.5, missing_rate=0.0):
+        _check(lib().gmrm_generate_bed(self._h, C.c_uint32(seed), C.c_double(maf_lo), C.c_double(maf_hi), C.c_double(missing_rate)))
+
+    def download_bed(self, marker_begin: int | None = None, count: int | None = None) -> np.ndarray:
+        mb = self.marker_begin if marker_begin is None else marker_begin
+        n = self.marker_count if count is None else count
+        out = np.empty((n, self.mbytes), dtype=np.uint8)
+        _check(lib().gmrm_download_bed(self._h, _bp(out), mb, n))
+        return out
+
+    def finalize_bed(self):
+        _check(lib().gmrm_finalize_bed(self._h))
+
+    # ---- phenotypes / groups
+    def set_phenotype(self, t: int, eps0: np.ndarray, mask4: np.ndarray, nonas: int):
+        eps0 = np.ascontiguousarray(eps0[: self.N], dtype=np.float64)
+        mask4 = np.ascontiguousarray(mask4, dtype=np.uint8)
+        _check(lib().gmrm_set_phenotype(self._h, t, _dp(eps0), _bp(mask4), int(nonas)))
+
+    def set_groups(self, group_index: np.ndarray, cva: np.ndarray):
+        gi = np.ascontiguousarray(group_index, dtype=np.int32)
+        cva = np.ascontiguousarray(cva, dtype=np.float64)
+        assert gi.size == self.Mt and cva.size == self.G * self.K
+        _check(lib().gmrm_set_groups(self._h, _ip(gi), _dp(cva)))
+
+    # ---- statistics and hooks
+    def compute_marker_stats(self):
+        _check(lib().gmrm_compute_marker_stats(self._h))
+
+    def marker_stats(self, t: int):
+        mave = np.empty(self.marker_count); msig = np.empty(self.marker_count)
+        _check(lib().gmrm_get_marker_stats(self._h, t, _dp(mave), _dp(msig)))
+        return mave, msig
+
+    def dot_products(self, local_ids) -> np.ndarray:
+        ids = np.ascontiguousarray(local_ids, dtype=np.int32)
+        out = np.empty((ids.size, self.T))
+        _check(lib().gmrm_dot_products(self._h, _ip(ids), ids.size, _dp(out)))
+        return out
+
+    def decode_marker(self, local_id: int):
+        a = np.empty(self.N); b = np.empty(self.N)
+        _check(lib().gmrm_decode_marker(self._h, local_id, _dp(a), _dp(b)))
+        return a, b
+
+    def decode_namask(self, t: int) -> np.ndarray:
+        na = np.empty(self.N)
+        _check(lib().gmrm_decode_namask(self._h, t, _dp(na)))
+        return na
+
+    def apply_update(self, t: int, local_id: int, dbeta: float):
+        _check(lib().gmrm_apply_update(self._h, t, local_id, C.c_double(dbeta)))
+
+    # ---- chain
+    def init_chain(self, sigmag_init: np.ndarray | None = None):
+        a = None if sigmag_init is None else np.ascontiguousarray(sigmag_init, dtype=np.float64)
+        _check(lib().gmrm_init_chain(self._h, _dp(a)))
+
+    def run_iteration(self, it: int, replay: dict | None = None):
+        rp = None
+        keep = []
+        if replay is not None:
+            rp = Replay()
+            for name, _t in Replay._fields_:
+                a = replay.get(name)
+                if a is None:
+                    continue
+                a = np.ascontiguousarray(a, dtype=np.int32 if name == "perm" else np.float64)
+                keep.append(a)
+                setattr(rp, name, _ip(a) if name == "perm" else _dp(a))
+        _check(lib().gmrm_run_iteration(self._h, it, C.byref(rp) if rp is not None else None))
+
+    def state(self) -> dict:
+        T, G, K = self.T, self.G, self.K
+        d = {"sigmag": np.empty((T, G)), "sigmae": np.empty(T), "pi": np.empty((T, G, K)), "mu": np.empty(T),
+             "m0": np.empty((T, G), dtype=np.int32), "cass": np.empty((T, G, K), dtype=np.int32)}
+        st = State(_dp(d["sigmag"]), _dp(d["sigmae"]), _dp(d["pi"]), _dp(d["mu"]), _ip(d["m0"]), _ip(d["cass"]))
+        _check(lib().gmrm_get_state(self._h, C.byref(st)))
+        return d
+
+    def betas(self, t: int) -> np.ndarray:
+        out = np.empty(self.marker_count)
+        _check(lib().gmrm_get_betas(self._h, t, _dp(out)))
+        return out
+
+    def components(self, t: int) -> np.ndarray:
+        out = np.empty(self.marker_count, dtype=np.int32)
+        _check(lib().gmrm_get_components(self._h, t, _ip(out)))
+        return out
+
+    def epsilon(self, t: int) -> np.ndarray:
+        out = np.empty(self.N)
+        _check(lib().gmrm_get_epsilon(self._h, t, _dp(out)))
+        return out
+
+    def timing(self) -> dict:
+        tm = Timing()
+        _check(lib().gmrm_get_timing(self._h, C.byref(tm)))
+        return {k: getattr(tm, k) for k, _ in Timing._fields_}
+
+    def set_timing_detail(self, on: bool):
+        _check(lib().gmrm_set_timing_detail(self._h, int(on)))
+
+    def comm_init(self, uid: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        _check(lib().gmrm_comm_init(self._h, buf))

@@ -1,0 +1,760 @@
+// C ABI of gmrm_b200 (include/gmrm_b200.h): engine state, HBM buffers, per-iteration driver.
+// One engine == one GPU == one contiguous shard of markers.  No CPU fallback anywhere: every
+// entry point that computes does so by launching the kernels in kernels.cu.
+#include "../../include/gmrm_b200.h"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace gmrm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorMemoryAllocation ? GMRM_ENOMEM : GMRM_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+// ---- NCCL, bound at run time so that a single-GPU run needs no NCCL at all -----------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (h) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names)
+            if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+        Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast;
+    }
+} g_nccl;
+constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
+
+#define NC(call)                                                                                        \
+    do {                                                                                                \
+        int r_ = (call);                                                                                \
+        if (r_ != 0) return fail(GMRM_ENCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call,                  \
+                                 g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "nccl error");     \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        free();
+        n = count;
+        if (count == 0) return 0;
+        CU(cudaMalloc(&p, count * sizeof(T)));
+        return 0;
+    }
+    int zero(cudaStream_t s) {
+        if (n) CU(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+        return 0;
+    }
+    void free() {
+        if (p) cudaFree(p);
+        p = nullptr; n = 0;
+    }
+    ~DevBuf() { free(); }
+};
+
+void block_of(int Mt, int R, int r, int& S, int& M) {   // Bayes::set_block_of_markers, bayes.cpp:903-925
+    const int size = Mt / R, modu = Mt % R;
+    M = size + (r < modu ? 1 : 0);
+    S = r * size + std::min(r, modu);
+}
+
+}  // namespace
+
+struct gmrm_engine {
+    gmrm_config cfg{};
+    Layout L{};
+    cudaStream_t stream = nullptr;
+    int Vl = 0, r0 = 0, marker_begin = 0, Mloc = 0, Mm = 0;
+    bool bed_final = false, stats_done = false, chain_ready = false, groups_set = false;
+    std::vector<char> phen_set;
+    std::vector<double> h_cva;
+    std::vector<int32_t> h_nonas;
+
+    DevBuf<uint8_t> bed, namask2, stage;
+    DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old, zeros;
+    DevBuf<double> delta, delta_tot;
+    DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
+    DevBuf<uint32_t> miss_off, miss_idx;
+    DevBuf<PubEntry> pub;
+    DevBuf<int64_t> npub;
+    // replay staging
+    DevBuf<int32_t> rep_perm;
+    DevBuf<double> rep_u, rep_z, rep_small;
+
+    ncclComm_t comm = nullptr;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> dot_ev;
+    bool timing_detail = false;
+    gmrm_timing last{};
+
+    ~gmrm_engine() {
+        if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : dot_ev) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+extern "C" {
+
+const char* gmrm_last_error(void) { return g_err.c_str(); }
+const char* gmrm_version(void) { return "gmrm_b200 0.1 (sm_100a)"; }
+
+int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
+    if (!c || !out) return fail(GMRM_EINVAL, "null argument");
+    *out = nullptr;
+    if (c->N < 2 || c->Mt < 1 || c->T < 1 || c->T > 32 || c->G < 1 || c->K < 2 || c->K > kMaxK)
+        return fail(GMRM_EINVAL, "bad dimensions N=%d Mt=%d T=%d G=%d K=%d (T<=32, 2<=K<=%d)", c->N, c->Mt, c->T, c->G, c->K, kMaxK);
+    if (c->world_size < 1 || c->world_rank < 0 || c->world_rank >= c->world_size)
+        return fail(GMRM_EINVAL, "bad world_rank %d / world_size %d", c->world_rank, c->world_size);
+    if (c->vranks < c->world_size || c->vranks % c->world_size != 0 || c->vranks > c->Mt)
+        return fail(GMRM_EINVAL, "vranks=%d must be a multiple of world_size=%d and <= Mt=%d", c->vranks, c->world_size, c->Mt);
+    if (c->sync_rate < 1) return fail(GMRM_EINVAL, "sync_rate must be >= 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(GMRM_ENODEVICE, "no CUDA device: gmrm_b200 has no CPU path");
+    }
+    if (c->device < 0 || c->device >= ndev) return fail(GMRM_EINVAL, "device %d out of range (%d visible)", c->device, ndev);
+    CU(cudaSetDevice(c->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    if (prop.major != 10) return fail(GMRM_ENODEVICE, "device %s is sm_%d%d; this library carries sm_100a code only", prop.name, prop.major, prop.minor);
+
+    auto* e = new gmrm_engine();
+    e->cfg = *c;
+    const int nsm = c->nsm > 0 ? c->nsm : prop.multiProcessorCount;
+    e->L = make_layout(c->N, nsm);
+    if (e->L.E4 == 0) {
+        delete e;
+        return fail(GMRM_EINVAL, "N=%d does not fit %d tiles x 128 lanes x 32 individuals", c->N, nsm);
+    }
+    e->Vl = c->vranks / c->world_size;
+    e->r0 = c->world_rank * e->Vl;
+    int S, M, Slast, Mlast;
+    block_of(c->Mt, c->vranks, e->r0, S, M);
+    block_of(c->Mt, c->vranks, e->r0 + e->Vl - 1, Slast, Mlast);
+    e->marker_begin = S;
+    e->Mloc = Slast + Mlast - S;
+    e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
+    e->phen_set.assign(c->T, 0);
+    e->h_nonas.assign(c->T, 0);
+
+    int rc = 0;
+    auto A = [&](int r) { if (rc == 0) rc = r; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return fail(GMRM_ECUDA, "stream create failed"); }
+    for (auto& evn : e->ev) if (cudaEventCreate(&evn) != cudaSuccess) { delete e; return fail(GMRM_ECUDA, "event create failed"); }
+    const Layout& L = e->L;
+    const int T = c->T, G = c->G, K = c->K;
+    A(e->bed.alloc((size_t)e->Mloc * L.col_stride));
+    A(e->namask2.alloc((size_t)T * L.col_stride));
+    A(e->eps.alloc((size_t)T * L.npad));
+    A(e->mave.alloc((size_t)T * e->Mloc)); A(e->msig.alloc((size_t)T * e->Mloc));
+    A(e->betas.alloc((size_t)T * e->Mloc)); A(e->comp.alloc((size_t)T * e->Mloc));
+    A(e->group_loc.alloc(e->Mloc)); A(e->mtotgrp.alloc(G));
+    A(e->cva.alloc((size_t)G * K)); A(e->cvai.alloc((size_t)G * K));
+    A(e->steptab.alloc((size_t)e->Mm * e->Vl));
+    A(e->partial.alloc((size_t)e->Vl * T * L.nsm * 4));
+    A(e->spart.alloc((size_t)T * L.nsm));
+    A(e->pub.alloc((size_t)e->Vl * T));
+    A(e->cass.alloc((size_t)T * G * K)); A(e->m0.alloc((size_t)T * G));
+    A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T));
+    A(e->sigmag.alloc((size_t)T * G)); A(e->sigmae.alloc(T)); A(e->pi.alloc((size_t)T * G * K));
+    A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T));
+    A(e->zeros.alloc((size_t)kDotThreads * kBatch));
+    A(e->err.alloc(1)); A(e->npub.alloc(1));
+    A(e->miss_off.alloc((size_t)e->Mloc + 1));
+    if (c->world_size > 1) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
+    if (rc != 0) { delete e; return rc; }
+    // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
+    for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
+                    &e->mu_old, &e->zeros, &e->partial, &e->delta, &e->delta_tot})
+        if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
+        if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->bed.zero(e->stream) || e->namask2.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
+    if (cudaMemsetAsync(e->pub.p, 0, e->pub.n * sizeof(PubEntry), e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) {
+        delete e;
+        return fail(GMRM_ECUDA, "initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    *out = e;
+    return GMRM_OK;
+}
+
+void gmrm_destroy(gmrm_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    delete e;
+}
+
+int gmrm_shard_info(const gmrm_engine* e, int32_t* marker_begin, int32_t* marker_count, int64_t* column_stride_bytes,
+                    int32_t* individuals_per_lane, int32_t* tiles) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (marker_begin) *marker_begin = e->marker_begin;
+    if (marker_count) *marker_count = e->Mloc;
+    if (column_stride_bytes) *column_stride_bytes = e->L.col_stride;
+    if (individuals_per_lane) *individuals_per_lane = e->L.E;
+    if (tiles) *tiles = e->L.nsm;
+    return GMRM_OK;
+}
+
+// ------------------------------------------------------------------------------------ genotypes
+static int ensure_stage(gmrm_engine* e, size_t bytes) {
+    if (e->stage.n >= bytes) return 0;
+    return e->stage.alloc(bytes);
+}
+
+static int chunk_markers(const gmrm_engine* e) {
+    const size_t budget = 256u << 20;
+    size_t n = budget / (size_t)e->L.mbytes;
+    return (int)std::max<size_t>(1, std::min<size_t>(n, 65535));   // grid.y limit
+}
+
+int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, int32_t marker_count) {
+    if (!e || !bed) return fail(GMRM_EINVAL, "null argument");
+    if (marker_count < 0 || marker_begin < e->marker_begin || marker_begin + marker_count > e->marker_begin + e->Mloc)
+        return fail(GMRM_EINVAL, "markers [%d, %d) outside this shard [%d, %d)", marker_begin, marker_begin + marker_count,
+                    e->marker_begin, e->marker_begin + e->Mloc);
+    CU(cudaSetDevice(e->cfg.device));
+    const int chunk = chunk_markers(e);
+    int rc = ensure_stage(e, (size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes);
+    if (rc) return rc;
+    for (int done = 0; done < marker_count; done += chunk) {
+        const int n = std::min(chunk, marker_count - done);
+        CU(cudaMemcpyAsync(e->stage.p, bed + (size_t)done * e->L.mbytes, (size_t)n * e->L.mbytes, cudaMemcpyHostToDevice, e->stream));
+        launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)(marker_begin - e->marker_begin + done) * e->L.col_stride, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));   // the staging buffer is reused by the next chunk
+    }
+    e->bed_final = false;
+    return GMRM_OK;
+}
+
+int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_hi, double missing_rate) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    const int chunk = chunk_markers(e);
+    int rc = ensure_stage(e, (size_t)std::min(chunk, e->Mloc) * e->L.mbytes);
+    if (rc) return rc;
+    for (int done = 0; done < e->Mloc; done += chunk) {
+        const int n = std::min(chunk, e->Mloc - done);
+        launch_generate_plink(e->stage.p, n, e->marker_begin + done, e->L, seed, maf_lo, maf_hi, missing_rate, e->stream);
+        launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)done * e->L.col_stride, e->stream);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(e->stream));
+    e->bed_final = false;
+    return GMRM_OK;
+}
+
+int gmrm_download_bed(gmrm_engine* e, uint8_t* out, int32_t marker_begin, int32_t marker_count) {
+    if (!e || !out) return fail(GMRM_EINVAL, "null argument");
+    if (marker_count < 0 || marker_begin < e->marker_begin || marker_begin + marker_count > e->marker_begin + e->Mloc)
+        return fail(GMRM_EINVAL, "markers outside this shard");
+    CU(cudaSetDevice(e->cfg.device));
+    const int chunk = chunk_markers(e);
+    int rc = ensure_stage(e, (size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes);
+    if (rc) return rc;
+    for (int done = 0; done < marker_count; done += chunk) {
+        const int n = std::min(chunk, marker_count - done);
+        launch_untranscode(e->bed.p + (size_t)(marker_begin - e->marker_begin + done) * e->L.col_stride, n, e->L, e->stage.p, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + (size_t)done * e->L.mbytes, e->stage.p, (size_t)n * e->L.mbytes, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    return GMRM_OK;
+}
+
+int gmrm_finalize_bed(gmrm_engine* e) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    DevBuf<uint32_t> counts;
+    int rc = counts.alloc(e->Mloc);
+    if (rc) return rc;
+    launch_count_missing(e->bed.p, e->Mloc, e->L, counts.p, e->stream);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> h(e->Mloc), off((size_t)e->Mloc + 1, 0);
+    CU(cudaMemcpyAsync(h.data(), counts.p, (size_t)e->Mloc * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    uint64_t tot = 0;
+    for (int j = 0; j < e->Mloc; j++) { off[j] = (uint32_t)tot; tot += h[j]; }
+    if (tot > 0xffffffffull) return fail(GMRM_EINVAL, "more than 2^32 missing genotypes in one shard");
+    off[e->Mloc] = (uint32_t)tot;
+    CU(cudaMemcpyAsync(e->miss_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    rc = e->miss_idx.alloc(std::max<uint64_t>(tot, 1));
+    if (rc) return rc;
+    if (tot) launch_fill_missing(e->bed.p, e->Mloc, e->L, e->miss_off.p, e->miss_idx.p, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    e->stage.free();
+    e->bed_final = true;
+    e->stats_done = false;
+    return GMRM_OK;
+}
+
+// ---------------------------------------------------------------------------- phenotypes, groups
+int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint8_t* mask4, int32_t nonas) {
+    if (!e || !eps0 || !mask4) return fail(GMRM_EINVAL, "null argument");
+    if (t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "trait %d out of range", t);
+    if (nonas < 2 || nonas > e->cfg.N) return fail(GMRM_EINVAL, "nonas=%d out of range", nonas);
+    CU(cudaSetDevice(e->cfg.device));
+    const Layout& L = e->L;
+    std::vector<double> h((size_t)L.npad, 0.0);
+    std::vector<uint8_t> nm((size_t)L.col_stride, 0);
+    int seen = 0;
+    for (int i = 0; i < L.N; i++) {
+        const bool obs = (mask4[i / 4] >> (i % 4)) & 1;
+        h[i] = obs ? eps0[i] : 0.0;
+        if (!obs) continue;
+        seen++;
+        const int64_t s = i / L.E;
+        const int k = i % L.E, c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
+        nm[(size_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, k / 4)] |= (uint8_t)(1u << (2 * (k % 4)));
+    }
+    if (seen != nonas) return fail(GMRM_EINVAL, "mask4 has %d observed individuals but nonas=%d", seen, nonas);
+    CU(cudaMemcpyAsync(e->eps.p + (size_t)t * L.npad, h.data(), h.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->namask2.p + (size_t)t * L.col_stride, nm.data(), nm.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->nonas.p + t, &nonas, 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->h_nonas[t] = nonas;
+    e->phen_set[t] = 1;
+    e->stats_done = false;
+    e->chain_ready = false;
+    return GMRM_OK;
+}
+
+int gmrm_set_groups(gmrm_engine* e, const int32_t* group_index, const double* cva) {
+    if (!e || !group_index || !cva) return fail(GMRM_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const int G = e->cfg.G, K = e->cfg.K;
+    std::vector<int32_t> mt(G, 0);
+    for (int j = 0; j < e->cfg.Mt; j++) {
+        if (group_index[j] < 0 || group_index[j] >= G) return fail(GMRM_EINVAL, "marker %d has group %d outside [0, %d)", j, group_index[j], G);
+        mt[group_index[j]]++;                                         // bayes.cpp:807-809
+    }
+    std::vector<double> cvai((size_t)G * K, 0.0);
+    for (int g = 0; g < G; g++) {
+        if (cva[g * K] != 0.0) return fail(GMRM_EINVAL, "first mixture of group %d must be 0.0", g);     // options.cpp:273-276
+        for (int k = 1; k < K; k++) {
+            if (cva[g * K + k] <= cva[g * K + k - 1]) return fail(GMRM_EINVAL, "mixtures of group %d not ascending", g);   // 278-281
+            cvai[g * K + k] = 1.0 / cva[g * K + k];                    // 282
+        }
+    }
+    e->h_cva.assign(cva, cva + (size_t)G * K);
+    CU(cudaMemcpyAsync(e->group_loc.p, group_index + e->marker_begin, (size_t)e->Mloc * 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->mtotgrp.p, mt.data(), (size_t)G * 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->cva.p, cva, (size_t)G * K * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->cvai.p, cvai.data(), (size_t)G * K * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->groups_set = true;
+    e->chain_ready = false;
+    return GMRM_OK;
+}
+
+// ------------------------------------------------------------------------------ marker statistics
+int gmrm_compute_marker_stats(gmrm_engine* e) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
+    for (int t = 0; t < e->cfg.T; t++)
+        if (!e->phen_set[t]) return fail(GMRM_EINVAL, "phenotype %d not set", t);
+    CU(cudaSetDevice(e->cfg.device));
+    launch_stats(e->bed.p, e->Mloc, e->L, e->namask2.p, e->nonas.p, e->cfg.T, e->mave.p, e->msig.p, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    e->stats_done = true;
+    return GMRM_OK;
+}
+
+int gmrm_get_marker_stats(gmrm_engine* e, int32_t t, double* mave, double* msig) {
+    if (!e || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    CU(cudaSetDevice(e->cfg.device));
+    if (mave) CU(cudaMemcpy(mave, e->mave.p + (size_t)t * e->Mloc, (size_t)e->Mloc * 8, cudaMemcpyDeviceToHost));
+    if (msig) CU(cudaMemcpy(msig, e->msig.p + (size_t)t * e->Mloc, (size_t)e->Mloc * 8, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+
+// ------------------------------------------------------------------------------ shared launch glue
+// Traits per dot-kernel launch: the lane keeps E x Tc weights in registers; beyond ~48-64 doubles
+// ptxas spills (table in DESIGN.md), so wide lanes take fewer traits per pass over the genotypes.
+static int trait_chunk(int E) {
+    if (E * 4 <= 48) return 4;
+    if (E * 3 <= 48) return 3;
+    if (E * 2 <= 64) return 2;
+    return 1;
+}
+
+static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* partial) {
+    const int T = e->cfg.T, tc = trait_chunk(e->L.E);
+    for (int t0 = 0; t0 < T; t0 += tc) {
+        DotParams p{};
+        p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
+        p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm * 4;
+        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p;
+        if (launch_dot(e->L, std::min(tc, T - t0), p, e->stream) != 0) return fail(GMRM_ECUDA, "dot kernel launch setup failed");
+    }
+    return 0;
+}
+
+static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, const double* partial) {
+    SampleParams p{};
+    p.V = V; p.T = e->cfg.T; p.G = e->cfg.G; p.K = e->cfg.K; p.N = e->cfg.N; p.nsl = e->L.nsm * 4; p.nsm = e->L.nsm;
+    p.seed = e->cfg.seed; p.r0 = e->r0; p.R = e->cfg.vranks; p.marker_begin = e->marker_begin; p.Mloc = e->Mloc;
+    p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
+    p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
+    p.group = e->group_loc.p; p.cva = e->cva.p; p.cvai = e->cvai.p; p.sigmag = e->sigmag.p; p.sigmae = e->sigmae.p;
+    p.pi = e->pi.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
+    return p;
+}
+
+int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, double* out) {
+    if (!e || !local_ids || !out || n < 0) return fail(GMRM_EINVAL, "bad argument");
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    for (int i = 0; i < n; i++)
+        if (local_ids[i] < 0 || local_ids[i] >= e->Mloc) return fail(GMRM_EINVAL, "local marker %d out of range", local_ids[i]);
+    if (n == 0) return GMRM_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    const int T = e->cfg.T;
+    DevBuf<int32_t> cols; DevBuf<double> partial, res;
+    int rc = cols.alloc(n); if (rc) return rc;
+    rc = partial.alloc((size_t)n * T * e->L.nsm * 4); if (rc) return rc;
+    rc = res.alloc((size_t)n * T); if (rc) return rc;
+    CU(cudaMemcpyAsync(cols.p, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    launch_eps_offset(e->eps.p, e->namask2.p, e->L, T, nullptr, nullptr, e->spart.p, e->stream);   // refresh per-tile sums
+    rc = launch_dots(e, cols.p, n, partial.p); if (rc) return rc;
+    SampleParams sp = sample_params(e, cols.p, n, partial.p);
+    launch_finish_dots(sp, res.p, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, res.p, (size_t)n * T * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return GMRM_OK;
+}
+
+int gmrm_decode_marker(gmrm_engine* e, int32_t local_id, double* a, double* b) {
+    if (!e || local_id < 0 || local_id >= e->Mloc || (!a && !b)) return fail(GMRM_EINVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    DevBuf<double> da, db;
+    int rc = da.alloc(e->cfg.N); if (rc) return rc;
+    rc = db.alloc(e->cfg.N); if (rc) return rc;
+    launch_decode_column(e->bed.p + (size_t)local_id * e->L.col_stride, e->L, da.p, db.p, e->stream);
+    CU(cudaGetLastError());
+    if (a) CU(cudaMemcpyAsync(a, da.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
+    if (b) CU(cudaMemcpyAsync(b, db.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return GMRM_OK;
+}
+
+int gmrm_decode_namask(gmrm_engine* e, int32_t t, double* na) {
+    if (!e || !na || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    DevBuf<double> d;
+    int rc = d.alloc(e->cfg.N); if (rc) return rc;
+    // a NA-mask tile holds field 01 for observed individuals: decoded as a column, "b" is na_lut... of field != 3,
+    // and "a" is the field itself (1.0 observed, 0.0 not)
+    launch_decode_column(e->namask2.p + (size_t)t * e->L.col_stride, e->L, d.p, nullptr, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(na, d.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    return GMRM_OK;
+}
+
+int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double dbeta) {
+    if (!e || trait < 0 || trait >= e->cfg.T || local_id < 0 || local_id >= e->Mloc) return fail(GMRM_EINVAL, "bad argument");
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    CU(cudaSetDevice(e->cfg.device));
+    const int T = e->cfg.T;
+    double av, sg;
+    CU(cudaMemcpy(&av, e->mave.p + (size_t)trait * e->Mloc + local_id, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&sg, e->msig.p + (size_t)trait * e->Mloc + local_id, 8, cudaMemcpyDeviceToHost));
+    std::vector<PubEntry> pub(T, PubEntry{0.0, 0.0});
+    pub[trait].lam = dbeta * sg;                                   // phenotype.cpp:328
+    pub[trait].mave = av;
+    DevBuf<int32_t> cols; DevBuf<PubEntry> dpub;
+    int rc = cols.alloc(1); if (rc) return rc;
+    rc = dpub.alloc(T); if (rc) return rc;
+    CU(cudaMemcpyAsync(cols.p, &local_id, 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(dpub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));
+    UpdateParams up{};
+    up.bed = e->bed.p; up.col_stride = e->L.col_stride; up.cols = cols.p; up.V = 1; up.T = T; up.pub = dpub.p;
+    up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = e->L.npad; up.spart = e->spart.p; up.exact = 1;
+    if (launch_update(e->L, up, e->stream) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    return GMRM_OK;
+}
+
+// ------------------------------------------------------------------------------------- the chain
+int gmrm_init_chain(gmrm_engine* e, const double* sigmag_init) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    if (!e->groups_set) return fail(GMRM_EINVAL, "groups not set");
+    CU(cudaSetDevice(e->cfg.device));
+    const int T = e->cfg.T, G = e->cfg.G, K = e->cfg.K;
+    std::vector<int32_t> mt(G);
+    CU(cudaMemcpy(mt.data(), e->mtotgrp.p, (size_t)G * 4, cudaMemcpyDeviceToHost));
+    // sigmaG ~ Beta(1,1), zero for empty groups (bayes.cpp:326-331); Beta(1,1) == U(0,1)
+    std::vector<double> sg((size_t)T * G);
+    for (int t = 0; t < T; t++)
+        for (int g = 0; g < G; g++) {
+            double v = sigmag_init ? sigmag_init[t * G + g] : draw_uniform(e->cfg.seed, STREAM_SIGMAG0, 0, (uint32_t)g, (uint32_t)t);
+            if (mt[g] == 0) v = 0.0;
+            sg[t * G + g] = v;
+        }
+    // pi_prior (bayes.hpp:34-47)
+    std::vector<double> pi((size_t)T * G * K);
+    for (int g = 0; g < G; g++) {
+        double sum_cva = 0.0;
+        for (int j = 0; j < K - 1; j++) sum_cva += e->h_cva[g * K + j + 1];
+        for (int t = 0; t < T; t++) {
+            double* row = &pi[((size_t)t * G + g) * K];
+            row[0] = 0.5;
+            for (int j = 1; j < K; j++) row[j] = row[0] * e->h_cva[g * K + j] / sum_cva;
+        }
+    }
+    CU(cudaMemcpyAsync(e->sigmag.p, sg.data(), sg.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->pi.p, pi.data(), pi.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    if (e->betas.zero(e->stream) || e->comp.zero(e->stream) || e->mu.zero(e->stream) || e->mu_old.zero(e->stream) ||
+        e->cass.zero(e->stream) || e->m0.zero(e->stream) || e->err.zero(e->stream))
+        return GMRM_ECUDA;
+    // sigmaE start: sum eps^2 na / nonas / 2 (phenotype.cpp:448-457); eps is 0 at NA and pad slots
+    launch_eps_sumsq(e->eps.p, e->L.npad, e->L.npad, T, e->esq.p, e->stream);
+    launch_init_sigmae(e->esq.p, e->nonas.p, T, e->sigmae.p, e->stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(e->stream));
+    e->chain_ready = true;
+    return GMRM_OK;
+}
+
+static int upload_opt(DevBuf<double>& buf, const double* src, size_t n, cudaStream_t s, const double** dptr) {
+    *dptr = nullptr;
+    if (!src) return 0;
+    if (buf.n < n) { int rc = buf.alloc(n); if (rc) return rc; }
+    CU(cudaMemcpyAsync(buf.p, src, n * 8, cudaMemcpyHostToDevice, s));
+    *dptr = buf.p;
+    return 0;
+}
+
+int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (!e->chain_ready) return fail(GMRM_EINVAL, "call gmrm_init_chain first");
+    if (e->cfg.world_size > 1 && !e->comm) return fail(GMRM_EINVAL, "world_size > 1 needs gmrm_comm_init");
+    CU(cudaSetDevice(e->cfg.device));
+    const gmrm_config& c = e->cfg;
+    const Layout& L = e->L;
+    const int T = c.T, G = c.G, K = c.K, R = c.vranks, Mm = e->Mm, Vl = e->Vl;
+    cudaStream_t s = e->stream;
+    int rc;
+
+    // ---- replay variates for this iteration
+    const double *d_u = nullptr, *d_z = nullptr, *d_small = nullptr;
+    const int32_t* d_perm = nullptr;
+    const double *d_mu = nullptr, *d_sigg = nullptr, *d_piu = nullptr, *d_sige = nullptr;
+    if (rp) {
+        if ((rp->u == nullptr) != (rp->z == nullptr)) return fail(GMRM_EINVAL, "replay u and z must be given together");
+        const size_t nuz = (size_t)Mm * R * T;
+        if ((rc = upload_opt(e->rep_u, rp->u, nuz, s, &d_u))) return rc;
+        if ((rc = upload_opt(e->rep_z, rp->z, nuz, s, &d_z))) return rc;
+        if (rp->perm) {
+            if (e->rep_perm.n < (size_t)R * Mm && (rc = e->rep_perm.alloc((size_t)R * Mm))) return rc;
+            CU(cudaMemcpyAsync(e->rep_perm.p, rp->perm, (size_t)R * Mm * 4, cudaMemcpyHostToDevice, s));
+            d_perm = e->rep_perm.p;
+        }
+        const size_t nsmall = (size_t)T + (size_t)T * G + (size_t)T * G * K + T;
+        std::vector<double> small(nsmall, 0.0);
+        if (e->rep_small.n < nsmall && (rc = e->rep_small.alloc(nsmall))) return rc;
+        double* hp = small.data();
+        if (rp->mu_draw) { memcpy(hp, rp->mu_draw, T * 8); d_mu = e->rep_small.p; }
+        hp += T;
+        if (rp->sigg_unit) { memcpy(hp, rp->sigg_unit, (size_t)T * G * 8); d_sigg = e->rep_small.p + T; }
+        hp += (size_t)T * G;
+        if (rp->pi_unit) { memcpy(hp, rp->pi_unit, (size_t)T * G * K * 8); d_piu = e->rep_small.p + T + (size_t)T * G; }
+        hp += (size_t)T * G * K;
+        if (rp->sige_unit) { memcpy(hp, rp->sige_unit, T * 8); d_sige = e->rep_small.p + T + (size_t)T * G + (size_t)T * G * K; }
+        CU(cudaMemcpyAsync(e->rep_small.p, small.data(), nsmall * 8, cudaMemcpyHostToDevice, s));
+        CU(cudaStreamSynchronize(s));   // host staging vectors go out of scope
+        (void)d_small;
+    }
+
+    if (e->timing_detail && e->dot_ev.size() < (size_t)2 * Mm) {
+        const size_t old = e->dot_ev.size();
+        e->dot_ev.resize((size_t)2 * Mm);
+        for (size_t i = old; i < e->dot_ev.size(); i++) CU(cudaEventCreate(&e->dot_ev[i]));
+    }
+
+    int64_t launches = 0;
+    CU(cudaEventRecord(e->ev[0], s));
+    // ---- prologue (bayes.cpp:347-368)
+    MuDrawParams mp{};
+    mp.T = T; mp.it = it; mp.seed = c.seed; mp.sigmae = e->sigmae.p; mp.nonas = e->nonas.p; mp.mu = e->mu.p; mp.mu_old = e->mu_old.p; mp.rep_mu = d_mu;
+    launch_mu_draw(mp, s);
+    launch_eps_offset(e->eps.p, e->namask2.p, L, T, e->mu_old.p, e->mu.p, e->spart.p, s);
+    launch_steptab(e->steptab.p, Mm, Vl, e->r0, R, c.Mt, e->marker_begin, c.shuffle, c.seed, it, d_perm, s);
+    CU(cudaMemsetAsync(e->cass.p, 0, e->cass.n * 4, s));
+    CU(cudaMemsetAsync(e->npub.p, 0, 8, s));
+    launches += 3;
+
+    // ---- marker loop (bayes.cpp:375-555)
+    CU(cudaEventRecord(e->ev[1], s));
+    const bool multi = c.world_size > 1;
+    for (int st = 0; st < Mm; st++) {
+        const int32_t* cols = e->steptab.p + (size_t)st * Vl;
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[2 * st], s));
+        if ((rc = launch_dots(e, cols, Vl, e->partial.p))) return rc;
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[2 * st + 1], s));
+        SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
+        sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
+        launch_sample(sp, s);
+        UpdateParams up{};
+        up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
+        up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
+        if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
+        launches += (T + trait_chunk(L.E) - 1) / trait_chunk(L.E) + 2;
+        if (multi) return fail(GMRM_EINVAL, "multi-GPU exchange not wired yet");
+    }
+    CU(cudaEventRecord(e->ev[2], s));
+
+    // ---- epilogue (bayes.cpp:562-651)
+    launch_beta_sq(e->betas.p, e->group_loc.p, e->Mloc, T, G, e->bsq.p, s);
+    launch_eps_sumsq(e->eps.p, L.npad, c.N, T, e->esq.p, s);
+    GlobalDrawParams gp{};
+    gp.T = T; gp.G = G; gp.K = K; gp.N = c.N; gp.it = it; gp.seed = c.seed; gp.mtotgrp = e->mtotgrp.p; gp.bsq = e->bsq.p;
+    gp.cass = e->cass.p; gp.esq = e->esq.p; gp.sigmag = e->sigmag.p; gp.sigmae = e->sigmae.p; gp.pi = e->pi.p; gp.m0 = e->m0.p;
+    gp.rep_sigg_unit = d_sigg; gp.rep_pi_unit = d_piu; gp.rep_sige_unit = d_sige; gp.err = e->err.p;
+    launch_global_draw(gp, s);
+    launches += 3;
+    CU(cudaEventRecord(e->ev[3], s));
+    CU(cudaGetLastError());
+
+    int32_t herr = 0;
+    int64_t hpub = 0;
+    CU(cudaMemcpyAsync(&herr, e->err.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&hpub, e->npub.p, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    float ms_loop = 0, ms_all = 0;
+    CU(cudaEventElapsedTime(&ms_loop, e->ev[1], e->ev[2]));
+    CU(cudaEventElapsedTime(&ms_all, e->ev[0], e->ev[3]));
+    e->last.marker_loop_ms = ms_loop; e->last.iteration_ms = ms_all; e->last.launches = launches; e->last.steps = Mm; e->last.published = hpub;
+    e->last.dot_kernel_ms = 0.0;
+    if (e->timing_detail)
+        for (int st = 0; st < Mm; st++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[2 * st], e->dot_ev[2 * st + 1]));
+            e->last.dot_kernel_ms += ms;
+        }
+    if (herr != 0) {
+        CU(cudaMemset(e->err.p, 0, 4));
+        return fail(GMRM_EREPLAY, "replay variates exhausted (code %d): the chain asked for a draw the reference did not make", herr);
+    }
+    return GMRM_OK;
+}
+
+int gmrm_get_state(gmrm_engine* e, gmrm_state* o) {
+    if (!e || !o) return fail(GMRM_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t T = e->cfg.T, G = e->cfg.G, K = e->cfg.K;
+    if (o->sigmag) CU(cudaMemcpy(o->sigmag, e->sigmag.p, T * G * 8, cudaMemcpyDeviceToHost));
+    if (o->sigmae) CU(cudaMemcpy(o->sigmae, e->sigmae.p, T * 8, cudaMemcpyDeviceToHost));
+    if (o->pi) CU(cudaMemcpy(o->pi, e->pi.p, T * G * K * 8, cudaMemcpyDeviceToHost));
+    if (o->mu) CU(cudaMemcpy(o->mu, e->mu.p, T * 8, cudaMemcpyDeviceToHost));
+    if (o->m0) CU(cudaMemcpy(o->m0, e->m0.p, T * G * 4, cudaMemcpyDeviceToHost));
+    if (o->cass) CU(cudaMemcpy(o->cass, e->cass.p, T * G * K * 4, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+
+int gmrm_get_betas(gmrm_engine* e, int32_t t, double* betas) {
+    if (!e || !betas || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpy(betas, e->betas.p + (size_t)t * e->Mloc, (size_t)e->Mloc * 8, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+int gmrm_get_components(gmrm_engine* e, int32_t t, int32_t* comp) {
+    if (!e || !comp || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpy(comp, e->comp.p + (size_t)t * e->Mloc, (size_t)e->Mloc * 4, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+int gmrm_get_epsilon(gmrm_engine* e, int32_t t, double* eps) {
+    if (!e || !eps || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaMemcpy(eps, e->eps.p + (size_t)t * e->L.npad, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out) {
+    if (!e || !out) return fail(GMRM_EINVAL, "null argument");
+    *out = e->last;
+    return GMRM_OK;
+}
+int gmrm_set_timing_detail(gmrm_engine* e, int32_t on) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    e->timing_detail = on != 0;
+    return GMRM_OK;
+}
+
+// ------------------------------------------------------------------------------------ multi-GPU
+int gmrm_comm_unique_id(uint8_t id[128]) {
+    if (!id) return fail(GMRM_EINVAL, "null argument");
+    if (!g_nccl.load()) return fail(GMRM_ENCCL, "libnccl.so.2 not found: %s", dlerror());
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return GMRM_OK;
+}
+int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
+    if (!e || !id) return fail(GMRM_EINVAL, "null argument");
+    if (!g_nccl.load()) return fail(GMRM_ENCCL, "libnccl.so.2 not found: %s", dlerror());
+    CU(cudaSetDevice(e->cfg.device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NC(g_nccl.CommInitRank(&e->comm, e->cfg.world_size, u, e->cfg.world_rank));
+    return GMRM_OK;
+}
+
+}  // extern "C"

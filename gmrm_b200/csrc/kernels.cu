@@ -1,0 +1,843 @@
+// sm_100a kernels of the Gibbs marker loop (see kernels.cuh, layout.h).
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace gmrm {
+
+// =====================================================================================
+// small device helpers
+// =====================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// Replace the LOW word of a 64-bit register pair, keeping the high word where it is.  With the
+// high word 0 the pair reads as the denormal double x * 2^-1074.  Writing it this way (and not as
+// a fresh {x, 0} pack) is what lets ptxas keep one persistent zero register per multiplier, so
+// that a genotype costs exactly one shift + one DFMA (checked with cuobjdump).
+__device__ __forceinline__ void set_lo(double& D, uint32_t x) {
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 %0, {%1, hi};\n\t}" : "+d"(D) : "r"(x));
+}
+
+__device__ __forceinline__ double warp_sum_fixed(double v) {   // fixed xor tree: reproducible
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, fixed order; result valid in thread 0.  `red` holds >= blockDim/32 doubles.
+__device__ __forceinline__ double block_sum_fixed(double v, double* red) {
+    v = warp_sum_fixed(v);
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+__device__ __forceinline__ void tile_offset_to_slot_byte(int E4, int off, int& ls, int& b) {
+    const int nw = E4 / 4, wbytes = nw * kLanesPerTile * 4;
+    if (off < wbytes) {
+        const int wi = off / (kLanesPerTile * 4), rem = off % (kLanesPerTile * 4);
+        ls = rem / 4; b = wi * 4 + rem % 4;
+        return;
+    }
+    off -= wbytes;
+    int bb = 4 * nw;
+    if (E4 & 2) {
+        if (off < kLanesPerTile * 2) { ls = off / 2; b = bb + off % 2; return; }
+        off -= kLanesPerTile * 2;
+        bb += 2;
+    }
+    ls = off; b = bb;
+}
+
+// The groups (registers) of one lane-slot of one tile.
+template <int E4>
+struct SlotRegs {
+    static constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
+    uint32_t w[NW > 0 ? NW : 1];
+    uint32_t h, b;
+    __device__ __forceinline__ void load(const uint8_t* tile, int ls) {   // generic / shared / global pointer
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = *reinterpret_cast<const uint32_t*>(tile + i * kLanesPerTile * 4 + ls * 4);
+        h = 0; b = 0;
+        if (NH) h = *reinterpret_cast<const uint16_t*>(tile + NW * kLanesPerTile * 4 + ls * 2);
+        if (NB) b = *(tile + NW * kLanesPerTile * 4 + NH * kLanesPerTile * 2 + ls);
+    }
+    // 2-bit field of individual k of the slot
+    __device__ __forceinline__ uint32_t field(int k) const {
+        if (k < 16 * NW) return (w[k / 16] >> (2 * (k % 16))) & 3u;
+        k -= 16 * NW;
+        if (NH) { if (k < 8) return (h >> (2 * k)) & 3u; k -= 8; }
+        return (b >> (2 * k)) & 3u;
+    }
+};
+
+// =====================================================================================
+// .bed ingestion: transcode PLINK bytes <-> tile-planar dosage bytes (bit-exact, invertible)
+// =====================================================================================
+__global__ void transcode_kernel(const uint8_t* __restrict__ src, int nmark, Layout L, uint8_t* __restrict__ dst) {
+    const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (o >= L.col_stride || j >= nmark) return;
+    const int c = (int)(o / L.tile_bytes), off = (int)(o % L.tile_bytes);
+    int ls, b;
+    tile_offset_to_slot_byte(L.E4, off, ls, b);
+    const int64_t idx = ((int64_t)c * kLanesPerTile + ls) * L.E4 + b;
+    uint8_t v = 0;
+    if (idx < L.mbytes) v = plink_to_dosage(src[(int64_t)j * L.mbytes + idx]);
+    dst[(int64_t)j * L.col_stride + o] = v;
+}
+
+__global__ void untranscode_kernel(const uint8_t* __restrict__ tiles, int nmark, Layout L, uint8_t* __restrict__ dst) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (idx >= L.mbytes || j >= nmark) return;
+    const int64_t s = idx / L.E4;
+    const int b = (int)(idx % L.E4), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
+    const uint8_t y = tiles[(int64_t)j * L.col_stride + (int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, b)];
+    dst[(int64_t)j * L.mbytes + idx] = dosage_to_plink(y);
+}
+
+// Synthetic PLINK bytes: per-marker MAF ~ U(lo, hi), dosage ~ Binomial(2, p).
+__global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int first_marker, Layout L, uint32_t seed,
+                                      double maf_lo, double maf_hi, double missing_rate) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y;
+    if (idx >= L.mbytes || j >= nmark) return;
+    const uint32_t mg = (uint32_t)(first_marker + j);
+    const U4 pm = philox4x32(seed, 0x47454e30u, mg, 0, 0, 0);
+    const double p = maf_lo + (maf_hi - maf_lo) * u01(pm.x, pm.y);
+    const uint32_t thr = (uint32_t)(p * 65536.0);
+    const uint32_t mthr = (uint32_t)(missing_rate * 4294967296.0 > 4294967295.0 ? 4294967295.0 : missing_rate * 4294967296.0);
+    const U4 r = philox4x32(seed, 0x47454e31u, mg, (uint32_t)idx, 0, 0);
+    U4 rm = {~0u, ~0u, ~0u, ~0u};
+    if (missing_rate > 0.0) rm = philox4x32(seed, 0x47454e32u, mg, (uint32_t)idx, 0, 0);
+    const uint32_t rw[4] = {r.x, r.y, r.z, r.w}, mw[4] = {rm.x, rm.y, rm.z, rm.w};
+    uint8_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t i = idx * 4 + k;
+        uint32_t code = 0;   // PLINK pads with 00
+        if (i < L.N) {
+            const int d = ((rw[k] & 0xffffu) < thr) + ((rw[k] >> 16) < thr);
+            code = d == 2 ? 0u : d == 1 ? 2u : 3u;          // 00 = dosage 2, 10 = 1, 11 = 0
+            if (missing_rate > 0.0 && mw[k] < mthr) code = 1u;   // 01 = missing
+        }
+        byte |= (uint8_t)(code << (2 * k));
+    }
+    dst[(int64_t)j * L.mbytes + idx] = byte;
+}
+
+// Missing-genotype lists (CSR over shard-local markers), ascending individual index.
+// One warp per marker walks the column in PLINK byte order.
+__device__ __forceinline__ uint32_t missing_fields(const uint8_t* col, const Layout& L, int64_t idx) {
+    const int64_t s = idx / L.E4;
+    const int b = (int)(idx % L.E4), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
+    const uint32_t y = col[(int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, b)];
+    uint32_t m = y & (y >> 1) & 0x55u;            // field == 3
+    const int64_t i0 = idx * 4;
+    if (i0 + 3 >= L.N) {                          // drop pad individuals of the last byte
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (i0 + k >= L.N) m &= ~(1u << (2 * k));
+    }
+    return m;
+}
+
+__global__ void count_missing_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L, uint32_t* __restrict__ counts) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nmark) return;
+    const uint8_t* col = bed + (int64_t)j * L.col_stride;
+    uint32_t n = 0;
+    for (int64_t idx = lane; idx < L.mbytes; idx += 32) n += __popc(missing_fields(col, L, idx));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if (lane == 0) counts[j] = n;
+}
+
+__global__ void fill_missing_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L, const uint32_t* __restrict__ off,
+                                    uint32_t* __restrict__ out) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nmark) return;
+    const uint8_t* col = bed + (int64_t)j * L.col_stride;
+    uint32_t base = off[j];
+    for (int64_t idx0 = 0; idx0 < L.mbytes; idx0 += 32) {
+        const int64_t idx = idx0 + lane;
+        const uint32_t m = idx < L.mbytes ? missing_fields(col, L, idx) : 0u;
+        const uint32_t n = __popc(m);
+        uint32_t incl = n;                        // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t w = base + incl - n;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (m & (1u << (2 * k))) out[w++] = (uint32_t)(idx * 4 + k);
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// test hooks: the reference's table values of one column / one NA mask, individual by individual
+__global__ void decode_column_kernel(const uint8_t* __restrict__ col, Layout L, double* __restrict__ a, double* __restrict__ b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.N) return;
+    const int64_t s = i / L.E;
+    const int k = (int)(i % L.E), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
+    const uint32_t y = col[(int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, k / 4)];
+    const uint32_t d = (y >> (2 * (k % 4))) & 3u;        // 0,1,2 = dosage, 3 = missing
+    if (a) a[i] = d == 3 ? 0.0 : (double)d;              // dotp_lut_a
+    if (b) b[i] = d == 3 ? 0.0 : 1.0;                    // dotp_lut_b (for a NA mask tile: na_lut)
+}
+
+// =====================================================================================
+// marker statistics, PhenMgr::compute_markers_statistics (phenotype.cpp:466-556), from integer
+// counts of each dosage under the trait's NA mask: the sums of the
+// reference's loops are sums of small integers, hence these counts exactly.
+// =====================================================================================
+constexpr int kStatsMaxT = 32;
+__global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
+                                                    const uint8_t* __restrict__ namask2, const int32_t* __restrict__ nonas,
+                                                    int T, double* __restrict__ mave, double* __restrict__ msig) {
+    const int j = blockIdx.x;
+    if (j >= nmark) return;
+    const uint32_t* col = reinterpret_cast<const uint32_t*>(bed + (int64_t)j * L.col_stride);
+    const int nwords = (int)(L.col_stride / 4);
+    __shared__ int red[3][4];
+    for (int t = 0; t < T; t++) {
+        const uint32_t* nm = reinterpret_cast<const uint32_t*>(namask2 + (int64_t)t * L.col_stride);
+        int n0 = 0, n1 = 0, n2 = 0;
+        for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
+            const uint32_t w = col[i], m = nm[i];
+            const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+            n1 += __popc(lo & ~hi & m);
+            n2 += __popc(hi & ~lo & m);
+            n0 += __popc(~(lo | hi) & 0x55555555u & m);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+            n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+            n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = n0; red[1][threadIdx.x >> 5] = n1; red[2][threadIdx.x >> 5] = n2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double c0 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+            const double c1 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+            const double c2 = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+            const double suma = c1 + 2.0 * c2, sumb = c0 + c1 + c2;       // phenotype.cpp:536-537
+            const double av = suma / sumb;                                // 540
+            const double sumsqr = c0 * (0.0 - av) * (0.0 - av) + c1 * (1.0 - av) * (1.0 - av) + c2 * (2.0 - av) * (2.0 - av);  // 544-545
+            mave[(int64_t)t * nmark + j] = av;
+            msig[(int64_t)t * nmark + j] = 1.0 / sqrt(sumsqr / ((double)nonas[t] - 1.0));   // 548
+        }
+    }
+}
+
+// =====================================================================================
+// residual helpers
+// =====================================================================================
+// Phenotype::offset_epsilon twice (bayes.cpp:351,359): eps += mu_old*na; eps -= mu_new*na; and the
+// per-tile sum of eps that the sampler turns into sum b*eps.
+template <int E4>
+__global__ void __launch_bounds__(kLanesPerTile) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ namask2,
+                                                                  Layout L, const double* __restrict__ mu_old,
+                                                                  const double* __restrict__ mu_new, double* __restrict__ spart) {
+    constexpr int E = 4 * E4;
+    const int t = blockIdx.y, ls = threadIdx.x;
+    __shared__ double red[kLanesPerTile / 32];
+    SlotRegs<E4> na;
+    na.load(namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
+    double* e = eps + (int64_t)t * L.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
+    const double a = mu_old ? mu_old[t] : 0.0, b = mu_new ? -mu_new[t] : 0.0;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        double v = e[k];
+        const double m = na.field(k) ? 1.0 : 0.0;
+        v += a * m;            // phenotype.cpp:408
+        v += b * m;
+        e[k] = v;
+        s += v;
+    }
+    const double tot = block_sum_fixed(s, red);
+    if (threadIdx.x == 0) spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
+}
+
+// sum_{i<n} eps_i^2 per trait (Phenotype::epsilon_sumsqr, phenotype.cpp:251-261)
+__global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restrict__ eps, int64_t npad, int64_t n, double* __restrict__ out) {
+    __shared__ double red[32];
+    const double* e = eps + (int64_t)blockIdx.x * npad;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += e[i] * e[i];
+    const double tot = block_sum_fixed(s, red);
+    if (threadIdx.x == 0) out[blockIdx.x] = tot;
+}
+
+// =====================================================================================
+// K1: streamed decode-and-reduce of the step's V columns against the residuals.
+//
+// One CTA per tile (SM).  Warp 4*kWPS is the producer: one lane issues one cp.async.bulk per
+// (marker, tile) into an 8-stage shared-memory ring, completion on mbarriers.  The other 4*kWPS
+// warps are consumers: warp w serves sub-partition w&3 and takes every kWPS-th batch of 8 markers.
+// A consumer lane owns E consecutive individuals: their weights w_k stay in registers for the whole
+// launch, a marker costs E x (shift + DFMA) per lane (layout.h), then an 8-marker select-free
+// transposed butterfly leaves one per-warp partial per marker, written to partial[r][t][tile*4+sp].
+// =====================================================================================
+template <int E4, int T>
+__global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) {
+    constexpr int TILE = kLanesPerTile * E4;
+    constexpr int E = 4 * E4;
+    constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kBatch * TILE);
+    uint64_t* empty = full + kStages;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = (p.V + kBatch - 1) / kBatch;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 4 * kWPS) {
+        // ---------------- producer ----------------
+        if (lane == 0) {
+            const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * TILE;
+            for (int b = 0; b < nb; b++) {
+                const int s = b % kStages;
+                if (b >= kStages) mbar_wait(&empty[s], (uint32_t)((b / kStages) - 1) & 1u);
+                int cols[kBatch], nvalid = 0;
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    const int r = b * kBatch + j;
+                    cols[j] = r < p.V ? p.cols[r] : -1;
+                    nvalid += cols[j] >= 0;
+                }
+                mbar_expect_tx(&full[s], (uint32_t)(nvalid * TILE));
+#pragma unroll
+                for (int j = 0; j < kBatch; j++)
+                    if (cols[j] >= 0)
+                        bulk_g2s(ring + (s * kBatch + j) * TILE, tile0 + (int64_t)cols[j] * p.col_stride, TILE, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int sp = warp & 3, q = warp >> 2;
+    const int ls = sp * 32 + lane;
+    const int64_t slot = (int64_t)blockIdx.x * kLanesPerTile + ls;
+
+    // weights of this lane's E individuals, group by group (layout.h: w_k = 2^1000 (eps_k - eps_{k+1}/4))
+    double wgt[E][T];
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + slot * E;
+        double ev[E + 1];
+#pragma unroll
+        for (int k = 0; k < E; k++) ev[k] = e[k];
+        ev[E] = 0.0;
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            // last genotype of a group has no successor inside the group
+            const bool last = (k < 16 * NW) ? ((k % 16) == 15) : (NH && k < 16 * NW + 8) ? (k == 16 * NW + 7) : (k == E - 1);
+            wgt[k][t] = group_weight(ev[k], last ? 0.0 : ev[k + 1]);
+        }
+    }
+
+    // accumulator slot j of this lane holds marker j ^ P: makes the butterfly below select-free
+    const int P = (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1);
+    double D[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; j++) D[j] = p.zeros[j * kDotThreads + threadIdx.x];
+
+    for (int b = q; b < nb; b += kWPS) {
+        const int s = b % kStages;
+        mbar_wait(&full[s], (uint32_t)(b / kStages) & 1u);
+        const uint8_t* st = ring + s * kBatch * TILE;
+        SlotRegs<E4> g[kBatch];
+#pragma unroll
+        for (int j = 0; j < kBatch; j++) g[j].load(st + (j ^ P) * TILE, ls);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);     // registers hold the batch: the stage can be refilled
+
+        double acc[kBatch][T];
+#pragma unroll
+        for (int j = 0; j < kBatch; j++)
+#pragma unroll
+            for (int t = 0; t < T; t++) acc[j][t] = 0.0;
+
+#pragma unroll
+        for (int wi = 0; wi < NW; wi++)
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    set_lo(D[j], g[j].w[wi] << (30 - 2 * k));
+#pragma unroll
+                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[wi * 16 + k][t], acc[j][t]);
+                }
+        if (NH) {
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    set_lo(D[j], g[j].h << (30 - 2 * k));
+#pragma unroll
+                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + k][t], acc[j][t]);
+                }
+        }
+        if (NB) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int j = 0; j < kBatch; j++) {
+                    set_lo(D[j], g[j].b << (30 - 2 * k));
+#pragma unroll
+                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + 8 * NH + k][t], acc[j][t]);
+                }
+        }
+
+        // transposed butterfly: 8 markers x 32 lanes -> marker (P) total in every lane of a quad
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            double a4[4], a2[2], a1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) a4[j] = acc[j][t] + __shfl_xor_sync(0xffffffffu, acc[j + 4][t], 16);
+#pragma unroll
+            for (int j = 0; j < 2; j++) a2[j] = a4[j] + __shfl_xor_sync(0xffffffffu, a4[j + 2], 8);
+            a1 = a2[0] + __shfl_xor_sync(0xffffffffu, a2[1], 4);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            const int r = b * kBatch + P;
+            if ((lane & 3) == 0 && r < p.V)
+                p.partial[((int64_t)r * p.Ttot + p.t0 + t) * p.nsl + blockIdx.x * 4 + sp] = a1 * kDotUnscale;
+        }
+    }
+}
+
+// =====================================================================================
+// K2: one warp per virtual rank: finish the dot product, sample, publish.
+// =====================================================================================
+struct DotPieces { double dpa, dpb; };
+
+// sum a*eps and sum b*eps of trait t for the marker of virtual rank r (all lanes get the result)
+__device__ __forceinline__ DotPieces finish_dot(const SampleParams& p, int r, int col, int t, int lane) {
+    const double* part = p.partial + ((int64_t)r * p.T + t) * p.nsl;
+    double s = 0.0;
+    for (int i = lane; i < p.nsl; i += 32) s += part[i];
+    const double coded = warp_sum_fixed(s);                 // sum d*eps with missing coded 3
+    double sa = 0.0;
+    for (int i = lane; i < p.nsm; i += 32) sa += p.spart[(int64_t)t * p.nsm + i];
+    const double sall = warp_sum_fixed(sa);                 // sum eps over all slots
+    double sm = 0.0;
+    const uint32_t m0 = p.miss_off[col], m1 = p.miss_off[col + 1];
+    for (uint32_t i = m0 + lane; i < m1; i += 32) sm += p.eps[(int64_t)t * p.npad + p.miss_idx[i]];
+    const double smiss = m1 > m0 ? warp_sum_fixed(sm) : 0.0;
+    DotPieces d;
+    d.dpa = coded - 3.0 * smiss;     // a = 0 at missing (lut_a)
+    d.dpb = sall - smiss;            // b = 0 at missing (lut_b)
+    return d;
+}
+
+__global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v >= p.V) return;
+    const int col = p.cols[v];
+    if (col < 0) {
+        if (lane < p.T) { p.pub[(int64_t)v * p.T + lane].lam = 0.0; p.pub[(int64_t)v * p.T + lane].mave = 0.0; }
+        return;
+    }
+    double my_dpa = 0.0, my_dpb = 0.0;
+    for (int t = 0; t < p.T; t++) {
+        const DotPieces d = finish_dot(p, v, col, t, lane);
+        if (lane == t) { my_dpa = d.dpa; my_dpb = d.dpb; }
+    }
+    if (lane >= p.T) return;
+    const int t = lane;
+    const int grp = p.group[col];
+    const int64_t mi = (int64_t)t * p.Mloc + col;
+    const double mave = p.mave[mi], msig = p.msig[mi];
+    const double dot_raw = msig * (my_dpa - mave * my_dpb);                // bayes.cpp:766
+    const uint32_t mglo = (uint32_t)(p.marker_begin + col);
+    double u, z = 0.0;
+    const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + t;
+    const double sigg = p.sigmag[t * p.G + grp];
+    if (p.rep_u) {
+        u = p.rep_u[ri];
+        z = p.rep_z[ri];
+        if (sigg != 0.0 && !(u == u)) atomicExch(p.err, 1);               // reference drew nothing here
+    } else {
+        u = draw_uniform(p.seed, STREAM_SAMPLER_U, (uint32_t)p.it, mglo, (uint32_t)t);
+        z = draw_normal(p.seed, STREAM_SAMPLER_N, (uint32_t)p.it, mglo, (uint32_t)t);
+    }
+    const MarkerDraw d = sample_marker(dot_raw, p.betas[mi], p.sigmae[t], sigg, p.cva + grp * p.K, p.cvai + grp * p.K,
+                                       p.pi + ((int64_t)t * p.G + grp) * p.K, p.K, p.N, p.nonas[t], u, z);
+    if (p.rep_u && d.need_z && !(z == z)) atomicExch(p.err, 2);
+    p.betas[mi] = d.beta_new;
+    if (d.comp >= 0) {
+        p.comp[mi] = d.comp;                                               // bayes.cpp:462
+        atomicAdd(&p.cass[(t * p.G + grp) * p.K + d.comp], 1);              // 460
+    }
+    PubEntry e;
+    e.lam = fabs(d.dbeta) > 0.0 ? d.dbeta * msig : 0.0;                    // 483-487, phenotype.cpp:328
+    e.mave = mave;
+    p.pub[(int64_t)v * p.T + t] = e;
+    if (e.lam != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), 1ull);
+}
+
+// test hook behind gmrm_dot_products: out[v*T+t] = Bayes::dot_product
+__global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, double* __restrict__ out) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v >= p.V) return;
+    const int col = p.cols[v];
+    for (int t = 0; t < p.T; t++) {
+        const DotPieces d = finish_dot(p, v, col, t, lane);
+        const int64_t mi = (int64_t)t * p.Mloc + col;
+        if (lane == 0) out[(int64_t)v * p.T + t] = p.msig[mi] * (d.dpa - p.mave[mi] * d.dpb);
+    }
+}
+
+// =====================================================================================
+// K3: apply the step's published updates to the residuals, rank order, per individual.
+// Phenotype::update_epsilon, phenotype.cpp:326-329,375-390:  eps += (a - mave*b) * (dbeta*msig) * na
+// One thread per lane-slot (same mapping as K1); blockIdx.y = trait.
+// =====================================================================================
+template <int E4>
+__global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateParams p, Layout L) {
+    constexpr int E = 4 * E4;
+    extern __shared__ int32_t plist[];               // published virtual ranks of this trait, ascending
+    __shared__ int npub;
+    __shared__ double red[kUpdThreads / 32];
+    const int t = blockIdx.y, ls = threadIdx.x, lane = threadIdx.x & 31;
+
+    if (threadIdx.x < 32) {                          // ordered compaction by warp 0
+        int n = 0;
+        for (int v0 = 0; v0 < p.V; v0 += 32) {
+            const int v = v0 + lane;
+            const bool on = v < p.V && p.pub[(int64_t)v * p.T + t].lam != 0.0;
+            const uint32_t m = __ballot_sync(0xffffffffu, on);
+            if (on) plist[n + __popc(m & ((1u << lane) - 1u))] = v;
+            n += __popc(m);
+        }
+        if (lane == 0) npub = n;
+    }
+    __syncthreads();
+    const int n = npub;
+
+    SlotRegs<E4> na;
+    na.load(p.namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
+    double* ep = p.eps + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
+    double e[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) e[k] = ep[k];
+
+    const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * L.tile_bytes;
+    SlotRegs<E4> g, gnext;
+    if (n > 0) gnext.load(tile0 + (int64_t)p.cols[plist[0]] * p.col_stride, ls);
+    for (int i = 0; i < n; i++) {
+        g = gnext;
+        const int v = plist[i];
+        if (i + 1 < n) gnext.load(tile0 + (int64_t)p.cols[plist[i + 1]] * p.col_stride, ls);   // prefetch
+        const PubEntry pe = p.pub[(int64_t)v * p.T + t];
+        // reference arithmetic: (mdb*b + a) * bs_ * m  with mdb = -mave, bs_ = dbeta*msig
+        const double mdb = -pe.mave;
+        const double v0 = (mdb * 1.0 + 0.0) * pe.lam, v1 = (mdb * 1.0 + 1.0) * pe.lam, v2 = (mdb * 1.0 + 2.0) * pe.lam;
+#pragma unroll
+        for (int k = 0; k < E; k++) {
+            const uint32_t c = g.field(k);
+            double val = c == 0 ? v0 : c == 1 ? v1 : c == 2 ? v2 : 0.0;
+            if (!na.field(k)) val = 0.0;
+            e[k] += val;
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; k++) { ep[k] = e[k]; s += e[k]; }
+    const double tot = block_sum_fixed(s, red);
+    if (threadIdx.x == 0) p.spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
+}
+
+// =====================================================================================
+// per-iteration prologue / epilogue
+// =====================================================================================
+// marker of (step s, local virtual rank v): Bayes::set_block_of_markers (bayes.cpp:903-925) + midx
+__global__ void steptab_kernel(int32_t* __restrict__ tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin,
+                               int shuffle, uint32_t seed, int it, const int32_t* __restrict__ rep_perm) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)Mm * Vl) return;
+    const int s = (int)(i / Vl), v = (int)(i % Vl), r = r0 + v;
+    const int size = Mt / R, modu = Mt % R;
+    const int Mr = size + (r < modu ? 1 : 0);
+    const int Sr = r * size + (r < modu ? r : modu);
+    int out = -1;
+    if (s < Mr) {
+        int loc = s;
+        if (shuffle) loc = rep_perm ? rep_perm[(int64_t)r * Mm + s] : (int)perm_at((uint32_t)s, (uint32_t)Mr, seed, (uint32_t)it, (uint32_t)r);
+        out = Sr - marker_begin + loc;
+    }
+    tab[i] = out;
+}
+
+// sum of beta^2 per group over the shard (bayes.cpp:566-569); block = trait, fixed order
+__global__ void __launch_bounds__(256) beta_sq_kernel(const double* __restrict__ betas, const int32_t* __restrict__ group,
+                                                      int Mloc, int G, double* __restrict__ out) {
+    extern __shared__ double acc[];                  // [G][256]
+    const int t = blockIdx.x, tid = threadIdx.x;
+    for (int g = 0; g < G; g++) acc[g * 256 + tid] = 0.0;
+    const int chunk = (Mloc + 255) / 256;
+    const int j0 = tid * chunk, j1 = min(Mloc, j0 + chunk);
+    for (int j = j0; j < j1; j++) {
+        const double b = betas[(int64_t)t * Mloc + j];
+        acc[group[j] * 256 + tid] += b * b;
+    }
+    __syncthreads();
+    for (int g = 0; g < G; g++) {
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) acc[g * 256 + tid] += acc[g * 256 + tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) out[t * G + g] = acc[g * 256];
+    }
+}
+
+// sigmaE start value, Phenotype::update_epsilon_sigma (phenotype.cpp:448-457)
+__global__ void init_sigmae_kernel(const double* esq, const int32_t* nonas, int T, double* sigmae) {
+    const int t = threadIdx.x;
+    if (t < T) sigmae[t] = esq[t] / (double)nonas[t] * 0.5;
+}
+
+// new intercept (bayes.cpp:357, phenotype.cpp:279-282: mean epssum/nonas with epssum == 0)
+__global__ void mu_draw_kernel(const MuDrawParams p) {
+    const int t = threadIdx.x;
+    if (t >= p.T) return;
+    p.mu_old[t] = p.mu[t];
+    double m;
+    if (p.rep_mu) m = p.rep_mu[t];
+    else m = 0.0 / (double)p.nonas[t] + sqrt(p.sigmae[t] / (double)p.nonas[t]) * draw_normal(p.seed, STREAM_MU, (uint32_t)p.it, 0u, (uint32_t)t);
+    p.mu[t] = m;
+}
+
+// group variances, mixture proportions, residual variance (bayes.cpp:594-650); thread = trait
+__global__ void global_draw_kernel(const GlobalDrawParams p) {
+    const int t = threadIdx.x;
+    if (t >= p.T) return;
+    const double V0E = 0.0001, S02E = 0.0001, V0G = 0.0001, S02G = 0.0001;   // bayes.hpp:14-17
+    for (int g = 0; g < p.G; g++) {
+        p.m0[t * p.G + g] = 0;                                                // reset_m0, bayes.cpp:366
+        if (p.mtotgrp[g] == 0) continue;                                      // 597-598
+        const int32_t* cs = p.cass + (t * p.G + g) * p.K;
+        const int m0 = p.mtotgrp[g] - cs[0];                                  // 605
+        p.m0[t * p.G + g] = m0;
+        int csum = 0;
+        for (int k = 0; k < p.K; k++) csum += cs[k];
+        if (m0 == 0 || csum == 0) { p.sigmag[t * p.G + g] = 0.0; continue; }  // 608-611
+        const double a = V0G + (double)m0;
+        const double b = (p.bsq[t * p.G + g] * (double)m0 + V0G * S02G) / (V0G + (double)m0);   // 613
+        double unit;
+        if (p.rep_sigg_unit) { unit = p.rep_sigg_unit[t * p.G + g]; if (!(unit == unit)) atomicExch(p.err, 3); }
+        else unit = draw_gamma(0.5 * a, p.seed, STREAM_SIGMAG, (uint32_t)p.it, (uint32_t)g, (uint32_t)t);
+        p.sigmag[t * p.G + g] = inv_scaled_chisq_from_unit(a, b, unit);
+        double* pi = p.pi + ((int64_t)t * p.G + g) * p.K;                     // phenotype.cpp:227-237
+        double sum = 0.0;
+        for (int k = 0; k < p.K; k++) {
+            double val;
+            if (p.rep_pi_unit) { val = p.rep_pi_unit[(t * p.G + g) * p.K + k]; if (!(val == val)) atomicExch(p.err, 4); }
+            else val = draw_gamma((double)cs[k] + 1.0, p.seed, STREAM_PI, (uint32_t)p.it, (uint32_t)(g * p.K + k), (uint32_t)t);
+            pi[k] = val;
+            sum += val;
+        }
+        for (int k = 0; k < p.K; k++) pi[k] /= sum;
+    }
+    const double a = V0E + (double)p.N, b = (p.esq[t] + V0E * S02E) / (V0E + (double)p.N);   // 635
+    double unit;
+    if (p.rep_sige_unit) unit = p.rep_sige_unit[t];
+    else unit = draw_gamma(0.5 * a, p.seed, STREAM_SIGMAE, (uint32_t)p.it, 0u, (uint32_t)t);
+    p.sigmae[t] = inv_scaled_chisq_from_unit(a, b, unit);
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+void launch_transcode(const uint8_t* src, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s) {
+    if (nmark <= 0) return;
+    dim3 grid((unsigned)((L.col_stride + 255) / 256), (unsigned)nmark);
+    transcode_kernel<<<grid, 256, 0, s>>>(src, nmark, L, dst);
+}
+void launch_decode_column(const uint8_t* col, const Layout& L, double* a, double* b, cudaStream_t s) {
+    decode_column_kernel<<<(unsigned)((L.N + 255) / 256), 256, 0, s>>>(col, L, a, b);
+}
+void launch_untranscode(const uint8_t* tiles, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s) {
+    if (nmark <= 0) return;
+    dim3 grid((unsigned)((L.mbytes + 255) / 256), (unsigned)nmark);
+    untranscode_kernel<<<grid, 256, 0, s>>>(tiles, nmark, L, dst);
+}
+void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, const Layout& L, uint32_t seed, double maf_lo,
+                           double maf_hi, double missing_rate, cudaStream_t s) {
+    if (nmark <= 0) return;
+    dim3 grid((unsigned)((L.mbytes + 255) / 256), (unsigned)nmark);
+    generate_plink_kernel<<<grid, 256, 0, s>>>(dst, nmark, first_global_marker, L, seed, maf_lo, maf_hi, missing_rate);
+}
+void launch_count_missing(const uint8_t* bed, int nmark, const Layout& L, uint32_t* counts, cudaStream_t s) {
+    if (nmark <= 0) return;
+    count_missing_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(bed, nmark, L, counts);
+}
+void launch_fill_missing(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s) {
+    if (nmark <= 0) return;
+    fill_missing_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(bed, nmark, L, off, idx);
+}
+void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* namask2, const int32_t* nonas, int T,
+                  double* mave, double* msig, cudaStream_t s) {
+    if (nmark <= 0) return;
+    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, namask2, nonas, T, mave, msig);
+}
+
+template <int E4>
+static void eps_offset_t(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
+                         const double* mu_new, double* spart, cudaStream_t s) {
+    dim3 grid((unsigned)L.nsm, (unsigned)T);
+    eps_offset_kernel<E4><<<grid, kLanesPerTile, 0, s>>>(eps, namask2, L, mu_old, mu_new, spart);
+}
+#define GMRM_DISPATCH_E4(E4v, CALL)                 \
+    switch (E4v) {                                  \
+    case 1: { constexpr int E4 = 1; CALL; } break;  \
+    case 2: { constexpr int E4 = 2; CALL; } break;  \
+    case 3: { constexpr int E4 = 3; CALL; } break;  \
+    case 4: { constexpr int E4 = 4; CALL; } break;  \
+    case 5: { constexpr int E4 = 5; CALL; } break;  \
+    case 6: { constexpr int E4 = 6; CALL; } break;  \
+    case 7: { constexpr int E4 = 7; CALL; } break;  \
+    case 8: { constexpr int E4 = 8; CALL; } break;  \
+    default: break;                                 \
+    }
+
+void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
+                       const double* mu_new, double* spart, cudaStream_t s) {
+    GMRM_DISPATCH_E4(L.E4, (eps_offset_t<E4>(eps, namask2, L, T, mu_old, mu_new, spart, s)));
+}
+void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
+    eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);
+}
+
+template <int E4, int T>
+static int dot_launch_t(const DotParams& p, int nsm, cudaStream_t s) {
+    constexpr int smem = kStages * kBatch * kLanesPerTile * E4 + 2 * kStages * (int)sizeof(uint64_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(dot_kernel<E4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        attr_set = true;
+    }
+    dot_kernel<E4, T><<<nsm, kDotThreads, smem, s>>>(p);
+    return 0;
+}
+template <int E4>
+static int dot_launch_e(int T, const DotParams& p, int nsm, cudaStream_t s) {
+    switch (T) {
+    case 1: return dot_launch_t<E4, 1>(p, nsm, s);
+    case 2: return dot_launch_t<E4, 2>(p, nsm, s);
+    case 3: return dot_launch_t<E4, 3>(p, nsm, s);
+    case 4: return dot_launch_t<E4, 4>(p, nsm, s);
+    }
+    return -1;
+}
+// T in 1..4 per launch (the engine chunks more traits)
+int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s) {
+    int rc = -1;
+    GMRM_DISPATCH_E4(L.E4, (rc = dot_launch_e<E4>(T, p, L.nsm, s)));
+    return rc;
+}
+
+void launch_sample(const SampleParams& p, cudaStream_t s) {
+    if (p.V <= 0) return;
+    sample_kernel<<<(p.V + 3) / 4, 128, 0, s>>>(p);
+}
+void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
+    if (p.V <= 0) return;
+    finish_dots_kernel<<<(p.V + 3) / 4, 128, 0, s>>>(p, out);
+}
+
+template <int E4>
+static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t s) {
+    const int smem = p.V * (int)sizeof(int32_t);
+    static int attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        if (cudaFuncSetAttribute(update_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        attr = smem;
+    }
+    dim3 grid((unsigned)L.nsm, (unsigned)p.T);
+    update_kernel<E4><<<grid, kUpdThreads, smem, s>>>(p, L);
+    return 0;
+}
+int launch_update(const Layout& L, const UpdateParams& p, cudaStream_t s) {
+    int rc = -1;
+    GMRM_DISPATCH_E4(L.E4, (rc = update_launch_t<E4>(p, L, s)));
+    return rc;
+}
+
+void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin, int shuffle, uint32_t seed,
+                    int it, const int32_t* rep_perm, cudaStream_t s) {
+    const int64_t n = (int64_t)Mm * Vl;
+    if (n <= 0) return;
+    steptab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, Mm, Vl, r0, R, Mt, marker_begin, shuffle, seed, it, rep_perm);
+}
+void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, cudaStream_t s) {
+    const int smem = G * 256 * (int)sizeof(double);
+    static int attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(beta_sq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr = smem;
+    }
+    beta_sq_kernel<<<T, 256, smem, s>>>(betas, group, Mloc, G, out);
+}
+void launch_global_draw(const GlobalDrawParams& p, cudaStream_t s) { global_draw_kernel<<<1, 32, 0, s>>>(p); }
+void launch_mu_draw(const MuDrawParams& p, cudaStream_t s) { mu_draw_kernel<<<1, 32, 0, s>>>(p); }
+void launch_init_sigmae(const double* esq, const int32_t* nonas, int T, double* sigmae, cudaStream_t s) {
+    init_sigmae_kernel<<<1, 32, 0, s>>>(esq, nonas, T, sigmae);
+}
+
+}  // namespace gmrm

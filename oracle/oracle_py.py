@@ -155,7 +155,10 @@ def have_reference() -> bool:
 def run_reference(workdir, bed, dim, phens, gri, grm, out_dir, *, iterations, seed=171014, nranks=1,
                   shuffle=1, threads=1, log_dir=None, extra=(), timeout=600):
     """Run oracle/_ref/gmrm_ref (the unmodified reference) with the reference's own flags."""
-    env = dict(os.environ, GMRM_SHIM_NRANKS=str(nranks), OMP_NUM_THREADS=str(threads))
+    # MALLOC_PERTURB_=255 makes glibc hand out zero-filled blocks: the reference leaves the pad slots of
+    # epsilon_ uninitialised when N % 4 != 0 (phenotype.cpp:30 vs 653) and then multiplies them into every
+    # dot product (bayes.cpp:756-764); zero is what a fresh process sees and what the oracle assumes.
+    env = dict(os.environ, GMRM_SHIM_NRANKS=str(nranks), OMP_NUM_THREADS=str(threads), MALLOC_PERTURB_="255")
     if log_dir:
         os.makedirs(log_dir, exist_ok=True)
         env["GMRM_RNG_LOG_DIR"] = log_dir
