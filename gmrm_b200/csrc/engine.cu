@@ -132,6 +132,7 @@ struct gmrm_engine {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> dot_ev;
     bool timing_detail = false;
+    int dot_variant = 0;
     gmrm_timing last{};
 
     ~gmrm_engine() {
@@ -184,6 +185,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->marker_begin = S;
     e->Mloc = Slast + Mlast - S;
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
+    if (const char* v = getenv("GMRM_DOT_VARIANT")) e->dot_variant = atoi(v);
     e->phen_set.assign(c->T, 0);
     e->h_nonas.assign(c->T, 0);
 
@@ -208,7 +210,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T));
     A(e->sigmag.alloc((size_t)T * G)); A(e->sigmae.alloc(T)); A(e->pi.alloc((size_t)T * G * K));
     A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T));
-    A(e->zeros.alloc((size_t)kDotThreads * kBatch));
+    A(e->zeros.alloc((size_t)kDotMaxThreads * kDotMaxBatch));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
     A(e->miss_off.alloc((size_t)e->Mloc + 1));
     if (c->world_size > 1) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
@@ -438,7 +440,7 @@ static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* parti
         DotParams p{};
         p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
         p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm * 4;
-        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p;
+        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p; p.variant = e->dot_variant;
         if (launch_dot(e->L, std::min(tc, T - t0), p, e->stream) != 0) return fail(GMRM_ECUDA, "dot kernel launch setup failed");
     }
     return 0;

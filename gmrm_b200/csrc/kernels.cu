@@ -324,46 +324,45 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // launch, a marker costs E x (shift + DFMA) per lane (layout.h), then an 8-marker select-free
 // transposed butterfly leaves one per-warp partial per marker, written to partial[r][t][tile*4+sp].
 // =====================================================================================
-template <int E4, int T>
-__global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) {
+template <int E4, int T, int WPS, int BATCH>
+__global__ void __maxnreg__(WPS == 2 ? 224 : WPS == 3 ? 152 : 120) dot_kernel(const DotParams p) {
     constexpr int TILE = kLanesPerTile * E4;
     constexpr int E = 4 * E4;
     constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
+    constexpr int RING = dot_ring_tiles(WPS);
+    constexpr int STAGES = RING / BATCH;
+    constexpr int NTHREADS = (4 * WPS + 1) * 32;
+    constexpr int LOGB = BATCH == 8 ? 3 : 2;
+    static_assert(BATCH == 8 || BATCH == 4, "batch of 4 or 8 markers");
+    static_assert(STAGES % WPS == 0, "a stage must always serve the same consumer group");
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* ring = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + kStages * kBatch * TILE);
-    uint64_t* empty = full + kStages;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING * TILE);
+    uint64_t* empty = full + STAGES;
+    int32_t* scols = reinterpret_cast<int32_t*>(empty + STAGES);     // the step's columns, padded with -1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = (p.V + kBatch - 1) / kBatch;
+    const int nb = (p.V + BATCH - 1) / BATCH;
 
+    for (int i = threadIdx.x; i < nb * BATCH; i += NTHREADS) scols[i] = i < p.V ? p.cols[i] : -1;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
 
-    if (warp == 4 * kWPS) {
-        // ---------------- producer ----------------
-        if (lane == 0) {
-            const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * TILE;
-            for (int b = 0; b < nb; b++) {
-                const int s = b % kStages;
-                if (b >= kStages) mbar_wait(&empty[s], (uint32_t)((b / kStages) - 1) & 1u);
-                int cols[kBatch], nvalid = 0;
-#pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    const int r = b * kBatch + j;
-                    cols[j] = r < p.V ? p.cols[r] : -1;
-                    nvalid += cols[j] >= 0;
-                }
-                mbar_expect_tx(&full[s], (uint32_t)(nvalid * TILE));
-#pragma unroll
-                for (int j = 0; j < kBatch; j++)
-                    if (cols[j] >= 0)
-                        bulk_g2s(ring + (s * kBatch + j) * TILE, tile0 + (int64_t)cols[j] * p.col_stride, TILE, &full[s]);
-            }
+    if (warp == 4 * WPS) {
+        // ---------------- producer: lane j < BATCH issues the copy of marker j of every batch ----------------
+        const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * TILE;
+        for (int b = 0; b < nb; b++) {
+            const int s = b % STAGES;
+            if (b >= STAGES) mbar_wait(&empty[s], (uint32_t)((b / STAGES) - 1) & 1u);
+            const int col = lane < BATCH ? scols[b * BATCH + lane] : -1;
+            const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, col >= 0));
+            if (lane == 0) mbar_expect_tx(&full[s], nvalid * TILE);
+            __syncwarp();
+            if (col >= 0) bulk_g2s(ring + (s * BATCH + lane) * TILE, tile0 + (int64_t)col * p.col_stride, TILE, &full[s]);
         }
         return;
     }
@@ -390,25 +389,44 @@ __global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) 
         }
     }
 
-    // accumulator slot j of this lane holds marker j ^ P: makes the butterfly below select-free
-    const int P = (((lane >> 4) & 1) << 2) | (((lane >> 3) & 1) << 1) | ((lane >> 2) & 1);
-    double D[kBatch];
+    // accumulator slot j of this lane holds marker j ^ P (P = lane bits 4,3[,2] reversed): makes the
+    // transposed butterfly below select-free
+    int P = 0;
 #pragma unroll
-    for (int j = 0; j < kBatch; j++) D[j] = p.zeros[j * kDotThreads + threadIdx.x];
+    for (int i = 0; i < LOGB; i++) P |= ((lane >> (4 - i)) & 1) << (LOGB - 1 - i);
+    // shared-memory offsets (from the stage base) of this lane's word / half / byte of accumulator slot j
+    uint32_t offw[BATCH], offh[BATCH], offb[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; j++) {
+        offw[j] = (uint32_t)((j ^ P) * TILE + ls * 4);
+        offh[j] = (uint32_t)((j ^ P) * TILE + NW * kLanesPerTile * 4 + ls * 2);
+        offb[j] = (uint32_t)((j ^ P) * TILE + NW * kLanesPerTile * 4 + NH * kLanesPerTile * 2 + ls);
+    }
+    double D[BATCH];        // one persistent (lo = shifted word, hi = 0) multiplier pair per accumulator
+#pragma unroll
+    for (int j = 0; j < BATCH; j++) D[j] = p.zeros[j * NTHREADS + threadIdx.x];
+    const uint32_t ring_u32 = smem_u32(ring);
 
-    for (int b = q; b < nb; b += kWPS) {
-        const int s = b % kStages;
-        mbar_wait(&full[s], (uint32_t)(b / kStages) & 1u);
-        const uint8_t* st = ring + s * kBatch * TILE;
-        SlotRegs<E4> g[kBatch];
+    for (int b = q; b < nb; b += WPS) {
+        const int s = b % STAGES;
+        mbar_wait(&full[s], (uint32_t)(b / STAGES) & 1u);
+        const uint32_t st = ring_u32 + (uint32_t)(s * BATCH * TILE);
+        uint32_t gw[BATCH][NW > 0 ? NW : 1], gh[BATCH], gb[BATCH];
 #pragma unroll
-        for (int j = 0; j < kBatch; j++) g[j].load(st + (j ^ P) * TILE, ls);
+        for (int j = 0; j < BATCH; j++) {
+#pragma unroll
+            for (int wi = 0; wi < NW; wi++)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gw[j][wi]) : "r"(st + offw[j] + wi * kLanesPerTile * 4));
+            gh[j] = 0; gb[j] = 0;
+            if (NH) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(gh[j]) : "r"(st + offh[j]));
+            if (NB) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gb[j]) : "r"(st + offb[j]));
+        }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);     // registers hold the batch: the stage can be refilled
 
-        double acc[kBatch][T];
+        double acc[BATCH][T];
 #pragma unroll
-        for (int j = 0; j < kBatch; j++)
+        for (int j = 0; j < BATCH; j++)
 #pragma unroll
             for (int t = 0; t < T; t++) acc[j][t] = 0.0;
 
@@ -417,8 +435,8 @@ __global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) 
 #pragma unroll
             for (int k = 0; k < 16; k++)
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    set_lo(D[j], g[j].w[wi] << (30 - 2 * k));
+                for (int j = 0; j < BATCH; j++) {
+                    set_lo(D[j], gw[j][wi] << (30 - 2 * k));
 #pragma unroll
                     for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[wi * 16 + k][t], acc[j][t]);
                 }
@@ -426,8 +444,8 @@ __global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) 
 #pragma unroll
             for (int k = 0; k < 8; k++)
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    set_lo(D[j], g[j].h << (30 - 2 * k));
+                for (int j = 0; j < BATCH; j++) {
+                    set_lo(D[j], gh[j] << (30 - 2 * k));
 #pragma unroll
                     for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + k][t], acc[j][t]);
                 }
@@ -436,27 +454,30 @@ __global__ void __launch_bounds__(kDotThreads, 1) dot_kernel(const DotParams p) 
 #pragma unroll
             for (int k = 0; k < 4; k++)
 #pragma unroll
-                for (int j = 0; j < kBatch; j++) {
-                    set_lo(D[j], g[j].b << (30 - 2 * k));
+                for (int j = 0; j < BATCH; j++) {
+                    set_lo(D[j], gb[j] << (30 - 2 * k));
 #pragma unroll
                     for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + 8 * NH + k][t], acc[j][t]);
                 }
         }
 
-        // transposed butterfly: 8 markers x 32 lanes -> marker (P) total in every lane of a quad
+        // transposed butterfly: BATCH markers x 32 lanes -> total of marker P in every lane sharing P
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            double a4[4], a2[2], a1;
+            double a[BATCH];
 #pragma unroll
-            for (int j = 0; j < 4; j++) a4[j] = acc[j][t] + __shfl_xor_sync(0xffffffffu, acc[j + 4][t], 16);
+            for (int j = 0; j < BATCH; j++) a[j] = acc[j][t];
 #pragma unroll
-            for (int j = 0; j < 2; j++) a2[j] = a4[j] + __shfl_xor_sync(0xffffffffu, a4[j + 2], 8);
-            a1 = a2[0] + __shfl_xor_sync(0xffffffffu, a2[1], 4);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            const int r = b * kBatch + P;
-            if ((lane & 3) == 0 && r < p.V)
-                p.partial[((int64_t)r * p.Ttot + p.t0 + t) * p.nsl + blockIdx.x * 4 + sp] = a1 * kDotUnscale;
+            for (int i = 0; i < LOGB; i++) {
+                const int half = BATCH >> (i + 1);
+#pragma unroll
+                for (int j = 0; j < half; j++) a[j] += __shfl_xor_sync(0xffffffffu, a[j + half], 16 >> i);
+            }
+#pragma unroll
+            for (int o = 16 >> LOGB; o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
+            const int r = b * BATCH + P;
+            if ((lane & ((32 >> LOGB) - 1)) == 0 && r < p.V)
+                p.partial[((int64_t)r * p.Ttot + p.t0 + t) * p.nsl + blockIdx.x * 4 + sp] = a[0] * kDotUnscale;
         }
     }
 }
@@ -505,20 +526,26 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
     const double mave = p.mave[mi], msig = p.msig[mi];
     const double dot_raw = msig * (my_dpa - mave * my_dpb);                // bayes.cpp:766
     const uint32_t mglo = (uint32_t)(p.marker_begin + col);
-    double u, z = 0.0;
+    double u;
     const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + t;
     const double sigg = p.sigmag[t * p.G + grp];
     if (p.rep_u) {
         u = p.rep_u[ri];
-        z = p.rep_z[ri];
         if (sigg != 0.0 && !(u == u)) atomicExch(p.err, 1);               // reference drew nothing here
     } else {
         u = draw_uniform(p.seed, STREAM_SAMPLER_U, (uint32_t)p.it, mglo, (uint32_t)t);
-        z = draw_normal(p.seed, STREAM_SAMPLER_N, (uint32_t)p.it, mglo, (uint32_t)t);
     }
+    // the normal is only materialised when a non-null component is chosen (bayes.cpp:456)
+    auto zdraw = [&]() -> double {
+        if (p.rep_z) {
+            const double z = p.rep_z[ri];
+            if (!(z == z)) atomicExch(p.err, 2);
+            return z;
+        }
+        return draw_normal(p.seed, STREAM_SAMPLER_N, (uint32_t)p.it, mglo, (uint32_t)t);
+    };
     const MarkerDraw d = sample_marker(dot_raw, p.betas[mi], p.sigmae[t], sigg, p.cva + grp * p.K, p.cvai + grp * p.K,
-                                       p.pi + ((int64_t)t * p.G + grp) * p.K, p.K, p.N, p.nonas[t], u, z);
-    if (p.rep_u && d.need_z && !(z == z)) atomicExch(p.err, 2);
+                                       p.pi + ((int64_t)t * p.G + grp) * p.K, p.K, p.N, p.nonas[t], u, zdraw);
     p.betas[mi] = d.beta_new;
     if (d.comp >= 0) {
         p.comp[mi] = d.comp;                                               // bayes.cpp:462
@@ -764,16 +791,28 @@ void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double*
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);
 }
 
+template <int E4, int T, int WPS, int BATCH>
+static int dot_launch_v(const DotParams& p, int nsm, cudaStream_t s) {
+    const int nbpad = (p.V + BATCH - 1) / BATCH * BATCH;
+    const int smem = dot_ring_tiles(WPS) * kLanesPerTile * E4 + 2 * (dot_ring_tiles(WPS) / BATCH) * (int)sizeof(uint64_t) + nbpad * (int)sizeof(int32_t);
+    static int attr = 0;
+    if (smem > attr) {
+        if (cudaFuncSetAttribute(dot_kernel<E4, T, WPS, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        attr = smem;
+    }
+    dot_kernel<E4, T, WPS, BATCH><<<nsm, (4 * WPS + 1) * 32, smem, s>>>(p);
+    return 0;
+}
+// variants (consumer warps per sub-partition, markers per batch): 0 = (3,4) default, 1 = (4,4), 2 = (2,4), 3 = (2,8).
+// All are instantiated for single-trait runs (the headline path); multi-trait launches use the default.
 template <int E4, int T>
 static int dot_launch_t(const DotParams& p, int nsm, cudaStream_t s) {
-    constexpr int smem = kStages * kBatch * kLanesPerTile * E4 + 2 * kStages * (int)sizeof(uint64_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(dot_kernel<E4, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        attr_set = true;
+    if (T == 1) {
+        if (p.variant == 1) return dot_launch_v<E4, 1, 4, 4>(p, nsm, s);
+        if (p.variant == 2) return dot_launch_v<E4, 1, 2, 4>(p, nsm, s);
+        if (p.variant == 3) return dot_launch_v<E4, 1, 2, 8>(p, nsm, s);
     }
-    dot_kernel<E4, T><<<nsm, kDotThreads, smem, s>>>(p);
-    return 0;
+    return dot_launch_v<E4, T, 3, 4>(p, nsm, s);
 }
 template <int E4>
 static int dot_launch_e(int T, const DotParams& p, int nsm, cudaStream_t s) {

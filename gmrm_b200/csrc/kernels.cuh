@@ -12,10 +12,11 @@ namespace gmrm {
 
 // ------------------------------------------------------------------------------------------
 // dot kernel geometry
-constexpr int kBatch = 8;     // markers per ring stage == markers a consumer warp holds in registers
-constexpr int kStages = 8;    // ring depth (8 x 8 x tile_bytes <= 64 KB)
-constexpr int kWPS = 2;       // consumer warps per SM sub-partition (they alternate batches)
-constexpr int kDotThreads = (4 * kWPS + 1) * 32;   // + 1 producer warp
+// shared-memory ring of the dot kernel: 64 tiles (<= 64 KB; 48 when 3 consumer warps share a sub-partition so
+// that a stage always serves the same warp), cut into stages of BATCH markers
+__host__ __device__ constexpr int dot_ring_tiles(int wps) { return wps == 3 ? 48 : 64; }
+constexpr int kDotMaxThreads = 17 * 32; // 4 consumer warps per sub-partition + 1 producer warp, the widest variant
+constexpr int kDotMaxBatch = 8;
 constexpr int kUpdThreads = kLanesPerTile;
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
@@ -33,7 +34,8 @@ struct DotParams {
     double* partial;         // [V][Ttot][nsl]
     int32_t nsl;             // nsm * 4
     int32_t Ttot, t0;        // this launch handles traits t0 .. t0+T-1 of Ttot
-    const double* zeros;     // >= kDotThreads * kBatch zeros (opaque to ptxas, see set_lo)
+    const double* zeros;     // >= kDotMaxThreads * kDotMaxBatch zeros (opaque to ptxas, see set_lo)
+    int32_t variant;         // (consumer warps / sub-partition, markers / batch): 0 = (3,4), 1 = (4,4), 2 = (2,4), 3 = (2,8)
 };
 
 struct SampleParams {

@@ -20,12 +20,13 @@ struct MarkerDraw {
     int need_z;     // 1 when a normal was consumed
 };
 
-// u: uniform in [0,1); z: standard normal (used only when a non-null component is chosen).
-// cva/cvai/pi: this marker's group rows, K entries each.
+// u: uniform in [0,1); zdraw(): returns the standard normal, called only when a non-null component
+// is chosen.  cva/cvai/pi: this marker's group rows, K entries each.
+template <class ZDraw>
 GMRM_HD MarkerDraw sample_marker(double dot_raw,   // msig*(sum a*eps - mave*sum b*eps), bayes.cpp:418
                                  double beta, double sigmae, double sigmag, const double* cva,
                                  const double* cvai, const double* pi, int K, int N, int nonas,
-                                 double u, double z) {
+                                 double u, ZDraw zdraw) {
     MarkerDraw r;
     r.need_z = 0;
     if (sigmag == 0.0) {                                     // bayes.cpp:396-400: no draw, no cass, beta = 0
@@ -56,7 +57,7 @@ GMRM_HD MarkerDraw sample_marker(double dot_raw,   // msig*(sum a*eps - mave*sum
             if (i == 0) {
                 r.beta_new = 0.0;
             } else {
-                r.beta_new = muk[i] + sqrt(sigmae / denom[i - 1]) * z;                    // 456, distributions.hpp:48-53
+                r.beta_new = muk[i] + sqrt(sigmae / denom[i - 1]) * zdraw();                    // 456, distributions.hpp:48-53
                 r.need_z = 1;
             }
             r.comp = i;
