@@ -132,7 +132,7 @@ struct gmrm_engine {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> dot_ev;
     bool timing_detail = false;
-    int dot_variant = 0;
+    int dot_variant = 0, dot_debug = 0;
     gmrm_timing last{};
 
     ~gmrm_engine() {
@@ -186,6 +186,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->Mloc = Slast + Mlast - S;
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
     if (const char* v = getenv("GMRM_DOT_VARIANT")) e->dot_variant = atoi(v);
+    if (const char* v = getenv("GMRM_DOT_DEBUG")) e->dot_debug = atoi(v);
     e->phen_set.assign(c->T, 0);
     e->h_nonas.assign(c->T, 0);
 
@@ -440,8 +441,9 @@ static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* parti
         DotParams p{};
         p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
         p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm * 4;
-        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p; p.variant = e->dot_variant;
-        if (launch_dot(e->L, std::min(tc, T - t0), p, e->stream) != 0) return fail(GMRM_ECUDA, "dot kernel launch setup failed");
+        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p; p.variant = e->dot_variant; p.debug = e->dot_debug;
+        if (launch_dot(e->L, std::min(tc, T - t0), p, e->stream) != 0)
+            return fail(GMRM_ECUDA, "dot kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }

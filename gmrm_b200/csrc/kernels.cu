@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // transposed butterfly leaves one per-warp partial per marker, written to partial[r][t][tile*4+sp].
 // =====================================================================================
 template <int E4, int T, int WPS, int BATCH>
-__global__ void __maxnreg__(WPS == 2 ? 224 : WPS == 3 ? 152 : 120) dot_kernel(const DotParams p) {
+__global__ void __launch_bounds__((4 * WPS + 1) * 32, 1) dot_kernel(const DotParams p) {
     constexpr int TILE = kLanesPerTile * E4;
     constexpr int E = 4 * E4;
     constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
@@ -353,6 +353,7 @@ __global__ void __maxnreg__(WPS == 2 ? 224 : WPS == 3 ? 152 : 120) dot_kernel(co
     __syncthreads();
 
     if (warp == 4 * WPS) {
+        if (p.debug == 2) return;                     // debug: compute only, nothing is fed
         // ---------------- producer: lane j < BATCH issues the copy of marker j of every batch ----------------
         const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * TILE;
         for (int b = 0; b < nb; b++) {
@@ -409,7 +410,7 @@ __global__ void __maxnreg__(WPS == 2 ? 224 : WPS == 3 ? 152 : 120) dot_kernel(co
 
     for (int b = q; b < nb; b += WPS) {
         const int s = b % STAGES;
-        mbar_wait(&full[s], (uint32_t)(b / STAGES) & 1u);
+        if (p.debug != 2) mbar_wait(&full[s], (uint32_t)(b / STAGES) & 1u);
         const uint32_t st = ring_u32 + (uint32_t)(s * BATCH * TILE);
         uint32_t gw[BATCH][NW > 0 ? NW : 1], gh[BATCH], gb[BATCH];
 #pragma unroll
@@ -422,7 +423,8 @@ __global__ void __maxnreg__(WPS == 2 ? 224 : WPS == 3 ? 152 : 120) dot_kernel(co
             if (NB) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gb[j]) : "r"(st + offb[j]));
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);     // registers hold the batch: the stage can be refilled
+        if (lane == 0 && p.debug != 2) mbar_arrive(&empty[s]);     // registers hold the batch: the stage can be refilled
+        if (p.debug == 1) continue;                   // debug: feed only, no arithmetic
 
         double acc[BATCH][T];
 #pragma unroll
@@ -571,17 +573,26 @@ __global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, 
 }
 
 // =====================================================================================
-// K3: apply the step's published updates to the residuals, rank order, per individual.
+// K3: apply the step's published updates to the residuals.
 // Phenotype::update_epsilon, phenotype.cpp:326-329,375-390:  eps += (a - mave*b) * (dbeta*msig) * na
-// One thread per lane-slot (same mapping as K1); blockIdx.y = trait.
+//
+// One CTA per (tile, trait), 4 x kUpdSplit warps.  Warp w serves the lane-slots of sub-partition
+// w & 3 (same mapping as K1) and takes every kUpdSplit-th published marker, in rank order, prefetching
+// kUpdPF columns ahead; its increments stay in registers.  The splits are then combined through shared
+// memory in a fixed order (reproducible), masked by the NA mask and added to eps; the per-tile sum of
+// eps that K2 needs is refreshed on the way.
 // =====================================================================================
 template <int E4>
-__global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateParams p, Layout L) {
+__global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdateParams p, Layout L) {
     constexpr int E = 4 * E4;
-    extern __shared__ int32_t plist[];               // published virtual ranks of this trait, ascending
+    constexpr int EK = E / kUpdSplit;                 // individuals of a slot one thread finalises (E is a multiple of 4)
+    extern __shared__ __align__(16) uint8_t usmem[];
+    double* dlt = reinterpret_cast<double*>(usmem);                                  // [kUpdSplit][E][128]
+    int32_t* plist = reinterpret_cast<int32_t*>(usmem + sizeof(double) * kUpdSplit * E * kLanesPerTile);   // published ranks, ascending
     __shared__ int npub;
     __shared__ double red[kUpdThreads / 32];
-    const int t = blockIdx.y, ls = threadIdx.x, lane = threadIdx.x & 31;
+    const int t = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sp = warp & 3, u = warp >> 2, ls = sp * 32 + lane;
 
     if (threadIdx.x < 32) {                          // ordered compaction by warp 0
         int n = 0;
@@ -596,36 +607,59 @@ __global__ void __launch_bounds__(kUpdThreads) update_kernel(const UpdateParams 
     }
     __syncthreads();
     const int n = npub;
+    if (n == 0) return;                              // nothing published for this trait: eps and its sums stand
 
+    const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * L.tile_bytes;
+    double d[E];
+#pragma unroll
+    for (int k = 0; k < E; k++) d[k] = 0.0;
+
+    SlotRegs<E4> g[kUpdPF], gn[kUpdPF];
+    const int mine = (n - u + kUpdSplit - 1) / kUpdSplit;      // markers i = u, u + S, u + 2S, ...
+    auto fetch = [&](SlotRegs<E4>* dst, int c0) {
+#pragma unroll
+        for (int j = 0; j < kUpdPF; j++)
+            if (c0 + j < mine) dst[j].load(tile0 + (int64_t)p.cols[plist[u + (c0 + j) * kUpdSplit]] * p.col_stride, ls);
+    };
+    fetch(gn, 0);
+    for (int c0 = 0; c0 < mine; c0 += kUpdPF) {
+#pragma unroll
+        for (int j = 0; j < kUpdPF; j++) g[j] = gn[j];
+        fetch(gn, c0 + kUpdPF);                                  // prefetch the next chunk
+#pragma unroll
+        for (int j = 0; j < kUpdPF; j++) {
+            if (c0 + j >= mine) break;
+            const PubEntry pe = p.pub[(int64_t)plist[u + (c0 + j) * kUpdSplit] * p.T + t];
+            // reference arithmetic: (mdb*b + a) * bs_  with mdb = -mave, bs_ = dbeta*msig; 0 where missing
+            const double mdb = -pe.mave;
+            const double v0 = (mdb * 1.0 + 0.0) * pe.lam, v1 = (mdb * 1.0 + 1.0) * pe.lam, v2 = (mdb * 1.0 + 2.0) * pe.lam;
+#pragma unroll
+            for (int k = 0; k < E; k++) {
+                const uint32_t c = g[j].field(k);
+                d[k] += c == 0 ? v0 : c == 1 ? v1 : c == 2 ? v2 : 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < E; k++) dlt[((int64_t)u * E + k) * kLanesPerTile + ls] = d[k];
+    __syncthreads();
+
+    // combine the splits in fixed order; thread (u, ls) finalises individuals u*EK .. u*EK+EK-1 of its slot
     SlotRegs<E4> na;
     na.load(p.namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
     double* ep = p.eps + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
-    double e[E];
-#pragma unroll
-    for (int k = 0; k < E; k++) e[k] = ep[k];
-
-    const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * L.tile_bytes;
-    SlotRegs<E4> g, gnext;
-    if (n > 0) gnext.load(tile0 + (int64_t)p.cols[plist[0]] * p.col_stride, ls);
-    for (int i = 0; i < n; i++) {
-        g = gnext;
-        const int v = plist[i];
-        if (i + 1 < n) gnext.load(tile0 + (int64_t)p.cols[plist[i + 1]] * p.col_stride, ls);   // prefetch
-        const PubEntry pe = p.pub[(int64_t)v * p.T + t];
-        // reference arithmetic: (mdb*b + a) * bs_ * m  with mdb = -mave, bs_ = dbeta*msig
-        const double mdb = -pe.mave;
-        const double v0 = (mdb * 1.0 + 0.0) * pe.lam, v1 = (mdb * 1.0 + 1.0) * pe.lam, v2 = (mdb * 1.0 + 2.0) * pe.lam;
-#pragma unroll
-        for (int k = 0; k < E; k++) {
-            const uint32_t c = g.field(k);
-            double val = c == 0 ? v0 : c == 1 ? v1 : c == 2 ? v2 : 0.0;
-            if (!na.field(k)) val = 0.0;
-            e[k] += val;
-        }
-    }
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < E; k++) { ep[k] = e[k]; s += e[k]; }
+    for (int kk = 0; kk < EK; kk++) {
+        const int k = u * EK + kk;
+        double inc = 0.0;
+#pragma unroll
+        for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * E + k) * kLanesPerTile + ls];
+        double e = ep[k];
+        if (na.field(k)) e += inc;                   // * na  (phenotype.cpp:388)
+        ep[k] = e;
+        s += e;
+    }
     const double tot = block_sum_fixed(s, red);
     if (threadIdx.x == 0) p.spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
 }
@@ -801,18 +835,19 @@ static int dot_launch_v(const DotParams& p, int nsm, cudaStream_t s) {
         attr = smem;
     }
     dot_kernel<E4, T, WPS, BATCH><<<nsm, (4 * WPS + 1) * 32, smem, s>>>(p);
-    return 0;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
-// variants (consumer warps per sub-partition, markers per batch): 0 = (3,4) default, 1 = (4,4), 2 = (2,4), 3 = (2,8).
+// variants (consumer warps per sub-partition, markers per batch): 0 = (2,8) default, 1 = (4,4), 2 = (2,4), 3 = (3,4).
 // All are instantiated for single-trait runs (the headline path); multi-trait launches use the default.
 template <int E4, int T>
 static int dot_launch_t(const DotParams& p, int nsm, cudaStream_t s) {
     if (T == 1) {
         if (p.variant == 1) return dot_launch_v<E4, 1, 4, 4>(p, nsm, s);
         if (p.variant == 2) return dot_launch_v<E4, 1, 2, 4>(p, nsm, s);
-        if (p.variant == 3) return dot_launch_v<E4, 1, 2, 8>(p, nsm, s);
+        if (p.variant == 3) return dot_launch_v<E4, 1, 3, 4>(p, nsm, s);
+        return dot_launch_v<E4, 1, 2, 8>(p, nsm, s);
     }
-    return dot_launch_v<E4, T, 3, 4>(p, nsm, s);
+    return dot_launch_v<E4, T, 2, 4>(p, nsm, s);     // multi-trait: widest register budget (168 / thread)
 }
 template <int E4>
 static int dot_launch_e(int T, const DotParams& p, int nsm, cudaStream_t s) {
@@ -842,7 +877,7 @@ void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
 
 template <int E4>
 static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t s) {
-    const int smem = p.V * (int)sizeof(int32_t);
+    const int smem = (int)sizeof(double) * kUpdSplit * 4 * E4 * kLanesPerTile + p.V * (int)sizeof(int32_t);
     static int attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         if (cudaFuncSetAttribute(update_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
@@ -850,7 +885,7 @@ static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t 
     }
     dim3 grid((unsigned)L.nsm, (unsigned)p.T);
     update_kernel<E4><<<grid, kUpdThreads, smem, s>>>(p, L);
-    return 0;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 int launch_update(const Layout& L, const UpdateParams& p, cudaStream_t s) {
     int rc = -1;

@@ -17,7 +17,9 @@ namespace gmrm {
 __host__ __device__ constexpr int dot_ring_tiles(int wps) { return wps == 3 ? 48 : 64; }
 constexpr int kDotMaxThreads = 17 * 32; // 4 consumer warps per sub-partition + 1 producer warp, the widest variant
 constexpr int kDotMaxBatch = 8;
-constexpr int kUpdThreads = kLanesPerTile;
+constexpr int kUpdSplit = 4;                              // warps per sub-partition in the update kernel
+constexpr int kUpdPF = 4;                                 // columns each update warp prefetches ahead
+constexpr int kUpdThreads = kLanesPerTile * kUpdSplit;
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
     double lam;     // dbeta * msig   (0 == nothing to apply)
@@ -35,7 +37,8 @@ struct DotParams {
     int32_t nsl;             // nsm * 4
     int32_t Ttot, t0;        // this launch handles traits t0 .. t0+T-1 of Ttot
     const double* zeros;     // >= kDotMaxThreads * kDotMaxBatch zeros (opaque to ptxas, see set_lo)
-    int32_t variant;         // (consumer warps / sub-partition, markers / batch): 0 = (3,4), 1 = (4,4), 2 = (2,4), 3 = (2,8)
+    int32_t debug;           // 0 normal; 1 feed only (no arithmetic); 2 compute only (no TMA, no barriers) -- profiling aids
+    int32_t variant;         // (consumer warps / sub-partition, markers / batch): 0 = (2,8), 1 = (4,4), 2 = (2,4), 3 = (3,4)
 };
 
 struct SampleParams {
