@@ -133,6 +133,7 @@ struct gmrm_engine {
     std::vector<cudaEvent_t> dot_ev;
     bool timing_detail = false;
     int dot_variant = 0, dot_debug = 0;
+    int dot_kernel = 1;        // 1: table-lookup kernel (single-trait runs), 0: shift+DFMA kernel
     gmrm_timing last{};
 
     ~gmrm_engine() {
@@ -187,6 +188,8 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
     if (const char* v = getenv("GMRM_DOT_VARIANT")) e->dot_variant = atoi(v);
     if (const char* v = getenv("GMRM_DOT_DEBUG")) e->dot_debug = atoi(v);
+    e->dot_kernel = c->T == 1 ? 1 : 0;
+    if (const char* v = getenv("GMRM_DOT_KERNEL")) e->dot_kernel = atoi(v);
     e->phen_set.assign(c->T, 0);
     e->h_nonas.assign(c->T, 0);
 
@@ -435,8 +438,22 @@ static int trait_chunk(int E) {
     return 1;
 }
 
+// partial sums per (marker, trait) that the sampler adds up: one per CTA for the table kernel, one per
+// CTA and sub-partition for the shift+DFMA kernel
+static int dot_nsl(const gmrm_engine* e) { return e->dot_kernel == 1 ? e->L.nsm : e->L.nsm * 4; }
+
 static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* partial) {
     const int T = e->cfg.T, tc = trait_chunk(e->L.E);
+    if (e->dot_kernel == 1) {                                   // table-lookup kernel, one trait per launch
+        for (int t = 0; t < T; t++) {
+            DotParams p{};
+            p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
+            p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm; p.Ttot = T; p.t0 = t;
+            if (launch_dot_table(e->L, p, e->stream) != 0)
+                return fail(GMRM_ECUDA, "table dot kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        return 0;
+    }
     for (int t0 = 0; t0 < T; t0 += tc) {
         DotParams p{};
         p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
@@ -450,7 +467,7 @@ static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* parti
 
 static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, const double* partial) {
     SampleParams p{};
-    p.V = V; p.T = e->cfg.T; p.G = e->cfg.G; p.K = e->cfg.K; p.N = e->cfg.N; p.nsl = e->L.nsm * 4; p.nsm = e->L.nsm;
+    p.V = V; p.T = e->cfg.T; p.G = e->cfg.G; p.K = e->cfg.K; p.N = e->cfg.N; p.nsl = dot_nsl(e); p.nsm = e->L.nsm;
     p.seed = e->cfg.seed; p.r0 = e->r0; p.R = e->cfg.vranks; p.marker_begin = e->marker_begin; p.Mloc = e->Mloc;
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
@@ -660,7 +677,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
         up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
         if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
-        launches += (T + trait_chunk(L.E) - 1) / trait_chunk(L.E) + 2;
+        launches += (e->dot_kernel == 1 ? T : (T + trait_chunk(L.E) - 1) / trait_chunk(L.E)) + 2;
         if (multi) return fail(GMRM_EINVAL, "multi-GPU exchange not wired yet");
     }
     CU(cudaEventRecord(e->ev[2], s));

@@ -485,6 +485,138 @@ __global__ void __launch_bounds__((4 * WPS + 1) * 32, 1) dot_kernel(const DotPar
 }
 
 // =====================================================================================
+// K1 (single-trait fast path): table-lookup dot product.
+//
+// The shift+DFMA kernel above is bounded by instruction issue, not by the FP64 pipe: on sm_100a any
+// integer instruction issued between two DFMAs costs about as much as the DFMA itself
+// (tools/pipe_micro.cu: 48 DFMA/clk/SM alone, 30 with one shift each), so one trait cannot get past
+// ~30 genotypes/clk/SM that way.  Here a group of 4 consecutive individuals (one byte of the column)
+// is handled by ONE shared-memory lookup and ONE add:
+//     table[q][byte] = sum_k field_k(byte) * eps[4q + k]          256 doubles per byte position
+// The tile of a CTA (128*E4 bytes per column) is cut into chunks of <= 112 bytes; a pass builds the
+// tables of one chunk (224 KB of shared memory) and streams that chunk of all V columns through
+// them: lane l of a warp loads word l of the chunk (one coalesced <= 112-byte row per marker) and
+// looks its 4 bytes up; 8 markers are reduced across lanes by a transposed butterfly.  Chunk c of
+// pass p is tile (p*nsm + cta) / chunks_per_tile ..., i.e. in one pass the CTAs together read one
+// contiguous nsm*CB-byte run of every column.  Per-marker partials are accumulated across passes
+// in partial[r][t][cta] (each CTA owns its slot: plain read-modify-write).
+// =====================================================================================
+constexpr int kTabWarps = 16;
+constexpr int kTabThreads = kTabWarps * 32;
+constexpr int kTabMaxCW = 28;      // words per chunk: 28 * 4 bytes * 2 KB of table = 224 KB
+
+struct TabGeom { int cw, cwp, npass; };
+__host__ __device__ inline TabGeom tab_geom(int tile_bytes) {
+    TabGeom g;
+    const int words = tile_bytes / 4;
+    g.npass = (words + kTabMaxCW - 1) / kTabMaxCW;
+    g.cw = (words + g.npass - 1) / g.npass;          // words per chunk (last chunk may be shorter)
+    g.cwp = (g.cw + 3) & ~3;                         // padded so that the byte stride keeps lanes on distinct banks
+    return g;
+}
+
+template <int E4>
+__global__ void __launch_bounds__(kTabThreads, 1) dot_table_kernel(const DotParams p, Layout L) {
+    constexpr int E = 4 * E4;
+    constexpr int TILE = kLanesPerTile * E4;
+    extern __shared__ __align__(16) uint8_t tsmem[];
+    double* tab = reinterpret_cast<double*>(tsmem);          // [256][4][cwp]
+    const TabGeom G = tab_geom(TILE);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int RS = 4 * G.cwp;                                // doubles between consecutive byte values
+    const int nbat = (p.V + 7) / 8;
+    const double* eps = p.eps + (int64_t)p.t0 * p.npad;
+    const uint32_t tab_u32 = smem_u32(tab);
+    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
+    const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // marker of the batch this lane ends up holding
+
+    for (int pass = 0; pass < G.npass; pass++) {
+        const int w0 = pass * G.cw;                          // first word of this chunk inside the tile
+        const int cw = min(G.cw, TILE / 4 - w0);             // words in this chunk
+        if (pass) __syncthreads();                           // everyone is done with the previous tables
+        // ---- build: 4 threads per (byte position) quad, 64 byte values each
+        for (int item = threadIdx.x; item < cw * 16; item += kTabThreads) {
+            const int quad = item % (cw * 4), sub = item / (cw * 4);
+            const int wl = quad >> 2, j = quad & 3;          // word (lane) and byte inside the word
+            int ls, bb;
+            tile_offset_to_slot_byte(E4, (w0 + wl) * 4 + j, ls, bb);
+            const double* e = eps + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E + 4 * bb;
+            const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+            double p01[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) p01[i] = (double)(i & 3) * e0 + (double)(i >> 2) * e1;
+            double* dst = tab + j * G.cwp + wl;
+#pragma unroll
+            for (int hb = 0; hb < 4; hb++) {
+                const int h = sub * 4 + hb;                  // high nibble of the byte value
+                const double p23 = (double)(h & 3) * e2 + (double)(h >> 2) * e3;
+#pragma unroll
+                for (int i = 0; i < 16; i++) dst[(int64_t)(h * 16 + i) * RS] = p01[i] + p23;
+            }
+        }
+        __syncthreads();
+
+        // ---- stream the chunk of all V columns through the tables
+        const uint8_t* chunk0 = p.bed + (int64_t)blockIdx.x * TILE + (int64_t)w0 * 4 + lane * 4;
+        const bool active = lane < cw;
+        uint32_t lb[4];                                      // shared-memory byte address of table[0][j][lane]
+#pragma unroll
+        for (int j = 0; j < 4; j++) lb[j] = tab_u32 + (uint32_t)((j * G.cwp + lane) * 8);
+        const uint32_t bstride = (uint32_t)(RS * 8);
+
+        uint32_t wn[8];
+        auto fetch = [&](int bi) {
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                const int r = bi * 8 + jj;
+                const int col = r < p.V ? p.cols[r] : -1;
+                wn[jj] = (active && col >= 0) ? *reinterpret_cast<const uint32_t*>(chunk0 + (int64_t)col * p.col_stride) : 0u;
+            }
+        };
+        if (warp < nbat) fetch(warp);
+        for (int bi = warp; bi < nbat; bi += kTabWarps) {
+            uint32_t w[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) w[jj] = wn[jj];
+            if (bi + kTabWarps < nbat) fetch(bi + kTabWarps);          // prefetch the next batch of this warp
+            double a[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj++) {
+                double v0, v1, v2, v3;
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(lb[0] + (w[jj] & 0xffu) * bstride));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(lb[1] + ((w[jj] >> 8) & 0xffu) * bstride));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(lb[2] + ((w[jj] >> 16) & 0xffu) * bstride));
+                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(lb[3] + (w[jj] >> 24) * bstride));
+                a[jj] = active ? (v0 + v1) + (v2 + v3) : 0.0;
+            }
+            // transposed butterfly over the 8 markers of the batch (fixed order: reproducible)
+            double b4[4], b2[2], b1;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double send = hi16 ? a[i] : a[i + 4], keep = hi16 ? a[i + 4] : a[i];
+                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+                const double send = hi8 ? b4[i] : b4[i + 2], keep = hi8 ? b4[i + 2] : b4[i];
+                b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+                const double send = hi4 ? b2[0] : b2[1], keep = hi4 ? b2[1] : b2[0];
+                b1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+            b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+            const int r = bi * 8 + own;
+            if ((lane & 3) == 0 && r < p.V) {
+                double* dst = p.partial + ((int64_t)r * p.Ttot + p.t0) * p.nsl + blockIdx.x;
+                *dst = pass ? *dst + b1 : b1;
+            }
+        }
+    }
+}
+
+// =====================================================================================
 // K2: one warp per virtual rank: finish the dot product, sample, publish.
 // =====================================================================================
 struct DotPieces { double dpa, dpb; };
@@ -863,6 +995,25 @@ static int dot_launch_e(int T, const DotParams& p, int nsm, cudaStream_t s) {
 int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s) {
     int rc = -1;
     GMRM_DISPATCH_E4(L.E4, (rc = dot_launch_e<E4>(T, p, L.nsm, s)));
+    return rc;
+}
+
+template <int E4>
+static int dot_table_launch_t(const DotParams& p, const Layout& L, cudaStream_t s) {
+    const TabGeom G = tab_geom(L.tile_bytes);
+    const int smem = 256 * 4 * G.cwp * (int)sizeof(double);
+    static int attr = 0;
+    if (smem > attr) {
+        if (cudaFuncSetAttribute(dot_table_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+        attr = smem;
+    }
+    dot_table_kernel<E4><<<L.nsm, kTabThreads, smem, s>>>(p, L);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+}
+// one trait (p.t0) per launch; partial[r][t][cta] with p.nsl == nsm
+int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s) {
+    int rc = -1;
+    GMRM_DISPATCH_E4(L.E4, (rc = dot_table_launch_t<E4>(p, L, s)));
     return rc;
 }
 

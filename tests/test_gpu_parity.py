@@ -138,11 +138,12 @@ def test_marker_stats_dot_and_update(api, oracle, tmp_path, N, M, T, nsm, na, mi
     e.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-@pytest.mark.parametrize("N,nsm", [(128 * 28 - 1, 1), (5000, 2), (20000, 0)])
-def test_dot_kernel_variants(api, oracle, tmp_path, monkeypatch, variant, N, nsm):
-    """Every (consumer warps, batch) variant of the dot kernel (GMRM_DOT_VARIANT) against the oracle,
-    with a marker count that is not a multiple of the batch."""
+@pytest.mark.parametrize("kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3)])
+@pytest.mark.parametrize("N,nsm", [(128 * 28 - 1, 1), (5000, 2), (20000, 0), (128 * 32, 1), (128 * 20 - 2, 1), (777, 1)])
+def test_dot_kernel_variants(api, oracle, tmp_path, monkeypatch, kernel, variant, N, nsm):
+    """Both dot kernels (GMRM_DOT_KERNEL: 1 = table lookup, 0 = shift+DFMA with its (consumer warps, batch)
+    variants, GMRM_DOT_VARIANT) against the oracle, with a marker count that is not a multiple of the batch."""
+    monkeypatch.setenv("GMRM_DOT_KERNEL", str(kernel))
     monkeypatch.setenv("GMRM_DOT_VARIANT", str(variant))
     M = 203
     inp = make_case(oracle, tmp_path, N=N, M=M, missing_rate=0.01, seed=variant + 3)
