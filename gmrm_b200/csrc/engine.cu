@@ -188,7 +188,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
     if (const char* v = getenv("GMRM_DOT_VARIANT")) e->dot_variant = atoi(v);
     if (const char* v = getenv("GMRM_DOT_DEBUG")) e->dot_debug = atoi(v);
-    e->dot_kernel = c->T == 1 ? 1 : 0;
+    e->dot_kernel = 0;     // GMRM_DOT_KERNEL=1 selects the table-lookup kernel (kept as a measured alternative)
     if (const char* v = getenv("GMRM_DOT_KERNEL")) e->dot_kernel = atoi(v);
     e->phen_set.assign(c->T, 0);
     e->h_nonas.assign(c->T, 0);
@@ -207,7 +207,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->group_loc.alloc(e->Mloc)); A(e->mtotgrp.alloc(G));
     A(e->cva.alloc((size_t)G * K)); A(e->cvai.alloc((size_t)G * K));
     A(e->steptab.alloc((size_t)e->Mm * e->Vl));
-    A(e->partial.alloc((size_t)e->Vl * T * L.nsm * 4));
+    A(e->partial.alloc((size_t)e->Vl * T * L.nsm * 16));
     A(e->spart.alloc((size_t)T * L.nsm));
     A(e->pub.alloc((size_t)e->Vl * T));
     A(e->cass.alloc((size_t)T * G * K)); A(e->m0.alloc((size_t)T * G));
@@ -440,7 +440,7 @@ static int trait_chunk(int E) {
 
 // partial sums per (marker, trait) that the sampler adds up: one per CTA for the table kernel, one per
 // CTA and sub-partition for the shift+DFMA kernel
-static int dot_nsl(const gmrm_engine* e) { return e->dot_kernel == 1 ? e->L.nsm : e->L.nsm * 4; }
+static int dot_nsl(const gmrm_engine* e) { return e->dot_kernel == 1 ? e->L.nsm * dot_table_passes(e->L) : e->L.nsm * 4; }
 
 static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* partial) {
     const int T = e->cfg.T, tc = trait_chunk(e->L.E);
@@ -448,7 +448,7 @@ static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* parti
         for (int t = 0; t < T; t++) {
             DotParams p{};
             p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
-            p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm; p.Ttot = T; p.t0 = t;
+            p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = dot_nsl(e); p.Ttot = T; p.t0 = t;
             if (launch_dot_table(e->L, p, e->stream) != 0)
                 return fail(GMRM_ECUDA, "table dot kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
@@ -486,7 +486,7 @@ int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, doubl
     const int T = e->cfg.T;
     DevBuf<int32_t> cols; DevBuf<double> partial, res;
     int rc = cols.alloc(n); if (rc) return rc;
-    rc = partial.alloc((size_t)n * T * e->L.nsm * 4); if (rc) return rc;
+    rc = partial.alloc((size_t)n * T * e->L.nsm * 16); if (rc) return rc;
     rc = res.alloc((size_t)n * T); if (rc) return rc;
     CU(cudaMemcpyAsync(cols.p, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     launch_eps_offset(e->eps.p, e->namask2.p, e->L, T, nullptr, nullptr, e->spart.p, e->stream);   // refresh per-tile sums

@@ -504,6 +504,7 @@ __global__ void __launch_bounds__((4 * WPS + 1) * 32, 1) dot_kernel(const DotPar
 constexpr int kTabWarps = 16;
 constexpr int kTabThreads = kTabWarps * 32;
 constexpr int kTabMaxCW = 28;      // words per chunk: 28 * 4 bytes * 2 KB of table = 224 KB
+constexpr int kTabBatch = 16;      // markers per warp batch (loads in flight per warp, width of the butterfly)
 
 struct TabGeom { int cw, cwp, npass; };
 __host__ __device__ inline TabGeom tab_geom(int tile_bytes) {
@@ -524,14 +525,20 @@ __global__ void __launch_bounds__(kTabThreads, 1) dot_table_kernel(const DotPara
     const TabGeom G = tab_geom(TILE);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int RS = 4 * G.cwp;                                // doubles between consecutive byte values
-    const int nbat = (p.V + 7) / 8;
+    constexpr int B = kTabBatch;
+    const int nbat = (p.V + B - 1) / B;
     const double* eps = p.eps + (int64_t)p.t0 * p.npad;
     const uint32_t tab_u32 = smem_u32(tab);
-    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
-    const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);   // marker of the batch this lane ends up holding
+    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4, hi2 = lane & 2;
+    // marker of the batch whose total this lane holds after the butterfly
+    const int own = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
     for (int pass = 0; pass < G.npass; pass++) {
-        const int w0 = pass * G.cw;                          // first word of this chunk inside the tile
+        // unit u = (tile, chunk) handled by this CTA in this pass: neighbouring CTAs take neighbouring chunks
+        // of the same tile, so that in one pass the grid reads one contiguous run of every column
+        const int u = pass * gridDim.x + blockIdx.x;
+        const int tile = u / G.npass, chunk = u % G.npass;
+        const int w0 = chunk * G.cw;                         // first word of this chunk inside the tile
         const int cw = min(G.cw, TILE / 4 - w0);             // words in this chunk
         if (pass) __syncthreads();                           // everyone is done with the previous tables
         // ---- build: 4 threads per (byte position) quad, 64 byte values each
@@ -540,7 +547,7 @@ __global__ void __launch_bounds__(kTabThreads, 1) dot_table_kernel(const DotPara
             const int wl = quad >> 2, j = quad & 3;          // word (lane) and byte inside the word
             int ls, bb;
             tile_offset_to_slot_byte(E4, (w0 + wl) * 4 + j, ls, bb);
-            const double* e = eps + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E + 4 * bb;
+            const double* e = eps + ((int64_t)tile * kLanesPerTile + ls) * E + 4 * bb;
             const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
             double p01[16];
 #pragma unroll
@@ -557,61 +564,66 @@ __global__ void __launch_bounds__(kTabThreads, 1) dot_table_kernel(const DotPara
         __syncthreads();
 
         // ---- stream the chunk of all V columns through the tables
-        const uint8_t* chunk0 = p.bed + (int64_t)blockIdx.x * TILE + (int64_t)w0 * 4 + lane * 4;
+        const uint8_t* chunk0 = p.bed + (int64_t)tile * TILE + (int64_t)w0 * 4 + lane * 4;
         const bool active = lane < cw;
+        // inactive lanes (word 0 -> table[0] == 0) are parked on columns whose banks the active lanes of their
+        // half-warp do not use
+        const int colw = active ? lane : (lane & 15) % (cw < 16 ? cw : 16);
         uint32_t lb[4];                                      // shared-memory byte address of table[0][j][lane]
 #pragma unroll
-        for (int j = 0; j < 4; j++) lb[j] = tab_u32 + (uint32_t)((j * G.cwp + lane) * 8);
+        for (int j = 0; j < 4; j++) lb[j] = tab_u32 + (uint32_t)((j * G.cwp + colw) * 8);
         const uint32_t bstride = (uint32_t)(RS * 8);
 
-        uint32_t wn[8];
+        uint32_t wn[B];
         auto fetch = [&](int bi) {
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
-                const int r = bi * 8 + jj;
+            for (int jj = 0; jj < B; jj++) {
+                const int r = bi * B + jj;
                 const int col = r < p.V ? p.cols[r] : -1;
-                wn[jj] = (active && col >= 0) ? *reinterpret_cast<const uint32_t*>(chunk0 + (int64_t)col * p.col_stride) : 0u;
+                wn[jj] = (active && col >= 0) ? __ldg(reinterpret_cast<const uint32_t*>(chunk0 + (int64_t)col * p.col_stride)) : 0u;
             }
         };
         if (warp < nbat) fetch(warp);
         for (int bi = warp; bi < nbat; bi += kTabWarps) {
-            uint32_t w[8];
+            uint32_t w[B];
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) w[jj] = wn[jj];
+            for (int jj = 0; jj < B; jj++) w[jj] = wn[jj];
             if (bi + kTabWarps < nbat) fetch(bi + kTabWarps);          // prefetch the next batch of this warp
-            double a[8];
+            double a[B];
 #pragma unroll
-            for (int jj = 0; jj < 8; jj++) {
+            for (int jj = 0; jj < B; jj++) {
                 double v0, v1, v2, v3;
                 asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(lb[0] + (w[jj] & 0xffu) * bstride));
                 asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(lb[1] + ((w[jj] >> 8) & 0xffu) * bstride));
                 asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(lb[2] + ((w[jj] >> 16) & 0xffu) * bstride));
                 asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(lb[3] + (w[jj] >> 24) * bstride));
-                a[jj] = active ? (v0 + v1) + (v2 + v3) : 0.0;
+                a[jj] = (v0 + v1) + (v2 + v3);               // inactive lanes hold word 0: table[0] == 0
             }
-            // transposed butterfly over the 8 markers of the batch (fixed order: reproducible)
-            double b4[4], b2[2], b1;
+            // transposed butterfly over the 16 markers of the batch (fixed order: reproducible)
+            double b8[8], b4[4], b2[2], b1;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const double send = hi16 ? a[i] : a[i + 8], keep = hi16 ? a[i + 8] : a[i];
+                b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const double send = hi16 ? a[i] : a[i + 4], keep = hi16 ? a[i + 4] : a[i];
-                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                const double send = hi8 ? b8[i] : b8[i + 4], keep = hi8 ? b8[i + 4] : b8[i];
+                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
 #pragma unroll
             for (int i = 0; i < 2; i++) {
-                const double send = hi8 ? b4[i] : b4[i + 2], keep = hi8 ? b4[i + 2] : b4[i];
-                b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                const double send = hi4 ? b4[i] : b4[i + 2], keep = hi4 ? b4[i + 2] : b4[i];
+                b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
             {
-                const double send = hi4 ? b2[0] : b2[1], keep = hi4 ? b2[1] : b2[0];
-                b1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                const double send = hi2 ? b2[0] : b2[1], keep = hi2 ? b2[1] : b2[0];
+                b1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
-            b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-            const int r = bi * 8 + own;
-            if ((lane & 3) == 0 && r < p.V) {
-                double* dst = p.partial + ((int64_t)r * p.Ttot + p.t0) * p.nsl + blockIdx.x;
-                *dst = pass ? *dst + b1 : b1;
-            }
+            const int r = bi * B + own;
+            if ((lane & 1) == 0 && r < p.V)                  // one slot per unit: plain stores, no read-modify-write
+                p.partial[((int64_t)r * p.Ttot + p.t0) * p.nsl + u] = b1;
         }
     }
 }
@@ -1010,7 +1022,8 @@ static int dot_table_launch_t(const DotParams& p, const Layout& L, cudaStream_t 
     dot_table_kernel<E4><<<L.nsm, kTabThreads, smem, s>>>(p, L);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
-// one trait (p.t0) per launch; partial[r][t][cta] with p.nsl == nsm
+// one trait (p.t0) per launch; partial[r][t][unit] with p.nsl == nsm * passes
+int dot_table_passes(const Layout& L) { return tab_geom(L.tile_bytes).npass; }
 int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s) {
     int rc = -1;
     GMRM_DISPATCH_E4(L.E4, (rc = dot_table_launch_t<E4>(p, L, s)));

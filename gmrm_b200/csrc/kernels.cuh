@@ -105,6 +105,7 @@ void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
 int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s);
 int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s);
+int dot_table_passes(const Layout& L);
 void launch_sample(const SampleParams& p, cudaStream_t s);
 int launch_update(const Layout& L, const UpdateParams& p, cudaStream_t s);
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s);
