@@ -118,7 +118,7 @@ struct gmrm_engine {
 
     DevBuf<uint8_t> bed, namask2, stage;
     DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old, zeros;
-    DevBuf<double> delta, delta_tot;
+    DevBuf<double> delta, delta_tot, gc;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
     DevBuf<uint32_t> miss_off, miss_idx;
     DevBuf<PubEntry> pub;
@@ -213,7 +213,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->cass.alloc((size_t)T * G * K)); A(e->m0.alloc((size_t)T * G));
     A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T));
     A(e->sigmag.alloc((size_t)T * G)); A(e->sigmae.alloc(T)); A(e->pi.alloc((size_t)T * G * K));
-    A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T));
+    A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T)); A(e->gc.alloc((size_t)T * G * 4 * K));
     A(e->zeros.alloc((size_t)kDotMaxThreads * kDotMaxBatch));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
     A(e->miss_off.alloc((size_t)e->Mloc + 1));
@@ -472,7 +472,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.cva = e->cva.p; p.cvai = e->cvai.p; p.sigmag = e->sigmag.p; p.sigmae = e->sigmae.p;
-    p.pi = e->pi.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
+    p.pi = e->pi.p; p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }
 
@@ -644,9 +644,9 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         (void)d_small;
     }
 
-    if (e->timing_detail && e->dot_ev.size() < (size_t)2 * Mm) {
+    if (e->timing_detail && e->dot_ev.size() < (size_t)4 * Mm) {
         const size_t old = e->dot_ev.size();
-        e->dot_ev.resize((size_t)2 * Mm);
+        e->dot_ev.resize((size_t)4 * Mm);
         for (size_t i = old; i < e->dot_ev.size(); i++) CU(cudaEventCreate(&e->dot_ev[i]));
     }
 
@@ -658,25 +658,28 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     launch_mu_draw(mp, s);
     launch_eps_offset(e->eps.p, e->namask2.p, L, T, e->mu_old.p, e->mu.p, e->spart.p, s);
     launch_steptab(e->steptab.p, Mm, Vl, e->r0, R, c.Mt, e->marker_begin, c.shuffle, c.seed, it, d_perm, s);
+    launch_group_consts(T, G, K, c.N, e->sigmag.p, e->sigmae.p, e->pi.p, e->cva.p, e->cvai.p, e->nonas.p, e->gc.p, s);
     CU(cudaMemsetAsync(e->cass.p, 0, e->cass.n * 4, s));
     CU(cudaMemsetAsync(e->npub.p, 0, 8, s));
-    launches += 3;
+    launches += 4;
 
     // ---- marker loop (bayes.cpp:375-555)
     CU(cudaEventRecord(e->ev[1], s));
     const bool multi = c.world_size > 1;
     for (int st = 0; st < Mm; st++) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[2 * st], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st], s));
         if ((rc = launch_dots(e, cols, Vl, e->partial.p))) return rc;
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[2 * st + 1], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 1], s));
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
         launch_sample(sp, s);
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 2], s));
         UpdateParams up{};
         up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
         up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
         if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 3], s));
         launches += (e->dot_kernel == 1 ? T : (T + trait_chunk(L.E) - 1) / trait_chunk(L.E)) + 2;
         if (multi) return fail(GMRM_EINVAL, "multi-GPU exchange not wired yet");
     }
@@ -703,12 +706,16 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     CU(cudaEventElapsedTime(&ms_loop, e->ev[1], e->ev[2]));
     CU(cudaEventElapsedTime(&ms_all, e->ev[0], e->ev[3]));
     e->last.marker_loop_ms = ms_loop; e->last.iteration_ms = ms_all; e->last.launches = launches; e->last.steps = Mm; e->last.published = hpub;
-    e->last.dot_kernel_ms = 0.0;
+    e->last.dot_kernel_ms = 0.0; e->last.sample_kernel_ms = 0.0; e->last.update_kernel_ms = 0.0;
     if (e->timing_detail)
         for (int st = 0; st < Mm; st++) {
             float ms = 0;
-            CU(cudaEventElapsedTime(&ms, e->dot_ev[2 * st], e->dot_ev[2 * st + 1]));
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st], e->dot_ev[4 * st + 1]));
             e->last.dot_kernel_ms += ms;
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st + 1], e->dot_ev[4 * st + 2]));
+            e->last.sample_kernel_ms += ms;
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st + 2], e->dot_ev[4 * st + 3]));
+            e->last.update_kernel_ms += ms;
         }
     if (herr != 0) {
         CU(cudaMemset(e->err.p, 0, 4));

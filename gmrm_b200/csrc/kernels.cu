@@ -637,10 +637,22 @@ struct DotPieces { double dpa, dpb; };
 __device__ __forceinline__ DotPieces finish_dot(const SampleParams& p, int r, int col, int t, int lane) {
     const double* part = p.partial + ((int64_t)r * p.T + t) * p.nsl;
     double s = 0.0;
-    for (int i = lane; i < p.nsl; i += 32) s += part[i];
+    for (int i0 = lane; i0 < p.nsl; i0 += 32 * 8) {          // 8 independent loads per round, fixed summation order
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = i0 + 32 * j < p.nsl ? part[i0 + 32 * j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) s += x[j];
+    }
     const double coded = warp_sum_fixed(s);                 // sum d*eps with missing coded 3
     double sa = 0.0;
-    for (int i = lane; i < p.nsm; i += 32) sa += p.spart[(int64_t)t * p.nsm + i];
+    for (int i0 = lane; i0 < p.nsm; i0 += 32 * 8) {
+        double x[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) x[j] = i0 + 32 * j < p.nsm ? p.spart[(int64_t)t * p.nsm + i0 + 32 * j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) sa += x[j];
+    }
     const double sall = warp_sum_fixed(sa);                 // sum eps over all slots
     double sm = 0.0;
     const uint32_t m0 = p.miss_off[col], m1 = p.miss_off[col + 1];
@@ -650,6 +662,36 @@ __device__ __forceinline__ DotPieces finish_dot(const SampleParams& p, int r, in
     d.dpa = coded - 3.0 * smiss;     // a = 0 at missing (lut_a)
     d.dpb = sall - smiss;            // b = 0 at missing (lut_b)
     return d;
+}
+
+// Per-(trait, group) pieces of the sampler that do not depend on the marker (bayes.cpp:403-405,413-416,
+// 429-431), evaluated once per iteration instead of once per marker:
+//   gc[0..K)   denom[k-1] = (N-1) + sige_g * cvai[k]            (k >= 1; slot 0 holds inv2sige)
+//   gc[K..2K)  log(pi[k])
+//   gc[2K..3K) -0.5 * log(sigg_e * (nonas-1) * cva[k] + 1)        (k >= 1)
+//   gc[3K..4K) sqrt(sigmae / denom[k-1])                          (k >= 1; sd of the beta draw, bayes.cpp:456)
+__global__ void group_consts_kernel(int T, int G, int K, int N, const double* __restrict__ sigmag, const double* __restrict__ sigmae,
+                                    const double* __restrict__ pi, const double* __restrict__ cva, const double* __restrict__ cvai,
+                                    const int32_t* __restrict__ nonas, double* __restrict__ gc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * G) return;
+    const int t = i / G, g = i % G;
+    double* o = gc + (int64_t)i * 4 * K;
+    const double sigg = sigmag[i], sige = sigmae[t];
+    if (sigg == 0.0) { for (int k = 0; k < 4 * K; k++) o[k] = 0.0; return; }
+    const double sige_g = sige / sigg;                       // 403
+    const double sigg_e = 1.0 / sige_g;                      // 404
+    o[0] = 1.0 / (2.0 * sige);                               // 405 inv2sige
+    for (int k = 0; k < K; k++) {
+        o[K + k] = log(pi[(int64_t)i * K + k]);              // 429
+        if (k > 0) {
+            const double denom = (double)(N - 1) + sige_g * cvai[g * K + k];                       // 414
+            o[k] = denom;
+            o[2 * K + k] = -0.5 * log(sigg_e * (double)(nonas[t] - 1) * cva[g * K + k] + 1.0);     // 431
+            o[3 * K + k] = sqrt(sige / denom);
+        }
+    }
+    o[2 * K] = 0.0; o[3 * K] = 0.0;
 }
 
 __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
@@ -690,8 +732,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
         }
         return draw_normal(p.seed, STREAM_SAMPLER_N, (uint32_t)p.it, mglo, (uint32_t)t);
     };
-    const MarkerDraw d = sample_marker(dot_raw, p.betas[mi], p.sigmae[t], sigg, p.cva + grp * p.K, p.cvai + grp * p.K,
-                                       p.pi + ((int64_t)t * p.G + grp) * p.K, p.K, p.N, p.nonas[t], u, zdraw);
+    const MarkerDraw d = sample_marker_pre(dot_raw, p.betas[mi], sigg, p.gc + ((int64_t)t * p.G + grp) * 4 * p.K, p.K, p.nonas[t], u, zdraw);
     p.betas[mi] = d.beta_new;
     if (d.comp >= 0) {
         p.comp[mi] = d.comp;                                               // bayes.cpp:462
@@ -726,64 +767,102 @@ __global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, 
 // memory in a fixed order (reproducible), masked by the NA mask and added to eps; the per-tile sum of
 // eps that K2 needs is refreshed on the way.
 // =====================================================================================
+struct UpdEntry {           // one published marker, staged in shared memory
+    double v[4];            // increment by genotype code: (a - mave*b) * dbeta*msig for dosage 0,1,2; 0 where missing
+};
+
 template <int E4>
 __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdateParams p, Layout L) {
     constexpr int E = 4 * E4;
     constexpr int EK = E / kUpdSplit;                 // individuals of a slot one thread finalises (E is a multiple of 4)
     extern __shared__ __align__(16) uint8_t usmem[];
     double* dlt = reinterpret_cast<double*>(usmem);                                  // [kUpdSplit][E][128]
-    int32_t* plist = reinterpret_cast<int32_t*>(usmem + sizeof(double) * kUpdSplit * E * kLanesPerTile);   // published ranks, ascending
+    UpdEntry* ent = reinterpret_cast<UpdEntry*>(usmem + sizeof(double) * kUpdSplit * E * kLanesPerTile);
+    int32_t* ecol = reinterpret_cast<int32_t*>(ent + kUpdCap);                        // column of each staged entry
     __shared__ int npub;
+    __shared__ int wcnt[kUpdCap / 32];
     __shared__ double red[kUpdThreads / 32];
     const int t = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sp = warp & 3, u = warp >> 2, ls = sp * 32 + lane;
-
-    if (threadIdx.x < 32) {                          // ordered compaction by warp 0
-        int n = 0;
-        for (int v0 = 0; v0 < p.V; v0 += 32) {
-            const int v = v0 + lane;
-            const bool on = v < p.V && p.pub[(int64_t)v * p.T + t].lam != 0.0;
-            const uint32_t m = __ballot_sync(0xffffffffu, on);
-            if (on) plist[n + __popc(m & ((1u << lane) - 1u))] = v;
-            n += __popc(m);
-        }
-        if (lane == 0) npub = n;
-    }
-    __syncthreads();
-    const int n = npub;
-    if (n == 0) return;                              // nothing published for this trait: eps and its sums stand
-
     const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * L.tile_bytes;
+    const uint32_t ent_u32 = smem_u32(ent);
+
     double d[E];
 #pragma unroll
     for (int k = 0; k < E; k++) d[k] = 0.0;
+    bool any = false;
 
-    SlotRegs<E4> g[kUpdPF], gn[kUpdPF];
-    const int mine = (n - u + kUpdSplit - 1) / kUpdSplit;      // markers i = u, u + S, u + 2S, ...
-    auto fetch = [&](SlotRegs<E4>* dst, int c0) {
+    // rounds of kUpdCap virtual ranks: their published entries (rank order) fit the staging area
+    for (int v_lo = 0; v_lo < p.V; v_lo += kUpdCap) {
+        const int v_hi = min(p.V, v_lo + kUpdCap);
+        __syncthreads();
+        // ordered compaction of the round's published entries by the whole CTA: thread tid looks at virtual
+        // ranks v_lo + tid + i*kUpdThreads (all loads in flight at once), warp counts are scanned through
+        // shared memory, rank order is preserved
+        constexpr int NI = kUpdCap / kUpdThreads;
+        PubEntry pe[NI];
+        uint32_t bal[NI];
 #pragma unroll
-        for (int j = 0; j < kUpdPF; j++)
-            if (c0 + j < mine) dst[j].load(tile0 + (int64_t)p.cols[plist[u + (c0 + j) * kUpdSplit]] * p.col_stride, ls);
-    };
-    fetch(gn, 0);
-    for (int c0 = 0; c0 < mine; c0 += kUpdPF) {
+        for (int i = 0; i < NI; i++) {
+            const int v = v_lo + i * kUpdThreads + threadIdx.x;
+            pe[i] = v < v_hi ? p.pub[(int64_t)v * p.T + t] : PubEntry{0.0, 0.0};
+        }
 #pragma unroll
-        for (int j = 0; j < kUpdPF; j++) g[j] = gn[j];
-        fetch(gn, c0 + kUpdPF);                                  // prefetch the next chunk
+        for (int i = 0; i < NI; i++) {
+            bal[i] = __ballot_sync(0xffffffffu, pe[i].lam != 0.0);
+            if (lane == 0) wcnt[i * (kUpdThreads / 32) + warp] = __popc(bal[i]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int i = 0; i < NI * (kUpdThreads / 32); i++) { const int c = wcnt[i]; wcnt[i] = acc; acc += c; }
+            npub = acc;
+        }
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < kUpdPF; j++) {
-            if (c0 + j >= mine) break;
-            const PubEntry pe = p.pub[(int64_t)plist[u + (c0 + j) * kUpdSplit] * p.T + t];
-            // reference arithmetic: (mdb*b + a) * bs_  with mdb = -mave, bs_ = dbeta*msig; 0 where missing
-            const double mdb = -pe.mave;
-            const double v0 = (mdb * 1.0 + 0.0) * pe.lam, v1 = (mdb * 1.0 + 1.0) * pe.lam, v2 = (mdb * 1.0 + 2.0) * pe.lam;
+        for (int i = 0; i < NI; i++) {
+            if (pe[i].lam != 0.0) {
+                const int idx = wcnt[i * (kUpdThreads / 32) + warp] + __popc(bal[i] & ((1u << lane) - 1u));
+                // reference arithmetic: (mdb*b + a) * bs_  with mdb = -mave, bs_ = dbeta*msig (phenotype.cpp:328-329,388)
+                const double mdb = -pe[i].mave;
+                ent[idx].v[0] = (mdb * 1.0 + 0.0) * pe[i].lam;
+                ent[idx].v[1] = (mdb * 1.0 + 1.0) * pe[i].lam;
+                ent[idx].v[2] = (mdb * 1.0 + 2.0) * pe[i].lam;
+                ent[idx].v[3] = 0.0;                 // missing: a = b = 0
+                ecol[idx] = p.cols[v_lo + i * kUpdThreads + threadIdx.x];
+            }
+        }
+        __syncthreads();
+        const int n = npub;
+        if (n == 0) continue;
+        any = true;
+
+        SlotRegs<E4> g[kUpdPF], gn[kUpdPF];
+        const int mine = (n - u + kUpdSplit - 1) / kUpdSplit;      // entries i = u, u + S, u + 2S, ...
+        auto fetch = [&](SlotRegs<E4>* dst, int c0) {
 #pragma unroll
-            for (int k = 0; k < E; k++) {
-                const uint32_t c = g[j].field(k);
-                d[k] += c == 0 ? v0 : c == 1 ? v1 : c == 2 ? v2 : 0.0;
+            for (int j = 0; j < kUpdPF; j++)
+                if (c0 + j < mine) dst[j].load(tile0 + (int64_t)ecol[u + (c0 + j) * kUpdSplit] * p.col_stride, ls);
+        };
+        fetch(gn, 0);
+        for (int c0 = 0; c0 < mine; c0 += kUpdPF) {
+#pragma unroll
+            for (int j = 0; j < kUpdPF; j++) g[j] = gn[j];
+            fetch(gn, c0 + kUpdPF);                                  // prefetch the next chunk
+#pragma unroll
+            for (int j = 0; j < kUpdPF; j++) {
+                if (c0 + j >= mine) break;
+                const uint32_t eb = ent_u32 + (uint32_t)((u + (c0 + j) * kUpdSplit) * sizeof(UpdEntry));
+#pragma unroll
+                for (int k = 0; k < E; k++) {
+                    double val;                      // v[code]: one shared-memory read (4 addresses: broadcast, no conflict)
+                    asm("ld.shared.f64 %0, [%1];" : "=d"(val) : "r"(eb + g[j].field(k) * 8u));
+                    d[k] += val;
+                }
             }
         }
     }
+    if (!__syncthreads_or(any)) return;              // nothing published for this trait: eps and its sums stand
 #pragma unroll
     for (int k = 0; k < E; k++) dlt[((int64_t)u * E + k) * kLanesPerTile + ls] = d[k];
     __syncthreads();
@@ -792,14 +871,16 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdatePara
     SlotRegs<E4> na;
     na.load(p.namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
     double* ep = p.eps + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
-    double s = 0.0;
+    double s = 0.0, ev[EK];
+#pragma unroll
+    for (int kk = 0; kk < EK; kk++) ev[kk] = ep[u * EK + kk];    // all loads in flight before the first use
 #pragma unroll
     for (int kk = 0; kk < EK; kk++) {
         const int k = u * EK + kk;
         double inc = 0.0;
 #pragma unroll
         for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * E + k) * kLanesPerTile + ls];
-        double e = ep[k];
+        double e = ev[kk];
         if (na.field(k)) e += inc;                   // * na  (phenotype.cpp:388)
         ep[k] = e;
         s += e;
@@ -1041,7 +1122,7 @@ void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
 
 template <int E4>
 static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t s) {
-    const int smem = (int)sizeof(double) * kUpdSplit * 4 * E4 * kLanesPerTile + p.V * (int)sizeof(int32_t);
+    const int smem = (int)sizeof(double) * kUpdSplit * 4 * E4 * kLanesPerTile + kUpdCap * (int)(sizeof(UpdEntry) + sizeof(int32_t));
     static int attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         if (cudaFuncSetAttribute(update_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
@@ -1071,6 +1152,10 @@ void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, 
         attr = smem;
     }
     beta_sq_kernel<<<T, 256, smem, s>>>(betas, group, Mloc, G, out);
+}
+void launch_group_consts(int T, int G, int K, int N, const double* sigmag, const double* sigmae, const double* pi, const double* cva,
+                         const double* cvai, const int32_t* nonas, double* gc, cudaStream_t s) {
+    group_consts_kernel<<<(T * G + 127) / 128, 128, 0, s>>>(T, G, K, N, sigmag, sigmae, pi, cva, cvai, nonas, gc);
 }
 void launch_global_draw(const GlobalDrawParams& p, cudaStream_t s) { global_draw_kernel<<<1, 32, 0, s>>>(p); }
 void launch_mu_draw(const MuDrawParams& p, cudaStream_t s) { mu_draw_kernel<<<1, 32, 0, s>>>(p); }

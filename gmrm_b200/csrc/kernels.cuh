@@ -18,6 +18,7 @@ __host__ __device__ constexpr int dot_ring_tiles(int wps) { return wps == 3 ? 48
 constexpr int kDotMaxThreads = 17 * 32; // 4 consumer warps per sub-partition + 1 producer warp, the widest variant
 constexpr int kDotMaxBatch = 8;
 constexpr int kUpdSplit = 4;                              // warps per sub-partition in the update kernel
+constexpr int kUpdCap = 2048;                             // virtual ranks staged per round of the update kernel
 constexpr int kUpdPF = 4;                                 // columns each update warp prefetches ahead
 constexpr int kUpdThreads = kLanesPerTile * kUpdSplit;
 
@@ -67,6 +68,7 @@ struct SampleParams {
     const double* sigmag;    // [T][G]
     const double* sigmae;    // [T]
     const double* pi;        // [T][G*K]
+    const double* gc;        // [T][G][4K] per-iteration sampler constants (group_consts_kernel)
     const int32_t* nonas;    // [T]
     int32_t* cass;           // [T][G*K]
     PubEntry* pub;           // [V][T]
@@ -125,6 +127,8 @@ struct GlobalDrawParams {
     int32_t* err;
 };
 void launch_global_draw(const GlobalDrawParams& p, cudaStream_t s);
+void launch_group_consts(int T, int G, int K, int N, const double* sigmag, const double* sigmae, const double* pi, const double* cva,
+                         const double* cvai, const int32_t* nonas, double* gc, cudaStream_t s);
 
 struct MuDrawParams {
     int32_t T, it; uint32_t seed;

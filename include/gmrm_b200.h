@@ -85,6 +85,8 @@ typedef struct {
     double marker_loop_ms;   /* device time of the marker loop of the last iteration (CUDA events)   */
     double iteration_ms;     /* device time of the whole last iteration                               */
     double dot_kernel_ms;    /* summed device time of the dot kernel launches (only if timing detail on) */
+    double sample_kernel_ms; /* same for the sampler kernel                                                   */
+    double update_kernel_ms; /* same for the residual-update kernel                                           */
     int64_t launches;        /* kernels launched by the last iteration                                */
     int64_t steps;           /* marker-steps of the last iteration                                    */
     int64_t published;       /* marker updates with dbeta != 0 in the last iteration (this shard)     */
