@@ -678,21 +678,36 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         UpdateParams up{};
         up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
         up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
+        up.delta = multi ? e->delta.p : nullptr;
         if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 3], s));
         launches += (e->dot_kernel == 1 ? T : (T + trait_chunk(L.E) - 1) / trait_chunk(L.E)) + 2;
-        if (multi) return fail(GMRM_EINVAL, "multi-GPU exchange not wired yet");
+        // ---- exchange (bayes.cpp:495-553): every sync_rate steps the shards all-reduce what they changed
+        if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+            NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
+            launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, e->spart.p, s);
+            launches += 2;
+        }
     }
     CU(cudaEventRecord(e->ev[2], s));
 
     // ---- epilogue (bayes.cpp:562-651)
     launch_beta_sq(e->betas.p, e->group_loc.p, e->Mloc, T, G, e->bsq.p, s);
+    if (multi) {   // Allreduce of beta_sqn and cass (bayes.cpp:575-588)
+        NC(g_nccl.AllReduce(e->bsq.p, e->bsq.p, (size_t)T * G, kNcclFloat64, kNcclSum, e->comm, s));
+        NC(g_nccl.AllReduce(e->cass.p, e->cass.p, (size_t)T * G * K, kNcclInt32, kNcclSum, e->comm, s));
+    }
     launch_eps_sumsq(e->eps.p, L.npad, c.N, T, e->esq.p, s);
     GlobalDrawParams gp{};
     gp.T = T; gp.G = G; gp.K = K; gp.N = c.N; gp.it = it; gp.seed = c.seed; gp.mtotgrp = e->mtotgrp.p; gp.bsq = e->bsq.p;
     gp.cass = e->cass.p; gp.esq = e->esq.p; gp.sigmag = e->sigmag.p; gp.sigmae = e->sigmae.p; gp.pi = e->pi.p; gp.m0 = e->m0.p;
     gp.rep_sigg_unit = d_sigg; gp.rep_pi_unit = d_piu; gp.rep_sige_unit = d_sige; gp.err = e->err.p;
     launch_global_draw(gp, s);
+    if (multi) {   // Bcast of shard 0's sigmaG, sigmaE, pi (bayes.cpp:626,638,649)
+        NC(g_nccl.Broadcast(e->sigmag.p, e->sigmag.p, (size_t)T * G, kNcclFloat64, 0, e->comm, s));
+        NC(g_nccl.Broadcast(e->sigmae.p, e->sigmae.p, (size_t)T, kNcclFloat64, 0, e->comm, s));
+        NC(g_nccl.Broadcast(e->pi.p, e->pi.p, (size_t)T * G * K, kNcclFloat64, 0, e->comm, s));
+    }
     launches += 3;
     CU(cudaEventRecord(e->ev[3], s));
     CU(cudaGetLastError());

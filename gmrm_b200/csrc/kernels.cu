@@ -304,6 +304,28 @@ __global__ void __launch_bounds__(kLanesPerTile) eps_offset_kernel(double* __res
     if (threadIdx.x == 0) spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
 }
 
+// Multi-GPU exchange (replaces the per-marker Allgatherv + local recompute of bayes.cpp:500-547): after the
+// all-reduce of the shards' residual deltas, add what the OTHER shards changed, clear the local delta, refresh
+// the per-tile sums.
+template <int E4>
+__global__ void __launch_bounds__(kLanesPerTile) eps_merge_kernel(double* __restrict__ eps, double* __restrict__ loc,
+                                                                 const double* __restrict__ tot, Layout L, double* __restrict__ spart) {
+    constexpr int E = 4 * E4;
+    const int t = blockIdx.y;
+    __shared__ double red[kLanesPerTile / 32];
+    const int64_t base = (int64_t)t * L.npad + ((int64_t)blockIdx.x * kLanesPerTile + threadIdx.x) * E;
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < E; k++) {
+        const double v = eps[base + k] + (tot[base + k] - loc[base + k]);
+        eps[base + k] = v;
+        loc[base + k] = 0.0;
+        s += v;
+    }
+    const double r = block_sum_fixed(s, red);
+    if (threadIdx.x == 0) spart[(int64_t)t * L.nsm + blockIdx.x] = r;
+}
+
 // sum_{i<n} eps_i^2 per trait (Phenotype::epsilon_sumsqr, phenotype.cpp:251-261)
 __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restrict__ eps, int64_t npad, int64_t n, double* __restrict__ out) {
     __shared__ double red[32];
@@ -871,6 +893,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdatePara
     SlotRegs<E4> na;
     na.load(p.namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
     double* ep = p.eps + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
+    double* dp = p.delta ? p.delta + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E : nullptr;
     double s = 0.0, ev[EK];
 #pragma unroll
     for (int kk = 0; kk < EK; kk++) ev[kk] = ep[u * EK + kk];    // all loads in flight before the first use
@@ -881,7 +904,10 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdatePara
 #pragma unroll
         for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * E + k) * kLanesPerTile + ls];
         double e = ev[kk];
-        if (na.field(k)) e += inc;                   // * na  (phenotype.cpp:388)
+        if (na.field(k)) {                           // * na  (phenotype.cpp:388)
+            e += inc;
+            if (dp) dp[k] += inc;                    // multi-GPU: what this shard changed since the last exchange
+        }
         ep[k] = e;
         s += e;
     }
@@ -1045,6 +1071,14 @@ static void eps_offset_t(double* eps, const uint8_t* namask2, const Layout& L, i
 void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
                        const double* mu_new, double* spart, cudaStream_t s) {
     GMRM_DISPATCH_E4(L.E4, (eps_offset_t<E4>(eps, namask2, L, T, mu_old, mu_new, spart, s)));
+}
+template <int E4>
+static void eps_merge_t(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s) {
+    dim3 grid((unsigned)L.nsm, (unsigned)T);
+    eps_merge_kernel<E4><<<grid, kLanesPerTile, 0, s>>>(eps, loc, tot, L, spart);
+}
+void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s) {
+    GMRM_DISPATCH_E4(L.E4, (eps_merge_t<E4>(eps, loc, tot, L, T, spart, s)));
 }
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);

@@ -89,6 +89,7 @@ struct UpdateParams {
     double* eps;             // [T][npad]
     int64_t npad;
     double* spart;           // [T][nsm]
+    double* delta;           // [T][npad] or nullptr: accumulates the applied increments (multi-GPU exchange)
     int32_t exact;           // 1: always use the reference-order arithmetic
 };
 
@@ -104,6 +105,7 @@ void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t*
                   double* mave, double* msig, cudaStream_t s);
 void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
                        const double* mu_new, double* spart, cudaStream_t s);
+void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
 int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s);
 int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s);

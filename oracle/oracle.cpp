@@ -90,6 +90,7 @@ struct Gibbs {
     std::vector<int> S, M;                       // per rank block (bayes.cpp:903-925)
     std::vector<std::vector<RankTrait>> rt;      // [R][T]
     std::vector<std::vector<double>> eps;        // [nrep*T][im4*4]
+    std::vector<std::vector<double>> dl;         // [nrep*T][im4*4] pending residual deltas (sync_rate > 1)
     std::vector<std::vector<double>> mave, msig; // [T][Mt]
     std::vector<double> cvai;                    // [G*K]
     std::vector<int> mtotgrp;                    // [G]
@@ -368,15 +369,44 @@ int Gibbs::run() {
             }
             // exchange + Bayes::update_epsilon, bayes.cpp:495-553, 681-706: every replica applies every
             // published update, in rank order, per trait only where that trait's dbeta != 0
-            for (int rep = 0; rep < c.nrep; rep++)
+            if (c.sync_rate == 1) {
+                for (int rep = 0; rep < c.nrep; rep++)
+                    for (int r = 0; r < R; r++) {
+                        if (!share[r]) continue;
+                        const uint8_t* col = bed + (size_t)(S[r] + mloc_of[r]) * mbytes;
+                        for (int t = 0; t < T; t++) {
+                            const double* d3 = &dbetas[((size_t)r * T + t) * 3];
+                            if (d3[0] != 0.0) oracle_update_eps(eps_of(rep, t), mask4 + (size_t)t * im4, im4, col, d3);
+                        }
+                    }
+            } else {
+                // sync_rate > 1 (superset of the reference, hydra lineage): a replica (GPU) applies its own ranks'
+                // updates at once and the others' only at the exchange, every sync_rate marker-steps
+                if (dl.empty()) dl.assign((size_t)c.nrep * T, std::vector<double>((size_t)im4 * 4, 0.0));
                 for (int r = 0; r < R; r++) {
                     if (!share[r]) continue;
+                    const int rep = rep_of(r);
                     const uint8_t* col = bed + (size_t)(S[r] + mloc_of[r]) * mbytes;
                     for (int t = 0; t < T; t++) {
                         const double* d3 = &dbetas[((size_t)r * T + t) * 3];
-                        if (d3[0] != 0.0) oracle_update_eps(eps_of(rep, t), mask4 + (size_t)t * im4, im4, col, d3);
+                        if (d3[0] == 0.0) continue;
+                        oracle_update_eps(eps_of(rep, t), mask4 + (size_t)t * im4, im4, col, d3);
+                        oracle_update_eps(dl[(size_t)rep * T + t].data(), mask4 + (size_t)t * im4, im4, col, d3);
                     }
                 }
+                if ((mrki + 1) % c.sync_rate == 0 || mrki == Mm - 1) {
+                    for (int rep = 0; rep < c.nrep; rep++)
+                        for (int rep2 = 0; rep2 < c.nrep; rep2++) {
+                            if (rep2 == rep) continue;
+                            for (int t = 0; t < T; t++) {
+                                double* e = eps_of(rep, t);
+                                const std::vector<double>& d = dl[(size_t)rep2 * T + t];
+                                for (int i = 0; i < im4 * 4; i++) e[i] += d[i];
+                            }
+                        }
+                    for (auto& d : dl) std::fill(d.begin(), d.end(), 0.0);
+                }
+            }
         }
 
         // ---- per-iteration epilogue, bayes.cpp:562-651
@@ -578,7 +608,7 @@ void oracle_block_of_markers(int Mt, int nranks, int rank, int* S, int* M, int* 
 int oracle_gibbs(const OracleCfg* cfg, const uint8_t* bed, const double* eps0, const uint8_t* mask4,
                  const int* nonas, const int* group_index, const double* cva, OracleOut* out) {
     g_err.clear();
-    if (cfg->sync_rate != 1) { g_err = "oracle: sync_rate != 1 not restated yet"; return -20; }
+    if (cfg->sync_rate < 1) { g_err = "oracle: sync_rate must be >= 1"; return -20; }
     Gibbs g(*cfg, *out);
     g.bed = bed; g.mask4 = mask4; g.nonas = nonas; g.group_index = group_index; g.cva = cva;
     g.eps0 = eps0;

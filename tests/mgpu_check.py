@@ -1,0 +1,80 @@
+"""Multi-GPU parity check, run under torch.distributed.run with one process per GPU (see
+tests/test_gpu_multi.py):  the marker-sharded chain (NCCL all-reduce of the residual deltas every
+sync_rate steps) against the CPU oracle with the same total number of virtual ranks and one residual
+replica per GPU.  Rank 0 prints MGPU_OK on success."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from gmrm_b200 import api, synth          # noqa: E402
+from oracle import oracle_py as O         # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    sync_rate = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, M, T, G, Vl, iters, seed = 3001, 1203, 2, 2, 8, 4, 77
+    R = Vl * world
+    obj = [None]
+    if rank == 0:
+        with tempfile.TemporaryDirectory() as tmp:
+            d = synth.write_dataset(tmp, N=N, M=M, n_traits=T, n_groups=G, na_rate=0.01, missing_rate=0.004, seed=9)
+            p = d["paths"]
+            obj = [O.load_inputs(p["bed"], p["dim"], p["phen"], p["gri"], p["grm"])]
+    dist.broadcast_object_list(obj, src=0)
+    inp = obj[0]
+    K = inp["cva"].shape[1]
+    e = api.Engine(N=N, Mt=M, T=T, G=G, K=K, vranks=R, world_size=world, world_rank=rank, sync_rate=sync_rate, seed=seed, device=local)
+    uid = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    e.comm_init(uid[0])
+    lo, n = e.marker_begin, e.marker_count
+    e.upload_bed(inp["bed"][lo:lo + n])
+    e.finalize_bed()
+    for t in range(T):
+        e.set_phenotype(t, inp["eps0"][t], inp["mask4"][t], int(inp["nonas"][t]))
+    e.set_groups(inp["group_index"], inp["cva"])
+    e.compute_marker_stats()
+    e.init_chain(None)
+    hist = []
+    for i in range(iters):
+        e.run_iteration(i + 1)
+        st = e.state()
+        st["betas"] = np.stack([e.betas(t) for t in range(T)])
+        st["comp"] = np.stack([e.components(t) for t in range(T)])
+        hist.append(st)
+    eps = np.stack([e.epsilon(t) for t in range(T)])
+    e.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, n, hist, eps))
+    ok = True
+    if rank == 0:
+        res = O.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=N, R=R,
+                      nrep=world, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
+        for (lo_g, n_g, hist_g, eps_g) in gathered:
+            for i in range(iters):
+                assert np.array_equal(hist_g[i]["comp"], res["comp"][i][:, lo_g:lo_g + n_g]), f"comp differs it {i + 1}"
+                np.testing.assert_allclose(hist_g[i]["betas"], res["betas"][i][:, lo_g:lo_g + n_g], rtol=1e-8, atol=1e-13)
+                np.testing.assert_allclose(hist_g[i]["sigmag"], res["sigmag"][i], rtol=1e-8)
+                np.testing.assert_allclose(hist_g[i]["sigmae"], res["sigmae"][i], rtol=1e-8)
+                np.testing.assert_allclose(hist_g[i]["pi"], res["pi"][i], rtol=1e-8)
+                assert np.array_equal(hist_g[i]["m0"], res["m0"][i])
+        # replicas agree with each other and with the oracle's replica 0 up to rounding
+        for (_, _, _, eps_g) in gathered:
+            np.testing.assert_allclose(eps_g, res["eps_final"][:, :N], rtol=0, atol=1e-10)
+        print(f"MGPU_OK world={world} sync_rate={sync_rate} R={R}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,21 @@
+"""GPU, >= 2 devices: marker-sharded chain over NCCL against the oracle (tests/mgpu_check.py)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("sync_rate", [1, 3])
+def test_two_gpu_chain_matches_oracle(sync_rate):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29611 + sync_rate), os.path.join(ROOT, "tests", "mgpu_check.py"), str(sync_rate)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MGPU_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
