@@ -183,13 +183,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     barrier()
-    dev_ms, dot_ms, smp_ms, upd_ms, launches, published = [], [], [], [], 0, 0
+    dev_ms, dot_ms, smp_ms, upd_ms, xch_ms, ar_ms, launches, published = [], [], [], [], [], [], 0, 0
     for _ in range(args.steps):
         it += 1
         e.run_iteration(it)
         tm = e.timing()
         dev_ms.append(tm["iteration_ms"]); dot_ms.append(tm["dot_kernel_ms"])
-        smp_ms.append(tm["sample_kernel_ms"]); upd_ms.append(tm["update_kernel_ms"])
+        smp_ms.append(tm["sample_kernel_ms"]); upd_ms.append(tm["update_kernel_ms"]); xch_ms.append(tm["exchange_ms"]); ar_ms.append(tm["allreduce_ms"])
         launches += tm["launches"]; published += tm["published"]
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -237,7 +237,9 @@ def run_ours(args):
                          "dot_share_of_step": (sum(dot_ms) / len(dot_ms)) / (sum(dev_ms) / len(dev_ms)),
                          "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_dot_ms,
                          "per_step_us": {"dot": 1e3 * sum(dot_ms) / len(dot_ms) / steps_per_it, "sample": 1e3 * sum(smp_ms) / len(smp_ms) / steps_per_it,
-                                         "update": 1e3 * sum(upd_ms) / len(upd_ms) / steps_per_it, "step": 1e3 * ms_per_step / steps_per_it}},
+                                         "update": 1e3 * sum(upd_ms) / len(upd_ms) / steps_per_it,
+                                         "exchange": 1e3 * sum(xch_ms) / len(xch_ms) / steps_per_it,
+                                         "allreduce": 1e3 * sum(ar_ms) / len(ar_ms) / steps_per_it, "step": 1e3 * ms_per_step / steps_per_it}},
             "e2e": {"value": M * T / e2e_s, "unit": "marker-updates/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": d2h // args.steps,
                     "note": "per-iteration call through the C ABI + read-back of betas/components/state to host; "

@@ -40,7 +40,7 @@ class State(C.Structure):
 
 
 class Timing(C.Structure):
-    _fields_ = [("marker_loop_ms", C.c_double), ("iteration_ms", C.c_double), ("dot_kernel_ms", C.c_double), ("sample_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double),
+    _fields_ = [("marker_loop_ms", C.c_double), ("iteration_ms", C.c_double), ("dot_kernel_ms", C.c_double), ("sample_kernel_ms", C.c_double), ("update_kernel_ms", C.c_double), ("exchange_ms", C.c_double), ("allreduce_ms", C.c_double),
                 ("launches", C.c_int64), ("steps", C.c_int64), ("published", C.c_int64)]
 
 

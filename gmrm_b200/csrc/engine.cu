@@ -116,7 +116,7 @@ struct gmrm_engine {
     std::vector<double> h_cva;
     std::vector<int32_t> h_nonas;
 
-    DevBuf<uint8_t> bed, namask2, stage;
+    DevBuf<uint8_t> bed, namask2, na01, stage;
     DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old, zeros;
     DevBuf<double> delta, delta_tot, gc;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
@@ -201,6 +201,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     const int T = c->T, G = c->G, K = c->K;
     A(e->bed.alloc((size_t)e->Mloc * L.col_stride));
     A(e->namask2.alloc((size_t)T * L.col_stride));
+    A(e->na01.alloc((size_t)T * L.npad));
     A(e->eps.alloc((size_t)T * L.npad));
     A(e->mave.alloc((size_t)T * e->Mloc)); A(e->msig.alloc((size_t)T * e->Mloc));
     A(e->betas.alloc((size_t)T * e->Mloc)); A(e->comp.alloc((size_t)T * e->Mloc));
@@ -225,7 +226,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
-    if (e->bed.zero(e->stream) || e->namask2.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
+    if (e->bed.zero(e->stream) || e->namask2.zero(e->stream) || e->na01.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
     if (cudaMemsetAsync(e->pub.p, 0, e->pub.n * sizeof(PubEntry), e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) {
         delete e;
         return fail(GMRM_ECUDA, "initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -354,13 +355,14 @@ int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint
     CU(cudaSetDevice(e->cfg.device));
     const Layout& L = e->L;
     std::vector<double> h((size_t)L.npad, 0.0);
-    std::vector<uint8_t> nm((size_t)L.col_stride, 0);
+    std::vector<uint8_t> nm((size_t)L.col_stride, 0), n01((size_t)L.npad, 0);
     int seen = 0;
     for (int i = 0; i < L.N; i++) {
         const bool obs = (mask4[i / 4] >> (i % 4)) & 1;
         h[i] = obs ? eps0[i] : 0.0;
         if (!obs) continue;
         seen++;
+        n01[i] = 1;
         const int64_t s = i / L.E;
         const int k = i % L.E, c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
         nm[(size_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, k / 4)] |= (uint8_t)(1u << (2 * (k % 4)));
@@ -368,6 +370,7 @@ int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint
     if (seen != nonas) return fail(GMRM_EINVAL, "mask4 has %d observed individuals but nonas=%d", seen, nonas);
     CU(cudaMemcpyAsync(e->eps.p + (size_t)t * L.npad, h.data(), h.size() * 8, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->namask2.p + (size_t)t * L.col_stride, nm.data(), nm.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->na01.p + (size_t)t * L.npad, n01.data(), n01.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->nonas.p + t, &nonas, 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->h_nonas[t] = nonas;
@@ -489,7 +492,7 @@ int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, doubl
     rc = partial.alloc((size_t)n * T * e->L.nsm * 16); if (rc) return rc;
     rc = res.alloc((size_t)n * T); if (rc) return rc;
     CU(cudaMemcpyAsync(cols.p, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-    launch_eps_offset(e->eps.p, e->namask2.p, e->L, T, nullptr, nullptr, e->spart.p, e->stream);   // refresh per-tile sums
+    launch_eps_offset(e->eps.p, e->na01.p, e->L, T, nullptr, nullptr, e->spart.p, e->stream);   // refresh per-tile sums
     rc = launch_dots(e, cols.p, n, partial.p); if (rc) return rc;
     SampleParams sp = sample_params(e, cols.p, n, partial.p);
     launch_finish_dots(sp, res.p, e->stream);
@@ -545,7 +548,7 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     CU(cudaMemcpyAsync(dpub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));
     UpdateParams up{};
     up.bed = e->bed.p; up.col_stride = e->L.col_stride; up.cols = cols.p; up.V = 1; up.T = T; up.pub = dpub.p;
-    up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = e->L.npad; up.spart = e->spart.p; up.exact = 1;
+    up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.na01 = e->na01.p; up.eps = e->eps.p; up.npad = e->L.npad; up.spart = e->spart.p; up.exact = 1;
     if (launch_update(e->L, up, e->stream) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
@@ -644,9 +647,9 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         (void)d_small;
     }
 
-    if (e->timing_detail && e->dot_ev.size() < (size_t)4 * Mm) {
+    if (e->timing_detail && e->dot_ev.size() < (size_t)6 * Mm) {
         const size_t old = e->dot_ev.size();
-        e->dot_ev.resize((size_t)4 * Mm);
+        e->dot_ev.resize((size_t)6 * Mm);
         for (size_t i = old; i < e->dot_ev.size(); i++) CU(cudaEventCreate(&e->dot_ev[i]));
     }
 
@@ -656,7 +659,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     MuDrawParams mp{};
     mp.T = T; mp.it = it; mp.seed = c.seed; mp.sigmae = e->sigmae.p; mp.nonas = e->nonas.p; mp.mu = e->mu.p; mp.mu_old = e->mu_old.p; mp.rep_mu = d_mu;
     launch_mu_draw(mp, s);
-    launch_eps_offset(e->eps.p, e->namask2.p, L, T, e->mu_old.p, e->mu.p, e->spart.p, s);
+    launch_eps_offset(e->eps.p, e->na01.p, L, T, e->mu_old.p, e->mu.p, e->spart.p, s);
     launch_steptab(e->steptab.p, Mm, Vl, e->r0, R, c.Mt, e->marker_begin, c.shuffle, c.seed, it, d_perm, s);
     launch_group_consts(T, G, K, c.N, e->sigmag.p, e->sigmae.p, e->pi.p, e->cva.p, e->cvai.p, e->nonas.p, e->gc.p, s);
     CU(cudaMemsetAsync(e->cass.p, 0, e->cass.n * 4, s));
@@ -668,26 +671,28 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     const bool multi = c.world_size > 1;
     for (int st = 0; st < Mm; st++) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st], s));
         if ((rc = launch_dots(e, cols, Vl, e->partial.p))) return rc;
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 1], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 1], s));
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
         launch_sample(sp, s);
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 2], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
         UpdateParams up{};
         up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
-        up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
+        up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.na01 = e->na01.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
         up.delta = multi ? e->delta.p : nullptr;
         if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[4 * st + 3], s));
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
         launches += (e->dot_kernel == 1 ? T : (T + trait_chunk(L.E) - 1) / trait_chunk(L.E)) + 2;
         // ---- exchange (bayes.cpp:495-553): every sync_rate steps the shards all-reduce what they changed
         if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
             NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
+            if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, e->spart.p, s);
             launches += 2;
         }
+        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 4], s));
     }
     CU(cudaEventRecord(e->ev[2], s));
 
@@ -721,16 +726,22 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     CU(cudaEventElapsedTime(&ms_loop, e->ev[1], e->ev[2]));
     CU(cudaEventElapsedTime(&ms_all, e->ev[0], e->ev[3]));
     e->last.marker_loop_ms = ms_loop; e->last.iteration_ms = ms_all; e->last.launches = launches; e->last.steps = Mm; e->last.published = hpub;
-    e->last.dot_kernel_ms = 0.0; e->last.sample_kernel_ms = 0.0; e->last.update_kernel_ms = 0.0;
+    e->last.dot_kernel_ms = 0.0; e->last.sample_kernel_ms = 0.0; e->last.update_kernel_ms = 0.0; e->last.exchange_ms = 0.0; e->last.allreduce_ms = 0.0;
     if (e->timing_detail)
         for (int st = 0; st < Mm; st++) {
             float ms = 0;
-            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st], e->dot_ev[4 * st + 1]));
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st], e->dot_ev[6 * st + 1]));
             e->last.dot_kernel_ms += ms;
-            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st + 1], e->dot_ev[4 * st + 2]));
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 1], e->dot_ev[6 * st + 2]));
             e->last.sample_kernel_ms += ms;
-            CU(cudaEventElapsedTime(&ms, e->dot_ev[4 * st + 2], e->dot_ev[4 * st + 3]));
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 2], e->dot_ev[6 * st + 3]));
             e->last.update_kernel_ms += ms;
+            CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 4]));
+            e->last.exchange_ms += ms;
+            if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+                CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 5]));
+                e->last.allreduce_ms += ms;
+            }
         }
     if (herr != 0) {
         CU(cudaMemset(e->err.p, 0, 4));

@@ -279,25 +279,22 @@ __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ 
 // =====================================================================================
 // Phenotype::offset_epsilon twice (bayes.cpp:351,359): eps += mu_old*na; eps -= mu_new*na; and the
 // per-tile sum of eps that the sampler turns into sum b*eps.
-template <int E4>
-__global__ void __launch_bounds__(kLanesPerTile) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ namask2,
-                                                                  Layout L, const double* __restrict__ mu_old,
-                                                                  const double* __restrict__ mu_new, double* __restrict__ spart) {
-    constexpr int E = 4 * E4;
-    const int t = blockIdx.y, ls = threadIdx.x;
-    __shared__ double red[kLanesPerTile / 32];
-    SlotRegs<E4> na;
-    na.load(namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
-    double* e = eps + (int64_t)t * L.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
+// A tile is the contiguous range of individuals [tile*128*E, (tile+1)*128*E): one block walks it with
+// coalesced accesses; na01 is the per-individual 0/1 NA indicator.
+__global__ void __launch_bounds__(256) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ na01, Layout L,
+                                                         const double* __restrict__ mu_old, const double* __restrict__ mu_new,
+                                                         double* __restrict__ spart) {
+    const int t = blockIdx.y, per = kLanesPerTile * L.E;
+    __shared__ double red[8];
+    const int64_t base = (int64_t)t * L.npad + (int64_t)blockIdx.x * per;
     const double a = mu_old ? mu_old[t] : 0.0, b = mu_new ? -mu_new[t] : 0.0;
     double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-        double v = e[k];
-        const double m = na.field(k) ? 1.0 : 0.0;
+    for (int i = threadIdx.x; i < per; i += 256) {
+        double v = eps[base + i];
+        const double m = na01[base + i] ? 1.0 : 0.0;
         v += a * m;            // phenotype.cpp:408
         v += b * m;
-        e[k] = v;
+        eps[base + i] = v;
         s += v;
     }
     const double tot = block_sum_fixed(s, red);
@@ -307,19 +304,16 @@ __global__ void __launch_bounds__(kLanesPerTile) eps_offset_kernel(double* __res
 // Multi-GPU exchange (replaces the per-marker Allgatherv + local recompute of bayes.cpp:500-547): after the
 // all-reduce of the shards' residual deltas, add what the OTHER shards changed, clear the local delta, refresh
 // the per-tile sums.
-template <int E4>
-__global__ void __launch_bounds__(kLanesPerTile) eps_merge_kernel(double* __restrict__ eps, double* __restrict__ loc,
-                                                                 const double* __restrict__ tot, Layout L, double* __restrict__ spart) {
-    constexpr int E = 4 * E4;
-    const int t = blockIdx.y;
-    __shared__ double red[kLanesPerTile / 32];
-    const int64_t base = (int64_t)t * L.npad + ((int64_t)blockIdx.x * kLanesPerTile + threadIdx.x) * E;
+__global__ void __launch_bounds__(256) eps_merge_kernel(double* __restrict__ eps, double* __restrict__ loc,
+                                                        const double* __restrict__ tot, Layout L, double* __restrict__ spart) {
+    const int t = blockIdx.y, per = kLanesPerTile * L.E;
+    __shared__ double red[8];
+    const int64_t base = (int64_t)t * L.npad + (int64_t)blockIdx.x * per;
     double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < E; k++) {
-        const double v = eps[base + k] + (tot[base + k] - loc[base + k]);
-        eps[base + k] = v;
-        loc[base + k] = 0.0;
+    for (int i = threadIdx.x; i < per; i += 256) {
+        const double v = eps[base + i] + (tot[base + i] - loc[base + i]);
+        eps[base + i] = v;
+        loc[base + i] = 0.0;
         s += v;
     }
     const double r = block_sum_fixed(s, red);
@@ -796,10 +790,9 @@ struct UpdEntry {           // one published marker, staged in shared memory
 template <int E4>
 __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdateParams p, Layout L) {
     constexpr int E = 4 * E4;
-    constexpr int EK = E / kUpdSplit;                 // individuals of a slot one thread finalises (E is a multiple of 4)
     extern __shared__ __align__(16) uint8_t usmem[];
-    double* dlt = reinterpret_cast<double*>(usmem);                                  // [kUpdSplit][E][128]
-    UpdEntry* ent = reinterpret_cast<UpdEntry*>(usmem + sizeof(double) * kUpdSplit * E * kLanesPerTile);
+    double* dlt = reinterpret_cast<double*>(usmem);                                  // [kUpdSplit][128][E + 1]
+    UpdEntry* ent = reinterpret_cast<UpdEntry*>(usmem + sizeof(double) * kUpdSplit * (E + 1) * kLanesPerTile);
     int32_t* ecol = reinterpret_cast<int32_t*>(ent + kUpdCap);                        // column of each staged entry
     __shared__ int npub;
     __shared__ int wcnt[kUpdCap / 32];
@@ -885,30 +878,26 @@ __global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdatePara
         }
     }
     if (!__syncthreads_or(any)) return;              // nothing published for this trait: eps and its sums stand
+    // increments of split u for slot ls, padded rows (E+1) keep both the writes and the reads below conflict-free
 #pragma unroll
-    for (int k = 0; k < E; k++) dlt[((int64_t)u * E + k) * kLanesPerTile + ls] = d[k];
+    for (int k = 0; k < E; k++) dlt[((int64_t)u * kLanesPerTile + ls) * (E + 1) + k] = d[k];
     __syncthreads();
 
-    // combine the splits in fixed order; thread (u, ls) finalises individuals u*EK .. u*EK+EK-1 of its slot
-    SlotRegs<E4> na;
-    na.load(p.namask2 + (int64_t)t * L.col_stride + (int64_t)blockIdx.x * L.tile_bytes, ls);
-    double* ep = p.eps + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E;
-    double* dp = p.delta ? p.delta + (int64_t)t * p.npad + ((int64_t)blockIdx.x * kLanesPerTile + ls) * E : nullptr;
-    double s = 0.0, ev[EK];
-#pragma unroll
-    for (int kk = 0; kk < EK; kk++) ev[kk] = ep[u * EK + kk];    // all loads in flight before the first use
-#pragma unroll
-    for (int kk = 0; kk < EK; kk++) {
-        const int k = u * EK + kk;
+    // combine the splits in fixed order and apply: the tile is a contiguous range of individuals -> coalesced
+    constexpr int PER = kLanesPerTile * E;
+    const int64_t base = (int64_t)t * p.npad + (int64_t)blockIdx.x * PER;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < PER; i += kUpdThreads) {
+        const int sl = i / E, k = i - sl * E;
         double inc = 0.0;
 #pragma unroll
-        for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * E + k) * kLanesPerTile + ls];
-        double e = ev[kk];
-        if (na.field(k)) {                           // * na  (phenotype.cpp:388)
+        for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * kLanesPerTile + sl) * (E + 1) + k];
+        double e = p.eps[base + i];
+        if (p.na01[base + i]) {                      // * na  (phenotype.cpp:388)
             e += inc;
-            if (dp) dp[k] += inc;                    // multi-GPU: what this shard changed since the last exchange
+            if (p.delta) p.delta[base + i] += inc;   // multi-GPU: what this shard changed since the last exchange
         }
-        ep[k] = e;
+        p.eps[base + i] = e;
         s += e;
     }
     const double tot = block_sum_fixed(s, red);
@@ -1049,12 +1038,6 @@ void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t*
     stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, namask2, nonas, T, mave, msig);
 }
 
-template <int E4>
-static void eps_offset_t(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
-                         const double* mu_new, double* spart, cudaStream_t s) {
-    dim3 grid((unsigned)L.nsm, (unsigned)T);
-    eps_offset_kernel<E4><<<grid, kLanesPerTile, 0, s>>>(eps, namask2, L, mu_old, mu_new, spart);
-}
 #define GMRM_DISPATCH_E4(E4v, CALL)                 \
     switch (E4v) {                                  \
     case 1: { constexpr int E4 = 1; CALL; } break;  \
@@ -1068,17 +1051,14 @@ static void eps_offset_t(double* eps, const uint8_t* namask2, const Layout& L, i
     default: break;                                 \
     }
 
-void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
+void launch_eps_offset(double* eps, const uint8_t* na01, const Layout& L, int T, const double* mu_old,
                        const double* mu_new, double* spart, cudaStream_t s) {
-    GMRM_DISPATCH_E4(L.E4, (eps_offset_t<E4>(eps, namask2, L, T, mu_old, mu_new, spart, s)));
-}
-template <int E4>
-static void eps_merge_t(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s) {
     dim3 grid((unsigned)L.nsm, (unsigned)T);
-    eps_merge_kernel<E4><<<grid, kLanesPerTile, 0, s>>>(eps, loc, tot, L, spart);
+    eps_offset_kernel<<<grid, 256, 0, s>>>(eps, na01, L, mu_old, mu_new, spart);
 }
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s) {
-    GMRM_DISPATCH_E4(L.E4, (eps_merge_t<E4>(eps, loc, tot, L, T, spart, s)));
+    dim3 grid((unsigned)L.nsm, (unsigned)T);
+    eps_merge_kernel<<<grid, 256, 0, s>>>(eps, loc, tot, L, spart);
 }
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);
@@ -1156,7 +1136,7 @@ void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
 
 template <int E4>
 static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t s) {
-    const int smem = (int)sizeof(double) * kUpdSplit * 4 * E4 * kLanesPerTile + kUpdCap * (int)(sizeof(UpdEntry) + sizeof(int32_t));
+    const int smem = (int)sizeof(double) * kUpdSplit * (4 * E4 + 1) * kLanesPerTile + kUpdCap * (int)(sizeof(UpdEntry) + sizeof(int32_t));
     static int attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         if (cudaFuncSetAttribute(update_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;

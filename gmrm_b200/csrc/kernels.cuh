@@ -86,6 +86,7 @@ struct UpdateParams {
     const PubEntry* pub;     // [V][T]
     const uint32_t* miss_off;// to pick the exact path for markers with missing genotypes
     const uint8_t* namask2;  // [T][col_stride] tile layout, field 01 = observed
+    const uint8_t* na01;     // [T][npad] 1 = observed, per individual
     double* eps;             // [T][npad]
     int64_t npad;
     double* spart;           // [T][nsm]
@@ -103,7 +104,7 @@ void launch_count_missing(const uint8_t* bed, int nmark, const Layout& L, uint32
 void launch_fill_missing(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s);
 void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* namask2, const int32_t* nonas, int T,
                   double* mave, double* msig, cudaStream_t s);
-void launch_eps_offset(double* eps, const uint8_t* namask2, const Layout& L, int T, const double* mu_old,
+void launch_eps_offset(double* eps, const uint8_t* na01, const Layout& L, int T, const double* mu_old,
                        const double* mu_new, double* spart, cudaStream_t s);
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);

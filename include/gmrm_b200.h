@@ -87,6 +87,8 @@ typedef struct {
     double dot_kernel_ms;    /* summed device time of the dot kernel launches (only if timing detail on) */
     double sample_kernel_ms; /* same for the sampler kernel                                                   */
     double update_kernel_ms; /* same for the residual-update kernel                                           */
+    double exchange_ms;      /* same for the cross-GPU exchange (all-reduce + merge), 0 on one GPU             */
+    double allreduce_ms;     /* the all-reduce part of exchange_ms (includes waiting for the slowest shard)    */
     int64_t launches;        /* kernels launched by the last iteration                                */
     int64_t steps;           /* marker-steps of the last iteration                                    */
     int64_t published;       /* marker updates with dbeta != 0 in the last iteration (this shard)     */
