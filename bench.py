@@ -228,11 +228,11 @@ def run_ours(args):
             "dtype": "f64", "data": "synthetic (Binomial(2,p) genotypes, p~U(0.05,0.5), generated on device; simulated phenotype)",
             "config": {"workload": f"{args.workload}: N={N} M={M} T={T} G={G} K={K}", "vranks_per_gpu": args.vranks_per_gpu,
                        "vranks_total": R, "sync_rate": args.sync_rate, "marker_steps_per_iter": steps_per_it,
-                       "layout": f"tile-planar 2-bit, {e.individuals_per_lane} individuals/lane, {e.tiles} tiles, "
-                                 f"{e.column_stride} B/column", "l2": "inputs >> L2 (no flush needed)",
+                       "layout": f"base-3 quads (1 byte = 4 genotypes), {e.tiles} CTAs, {e.column_stride} B/column",
+                       "l2": "inputs >> L2 (no flush needed)",
                        "setup_s": round(setup_s, 1), "hbm_gbs_iter": it_bytes / (ms_per_step * 1e-3) / 1e9,
                        "hbm_frac_iter": it_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
-            "roofline": {"bound": "hbm", "kernel": "dot_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "dot_share_of_step": (sum(dot_ms) / len(dot_ms)) / (sum(dev_ms) / len(dev_ms)),
                          "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_dot_ms,

@@ -116,11 +116,17 @@ struct gmrm_engine {
     std::vector<double> h_cva;
     std::vector<int32_t> h_nonas;
 
-    DevBuf<uint8_t> bed, namask2, na01, stage;
-    DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old, zeros;
+    DevBuf<uint8_t> bed, mask4, stage;
+    DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old;
     DevBuf<double> delta, delta_tot, gc;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
-    DevBuf<uint32_t> miss_off, miss_idx;
+    DevBuf<uint32_t> miss_off, miss_idx, miss_cnt;
+    // missing-genotype lists are collected per uploaded chunk (the base-3 bytes do not carry them) and
+    // assembled into one CSR by gmrm_finalize_bed
+    struct MissChunk { int begin = 0, count = 0; std::vector<uint32_t> cnt; DevBuf<uint32_t>* idx = nullptr; uint64_t total = 0; };
+    std::vector<MissChunk> miss_chunks;
+    int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
+    int step_warps = 16;             // consumer warps of the step kernel (GMRM_STEP_WARPS=23: measured alternative)
     DevBuf<PubEntry> pub;
     DevBuf<int64_t> npub;
     // replay staging
@@ -132,12 +138,11 @@ struct gmrm_engine {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> dot_ev;
     bool timing_detail = false;
-    int dot_variant = 0, dot_debug = 0;
-    int dot_kernel = 1;        // 1: table-lookup kernel (single-trait runs), 0: shift+DFMA kernel
     gmrm_timing last{};
 
     ~gmrm_engine() {
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (auto& c : miss_chunks) delete c.idx;
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : dot_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -174,10 +179,6 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->cfg = *c;
     const int nsm = c->nsm > 0 ? c->nsm : prop.multiProcessorCount;
     e->L = make_layout(c->N, nsm);
-    if (e->L.E4 == 0) {
-        delete e;
-        return fail(GMRM_EINVAL, "N=%d does not fit %d tiles x 128 lanes x 32 individuals", c->N, nsm);
-    }
     e->Vl = c->vranks / c->world_size;
     e->r0 = c->world_rank * e->Vl;
     int S, M, Slast, Mlast;
@@ -186,10 +187,13 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->marker_begin = S;
     e->Mloc = Slast + Mlast - S;
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
-    if (const char* v = getenv("GMRM_DOT_VARIANT")) e->dot_variant = atoi(v);
-    if (const char* v = getenv("GMRM_DOT_DEBUG")) e->dot_debug = atoi(v);
-    e->dot_kernel = 0;     // GMRM_DOT_KERNEL=1 selects the table-lookup kernel (kept as a measured alternative)
-    if (const char* v = getenv("GMRM_DOT_KERNEL")) e->dot_kernel = atoi(v);
+    if (const char* v = getenv("GMRM_STEP_WARPS")) e->step_warps = atoi(v) == 23 ? 23 : 16;
+    step_plan(e->L, e->Vl, c->T, &e->step_tc, &e->step_rpp);
+    if (e->step_tc < 1 || e->step_rpp < 1) {
+        const int vl = e->Vl;
+        delete e;
+        return fail(GMRM_EINVAL, "%d virtual ranks per GPU do not fit the step kernel's shared memory (partials + one table slot)", vl);
+    }
     e->phen_set.assign(c->T, 0);
     e->h_nonas.assign(c->T, 0);
 
@@ -200,33 +204,31 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     const Layout& L = e->L;
     const int T = c->T, G = c->G, K = c->K;
     A(e->bed.alloc((size_t)e->Mloc * L.col_stride));
-    A(e->namask2.alloc((size_t)T * L.col_stride));
-    A(e->na01.alloc((size_t)T * L.npad));
+    A(e->mask4.alloc((size_t)T * L.col_stride));
     A(e->eps.alloc((size_t)T * L.npad));
     A(e->mave.alloc((size_t)T * e->Mloc)); A(e->msig.alloc((size_t)T * e->Mloc));
     A(e->betas.alloc((size_t)T * e->Mloc)); A(e->comp.alloc((size_t)T * e->Mloc));
     A(e->group_loc.alloc(e->Mloc)); A(e->mtotgrp.alloc(G));
     A(e->cva.alloc((size_t)G * K)); A(e->cvai.alloc((size_t)G * K));
     A(e->steptab.alloc((size_t)e->Mm * e->Vl));
-    A(e->partial.alloc((size_t)e->Vl * T * L.nsm * 16));
+    A(e->partial.alloc((size_t)e->Vl * T * L.nsm));
     A(e->spart.alloc((size_t)T * L.nsm));
     A(e->pub.alloc((size_t)e->Vl * T));
     A(e->cass.alloc((size_t)T * G * K)); A(e->m0.alloc((size_t)T * G));
     A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T));
     A(e->sigmag.alloc((size_t)T * G)); A(e->sigmae.alloc(T)); A(e->pi.alloc((size_t)T * G * K));
     A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T)); A(e->gc.alloc((size_t)T * G * 4 * K));
-    A(e->zeros.alloc((size_t)kDotMaxThreads * kDotMaxBatch));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
-    A(e->miss_off.alloc((size_t)e->Mloc + 1));
+    A(e->miss_off.alloc((size_t)e->Mloc + 1)); A(e->miss_idx.alloc(1));
     if (c->world_size > 1) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
     if (rc != 0) { delete e; return rc; }
     // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
     for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
-                    &e->mu_old, &e->zeros, &e->partial, &e->delta, &e->delta_tot})
+                    &e->mu_old, &e->partial, &e->delta, &e->delta_tot})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
-    if (e->bed.zero(e->stream) || e->namask2.zero(e->stream) || e->na01.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
+    if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
     if (cudaMemsetAsync(e->pub.p, 0, e->pub.n * sizeof(PubEntry), e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) {
         delete e;
         return fail(GMRM_ECUDA, "initial memset failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -248,13 +250,14 @@ int gmrm_shard_info(const gmrm_engine* e, int32_t* marker_begin, int32_t* marker
     if (marker_begin) *marker_begin = e->marker_begin;
     if (marker_count) *marker_count = e->Mloc;
     if (column_stride_bytes) *column_stride_bytes = e->L.col_stride;
-    if (individuals_per_lane) *individuals_per_lane = e->L.E;
+    if (individuals_per_lane) *individuals_per_lane = 4;   /* one quad per byte */
     if (tiles) *tiles = e->L.nsm;
     return GMRM_OK;
 }
 
 // ------------------------------------------------------------------------------------ genotypes
 static int ensure_stage(gmrm_engine* e, size_t bytes) {
+    bytes = (bytes + 15) & ~(size_t)15;
     if (e->stage.n >= bytes) return 0;
     return e->stage.alloc(bytes);
 }
@@ -263,6 +266,47 @@ static int chunk_markers(const gmrm_engine* e) {
     const size_t budget = 256u << 20;
     size_t n = budget / (size_t)e->L.mbytes;
     return (int)std::max<size_t>(1, std::min<size_t>(n, 65535));   // grid.y limit
+}
+
+// PLINK bytes of markers [lb, lb+n) (shard-local) sit in e->stage: transcode them into the HBM layout and
+// collect their missing-genotype lists.
+static int ingest_staged(gmrm_engine* e, int lb, int n) {
+    if (e->miss_cnt.n < (size_t)n + 1) { int rc = e->miss_cnt.alloc((size_t)n + 1); if (rc) return rc; }
+    CU(cudaMemsetAsync(e->miss_cnt.p, 0, ((size_t)n + 1) * 4, e->stream));
+    launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)lb * e->L.col_stride, e->miss_cnt.p, e->stream);
+    CU(cudaGetLastError());
+    gmrm_engine::MissChunk ch;
+    ch.begin = lb; ch.count = n; ch.cnt.resize(n);
+    CU(cudaMemcpyAsync(ch.cnt.data(), e->miss_cnt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    std::vector<uint32_t> off((size_t)n + 1, 0);
+    uint64_t tot = 0;
+    for (int j = 0; j < n; j++) { off[j] = (uint32_t)tot; tot += ch.cnt[j]; }
+    if (tot > 0xffffffffull) return fail(GMRM_EINVAL, "more than 2^32 missing genotypes in one chunk");
+    off[n] = (uint32_t)tot;
+    ch.total = tot;
+    // an earlier upload of an overlapping range is superseded
+    for (size_t i = 0; i < e->miss_chunks.size();) {
+        auto& o = e->miss_chunks[i];
+        if (o.begin < lb + n && lb < o.begin + o.count) {
+            if (o.begin < lb || o.begin + o.count > lb + n) return fail(GMRM_EINVAL, "re-upload of markers [%d, %d) only partly covers an earlier chunk [%d, %d)", lb, lb + n, o.begin, o.begin + o.count);
+            delete o.idx;
+            e->miss_chunks.erase(e->miss_chunks.begin() + i);
+        } else {
+            i++;
+        }
+    }
+    if (tot) {
+        ch.idx = new DevBuf<uint32_t>();
+        int rc = ch.idx->alloc(tot);
+        if (rc) { delete ch.idx; return rc; }
+        CU(cudaMemcpyAsync(e->miss_cnt.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
+        launch_fill_missing(e->stage.p, n, e->L, e->miss_cnt.p, ch.idx->p, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(e->stream));
+    }
+    e->miss_chunks.push_back(std::move(ch));
+    return 0;
 }
 
 int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, int32_t marker_count) {
@@ -274,14 +318,12 @@ int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, in
     const int chunk = chunk_markers(e);
     int rc = ensure_stage(e, (size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes);
     if (rc) return rc;
+    e->bed_final = false;
     for (int done = 0; done < marker_count; done += chunk) {
         const int n = std::min(chunk, marker_count - done);
         CU(cudaMemcpyAsync(e->stage.p, bed + (size_t)done * e->L.mbytes, (size_t)n * e->L.mbytes, cudaMemcpyHostToDevice, e->stream));
-        launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)(marker_begin - e->marker_begin + done) * e->L.col_stride, e->stream);
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(e->stream));   // the staging buffer is reused by the next chunk
+        if ((rc = ingest_staged(e, marker_begin - e->marker_begin + done, n))) return rc;   // syncs: the staging buffer is reused
     }
-    e->bed_final = false;
     return GMRM_OK;
 }
 
@@ -291,31 +333,11 @@ int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_h
     const int chunk = chunk_markers(e);
     int rc = ensure_stage(e, (size_t)std::min(chunk, e->Mloc) * e->L.mbytes);
     if (rc) return rc;
+    e->bed_final = false;
     for (int done = 0; done < e->Mloc; done += chunk) {
         const int n = std::min(chunk, e->Mloc - done);
         launch_generate_plink(e->stage.p, n, e->marker_begin + done, e->L, seed, maf_lo, maf_hi, missing_rate, e->stream);
-        launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)done * e->L.col_stride, e->stream);
-        CU(cudaGetLastError());
-    }
-    CU(cudaStreamSynchronize(e->stream));
-    e->bed_final = false;
-    return GMRM_OK;
-}
-
-int gmrm_download_bed(gmrm_engine* e, uint8_t* out, int32_t marker_begin, int32_t marker_count) {
-    if (!e || !out) return fail(GMRM_EINVAL, "null argument");
-    if (marker_count < 0 || marker_begin < e->marker_begin || marker_begin + marker_count > e->marker_begin + e->Mloc)
-        return fail(GMRM_EINVAL, "markers outside this shard");
-    CU(cudaSetDevice(e->cfg.device));
-    const int chunk = chunk_markers(e);
-    int rc = ensure_stage(e, (size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes);
-    if (rc) return rc;
-    for (int done = 0; done < marker_count; done += chunk) {
-        const int n = std::min(chunk, marker_count - done);
-        launch_untranscode(e->bed.p + (size_t)(marker_begin - e->marker_begin + done) * e->L.col_stride, n, e->L, e->stage.p, e->stream);
-        CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(out + (size_t)done * e->L.mbytes, e->stage.p, (size_t)n * e->L.mbytes, cudaMemcpyDeviceToHost, e->stream));
-        CU(cudaStreamSynchronize(e->stream));
+        if ((rc = ingest_staged(e, done, n))) return rc;
     }
     return GMRM_OK;
 }
@@ -323,27 +345,43 @@ int gmrm_download_bed(gmrm_engine* e, uint8_t* out, int32_t marker_begin, int32_
 int gmrm_finalize_bed(gmrm_engine* e) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
     CU(cudaSetDevice(e->cfg.device));
-    DevBuf<uint32_t> counts;
-    int rc = counts.alloc(e->Mloc);
-    if (rc) return rc;
-    launch_count_missing(e->bed.p, e->Mloc, e->L, counts.p, e->stream);
-    CU(cudaGetLastError());
-    std::vector<uint32_t> h(e->Mloc), off((size_t)e->Mloc + 1, 0);
-    CU(cudaMemcpyAsync(h.data(), counts.p, (size_t)e->Mloc * 4, cudaMemcpyDeviceToHost, e->stream));
-    CU(cudaStreamSynchronize(e->stream));
+    std::vector<uint32_t> cnt(e->Mloc, 0), off((size_t)e->Mloc + 1, 0);
+    for (auto& c : e->miss_chunks)
+        for (int j = 0; j < c.count; j++) cnt[c.begin + j] = c.cnt[j];
     uint64_t tot = 0;
-    for (int j = 0; j < e->Mloc; j++) { off[j] = (uint32_t)tot; tot += h[j]; }
+    for (int j = 0; j < e->Mloc; j++) { off[j] = (uint32_t)tot; tot += cnt[j]; }
     if (tot > 0xffffffffull) return fail(GMRM_EINVAL, "more than 2^32 missing genotypes in one shard");
     off[e->Mloc] = (uint32_t)tot;
-    CU(cudaMemcpyAsync(e->miss_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
-    rc = e->miss_idx.alloc(std::max<uint64_t>(tot, 1));
+    int rc = e->miss_idx.alloc(std::max<uint64_t>(tot, 1));
     if (rc) return rc;
-    if (tot) launch_fill_missing(e->bed.p, e->Mloc, e->L, e->miss_off.p, e->miss_idx.p, e->stream);
-    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(e->miss_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    for (auto& c : e->miss_chunks)
+        if (c.total) CU(cudaMemcpyAsync(e->miss_idx.p + off[c.begin], c.idx->p, c.total * 4, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->stage.free();
     e->bed_final = true;
     e->stats_done = false;
+    return GMRM_OK;
+}
+
+int gmrm_download_bed(gmrm_engine* e, uint8_t* out, int32_t marker_begin, int32_t marker_count) {
+    if (!e || !out) return fail(GMRM_EINVAL, "null argument");
+    if (marker_count < 0 || marker_begin < e->marker_begin || marker_begin + marker_count > e->marker_begin + e->Mloc)
+        return fail(GMRM_EINVAL, "markers outside this shard");
+    if (!e->bed_final) { int rcf = gmrm_finalize_bed(e); if (rcf) return rcf; }   // the missing-genotype lists are part of the layout
+    CU(cudaSetDevice(e->cfg.device));
+    const int chunk = chunk_markers(e);
+    DevBuf<uint8_t> tmp;
+    int rc = tmp.alloc((((size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes) + 15) & ~(size_t)15);
+    if (rc) return rc;
+    for (int done = 0; done < marker_count; done += chunk) {
+        const int n = std::min(chunk, marker_count - done);
+        const int lb = marker_begin - e->marker_begin + done;
+        launch_untranscode(e->bed.p + (size_t)lb * e->L.col_stride, n, e->L, e->miss_off.p + lb, e->miss_idx.p, tmp.p, e->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out + (size_t)done * e->L.mbytes, tmp.p, (size_t)n * e->L.mbytes, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaStreamSynchronize(e->stream));
+    }
     return GMRM_OK;
 }
 
@@ -355,22 +393,18 @@ int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint
     CU(cudaSetDevice(e->cfg.device));
     const Layout& L = e->L;
     std::vector<double> h((size_t)L.npad, 0.0);
-    std::vector<uint8_t> nm((size_t)L.col_stride, 0), n01((size_t)L.npad, 0);
+    std::vector<uint8_t> nm((size_t)L.col_stride, 0);
     int seen = 0;
     for (int i = 0; i < L.N; i++) {
         const bool obs = (mask4[i / 4] >> (i % 4)) & 1;
         h[i] = obs ? eps0[i] : 0.0;
         if (!obs) continue;
         seen++;
-        n01[i] = 1;
-        const int64_t s = i / L.E;
-        const int k = i % L.E, c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
-        nm[(size_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, k / 4)] |= (uint8_t)(1u << (2 * (k % 4)));
+        nm[i / 4] |= (uint8_t)(1u << (i % 4));
     }
     if (seen != nonas) return fail(GMRM_EINVAL, "mask4 has %d observed individuals but nonas=%d", seen, nonas);
     CU(cudaMemcpyAsync(e->eps.p + (size_t)t * L.npad, h.data(), h.size() * 8, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->namask2.p + (size_t)t * L.col_stride, nm.data(), nm.size(), cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->na01.p + (size_t)t * L.npad, n01.data(), n01.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->mask4.p + (size_t)t * L.col_stride, nm.data(), nm.size(), cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->nonas.p + t, &nonas, 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->h_nonas[t] = nonas;
@@ -415,7 +449,7 @@ int gmrm_compute_marker_stats(gmrm_engine* e) {
     for (int t = 0; t < e->cfg.T; t++)
         if (!e->phen_set[t]) return fail(GMRM_EINVAL, "phenotype %d not set", t);
     CU(cudaSetDevice(e->cfg.device));
-    launch_stats(e->bed.p, e->Mloc, e->L, e->namask2.p, e->nonas.p, e->cfg.T, e->mave.p, e->msig.p, e->stream);
+    launch_stats(e->bed.p, e->Mloc, e->L, e->mask4.p, e->miss_off.p, e->miss_idx.p, e->nonas.p, e->cfg.T, e->mave.p, e->msig.p, e->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
     e->stats_done = true;
@@ -432,51 +466,52 @@ int gmrm_get_marker_stats(gmrm_engine* e, int32_t t, double* mave, double* msig)
 }
 
 // ------------------------------------------------------------------------------ shared launch glue
-// Traits per dot-kernel launch: the lane keeps E x Tc weights in registers; beyond ~48-64 doubles
-// ptxas spills (table in DESIGN.md), so wide lanes take fewer traits per pass over the genotypes.
-static int trait_chunk(int E) {
-    if (E * 4 <= 48) return 4;
-    if (E * 3 <= 48) return 3;
-    if (E * 2 <= 64) return 2;
-    return 1;
-}
-
-// partial sums per (marker, trait) that the sampler adds up: one per CTA for the table kernel, one per
-// CTA and sub-partition for the shift+DFMA kernel
-static int dot_nsl(const gmrm_engine* e) { return e->dot_kernel == 1 ? e->L.nsm * dot_table_passes(e->L) : e->L.nsm * 4; }
-
-static int launch_dots(gmrm_engine* e, const int32_t* cols, int V, double* partial) {
-    const int T = e->cfg.T, tc = trait_chunk(e->L.E);
-    if (e->dot_kernel == 1) {                                   // table-lookup kernel, one trait per launch
-        for (int t = 0; t < T; t++) {
-            DotParams p{};
-            p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
-            p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = dot_nsl(e); p.Ttot = T; p.t0 = t;
-            if (launch_dot_table(e->L, p, e->stream) != 0)
-                return fail(GMRM_ECUDA, "table dot kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        }
-        return 0;
+// One marker-step (kernels.cu K1) for all traits: pending updates of the previous step (pcols/pV/pub, may be
+// none), tables, and the dot products of the V columns `cols` (V == 0: update only).
+static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const int32_t* pcols, int pV, double* partial, int* nlaunch) {
+    const int T = e->cfg.T;
+    int tc = e->step_tc, rpp = e->step_rpp;
+    if (V > e->Vl || V == 0) {                                  // test hook with its own marker count / update-only launch
+        step_plan(e->L, V, T, &tc, &rpp);
+        if (tc < 1 || rpp < 1) return fail(GMRM_EINVAL, "%d markers per step do not fit the step kernel's shared memory", V);
     }
     for (int t0 = 0; t0 < T; t0 += tc) {
-        DotParams p{};
-        p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.cols = cols; p.V = V;
-        p.eps = e->eps.p; p.npad = e->L.npad; p.partial = partial; p.nsl = e->L.nsm * 4;
-        p.Ttot = T; p.t0 = t0; p.zeros = e->zeros.p; p.variant = e->dot_variant; p.debug = e->dot_debug;
-        if (launch_dot(e->L, std::min(tc, T - t0), p, e->stream) != 0)
-            return fail(GMRM_ECUDA, "dot kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        StepParams p{};
+        p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.nrows = e->L.nrows; p.cols = cols; p.V = V;
+        p.eps = e->eps.p; p.npad = e->L.npad; p.Ttot = T; p.t0 = t0; p.rows_per_pass = rpp;
+        p.partial = partial; p.spart = e->spart.p;
+        p.pcols = pcols; p.pV = pV; p.pub = e->pub.p; p.mask4 = e->mask4.p;
+        p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
+        p.delta = e->cfg.world_size > 1 ? e->delta.p : nullptr;
+        p.err = e->err.p;
+        p.nwarps = e->step_warps;
+        const int rc = launch_step(e->L, std::min(tc, T - t0), p, e->stream);
+        if (rc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+        if (nlaunch) (*nlaunch)++;
     }
     return 0;
 }
 
 static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, const double* partial) {
     SampleParams p{};
-    p.V = V; p.T = e->cfg.T; p.G = e->cfg.G; p.K = e->cfg.K; p.N = e->cfg.N; p.nsl = dot_nsl(e); p.nsm = e->L.nsm;
+    p.V = V; p.T = e->cfg.T; p.G = e->cfg.G; p.K = e->cfg.K; p.N = e->cfg.N; p.nsm = e->L.nsm;
     p.seed = e->cfg.seed; p.r0 = e->r0; p.R = e->cfg.vranks; p.marker_begin = e->marker_begin; p.Mloc = e->Mloc;
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
-    p.group = e->group_loc.p; p.cva = e->cva.p; p.cvai = e->cvai.p; p.sigmag = e->sigmag.p; p.sigmae = e->sigmae.p;
-    p.pi = e->pi.p; p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
+    p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
+    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
+}
+
+static int check_step_error(gmrm_engine* e) {
+    int32_t herr = 0;
+    CU(cudaMemcpyAsync(&herr, e->err.p, 4, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    if (herr == 10) {
+        CU(cudaMemset(e->err.p, 0, 4));
+        return fail(GMRM_ECUDA, "step kernel: dynamic shared memory does not start at or below address %u", kTabBase);
+    }
+    return 0;
 }
 
 int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, double* out) {
@@ -488,27 +523,33 @@ int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, doubl
     CU(cudaSetDevice(e->cfg.device));
     const int T = e->cfg.T;
     DevBuf<int32_t> cols; DevBuf<double> partial, res;
+    const int chunk = std::min(n, 1024);
     int rc = cols.alloc(n); if (rc) return rc;
-    rc = partial.alloc((size_t)n * T * e->L.nsm * 16); if (rc) return rc;
+    rc = partial.alloc((size_t)chunk * T * e->L.nsm); if (rc) return rc;
     rc = res.alloc((size_t)n * T); if (rc) return rc;
     CU(cudaMemcpyAsync(cols.p, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
-    launch_eps_offset(e->eps.p, e->na01.p, e->L, T, nullptr, nullptr, e->spart.p, e->stream);   // refresh per-tile sums
-    rc = launch_dots(e, cols.p, n, partial.p); if (rc) return rc;
-    SampleParams sp = sample_params(e, cols.p, n, partial.p);
-    launch_finish_dots(sp, res.p, e->stream);
-    CU(cudaGetLastError());
+    for (int done = 0; done < n; done += chunk) {
+        const int m = std::min(chunk, n - done);
+        rc = launch_step_all(e, cols.p + done, m, nullptr, 0, partial.p, nullptr); if (rc) return rc;
+        SampleParams sp = sample_params(e, cols.p + done, m, partial.p);
+        launch_finish_dots(sp, res.p + (size_t)done * T, e->stream);
+        CU(cudaGetLastError());
+    }
     CU(cudaMemcpyAsync(out, res.p, (size_t)n * T * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    return GMRM_OK;
+    return check_step_error(e);
 }
 
 int gmrm_decode_marker(gmrm_engine* e, int32_t local_id, double* a, double* b) {
     if (!e || local_id < 0 || local_id >= e->Mloc || (!a && !b)) return fail(GMRM_EINVAL, "bad argument");
+    if (!e->bed_final) { int rcf = gmrm_finalize_bed(e); if (rcf) return rcf; }
     CU(cudaSetDevice(e->cfg.device));
     DevBuf<double> da, db;
     int rc = da.alloc(e->cfg.N); if (rc) return rc;
     rc = db.alloc(e->cfg.N); if (rc) return rc;
-    launch_decode_column(e->bed.p + (size_t)local_id * e->L.col_stride, e->L, da.p, db.p, e->stream);
+    uint32_t off[2];
+    CU(cudaMemcpy(off, e->miss_off.p + local_id, 8, cudaMemcpyDeviceToHost));
+    launch_decode_column(e->bed.p + (size_t)local_id * e->L.col_stride, e->L, e->miss_idx.p + off[0], off[1] - off[0], da.p, db.p, e->stream);
     CU(cudaGetLastError());
     if (a) CU(cudaMemcpyAsync(a, da.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
     if (b) CU(cudaMemcpyAsync(b, db.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
@@ -521,9 +562,7 @@ int gmrm_decode_namask(gmrm_engine* e, int32_t t, double* na) {
     CU(cudaSetDevice(e->cfg.device));
     DevBuf<double> d;
     int rc = d.alloc(e->cfg.N); if (rc) return rc;
-    // a NA-mask tile holds field 01 for observed individuals: decoded as a column, "b" is na_lut... of field != 3,
-    // and "a" is the field itself (1.0 observed, 0.0 not)
-    launch_decode_column(e->namask2.p + (size_t)t * e->L.col_stride, e->L, d.p, nullptr, e->stream);
+    launch_decode_namask(e->mask4.p + (size_t)t * e->L.col_stride, e->L, d.p, e->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(na, d.p, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -541,18 +580,14 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     std::vector<PubEntry> pub(T, PubEntry{0.0, 0.0});
     pub[trait].lam = dbeta * sg;                                   // phenotype.cpp:328
     pub[trait].mave = av;
-    DevBuf<int32_t> cols; DevBuf<PubEntry> dpub;
+    DevBuf<int32_t> cols;
     int rc = cols.alloc(1); if (rc) return rc;
-    rc = dpub.alloc(T); if (rc) return rc;
     CU(cudaMemcpyAsync(cols.p, &local_id, 4, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(dpub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));
-    UpdateParams up{};
-    up.bed = e->bed.p; up.col_stride = e->L.col_stride; up.cols = cols.p; up.V = 1; up.T = T; up.pub = dpub.p;
-    up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.na01 = e->na01.p; up.eps = e->eps.p; up.npad = e->L.npad; up.spart = e->spart.p; up.exact = 1;
-    if (launch_update(e->L, up, e->stream) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
+    CU(cudaMemcpyAsync(e->pub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));   // virtual rank 0's slot
+    rc = launch_step_all(e, nullptr, 0, cols.p, 1, nullptr, nullptr); if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
-    return GMRM_OK;
+    return check_step_error(e);
 }
 
 // ------------------------------------------------------------------------------------- the chain
@@ -659,37 +694,42 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     MuDrawParams mp{};
     mp.T = T; mp.it = it; mp.seed = c.seed; mp.sigmae = e->sigmae.p; mp.nonas = e->nonas.p; mp.mu = e->mu.p; mp.mu_old = e->mu_old.p; mp.rep_mu = d_mu;
     launch_mu_draw(mp, s);
-    launch_eps_offset(e->eps.p, e->na01.p, L, T, e->mu_old.p, e->mu.p, e->spart.p, s);
+    launch_eps_offset(e->eps.p, e->mask4.p, L, T, e->mu_old.p, e->mu.p, s);
     launch_steptab(e->steptab.p, Mm, Vl, e->r0, R, c.Mt, e->marker_begin, c.shuffle, c.seed, it, d_perm, s);
     launch_group_consts(T, G, K, c.N, e->sigmag.p, e->sigmae.p, e->pi.p, e->cva.p, e->cvai.p, e->nonas.p, e->gc.p, s);
     CU(cudaMemsetAsync(e->cass.p, 0, e->cass.n * 4, s));
     CU(cudaMemsetAsync(e->npub.p, 0, 8, s));
     launches += 4;
 
-    // ---- marker loop (bayes.cpp:375-555)
+    // ---- marker loop (bayes.cpp:375-555).  The residual update of step s is fused into the step kernel of
+    // step s+1 (it needs the same rows of eps the table build reads); an update-only launch flushes it before a
+    // cross-GPU exchange and after the last step.
     CU(cudaEventRecord(e->ev[1], s));
     const bool multi = c.world_size > 1;
+    const int32_t* pcols = nullptr;          // columns whose published updates are still pending
     for (int st = 0; st < Mm; st++) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
+        int nl = 0;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st], s));
-        if ((rc = launch_dots(e, cols, Vl, e->partial.p))) return rc;
+        if ((rc = launch_step_all(e, cols, Vl, pcols, pcols ? Vl : 0, e->partial.p, &nl))) return rc;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 1], s));
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
         launch_sample(sp, s);
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
-        UpdateParams up{};
-        up.bed = e->bed.p; up.col_stride = L.col_stride; up.cols = cols; up.V = Vl; up.T = T; up.pub = e->pub.p;
-        up.miss_off = e->miss_off.p; up.namask2 = e->namask2.p; up.na01 = e->na01.p; up.eps = e->eps.p; up.npad = L.npad; up.spart = e->spart.p; up.exact = 1;
-        up.delta = multi ? e->delta.p : nullptr;
-        if (launch_update(L, up, s) != 0) return fail(GMRM_ECUDA, "update kernel launch setup failed");
+        pcols = cols;
+        const bool exchange = multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
+        if (exchange || st == Mm - 1) {
+            if ((rc = launch_step_all(e, nullptr, 0, pcols, Vl, nullptr, &nl))) return rc;
+            pcols = nullptr;
+        }
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
-        launches += (e->dot_kernel == 1 ? T : (T + trait_chunk(L.E) - 1) / trait_chunk(L.E)) + 2;
+        launches += nl + 1;
         // ---- exchange (bayes.cpp:495-553): every sync_rate steps the shards all-reduce what they changed
-        if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+        if (exchange) {
             NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
             if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
-            launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, e->spart.p, s);
+            launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, s);
             launches += 2;
         }
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 4], s));
@@ -743,6 +783,10 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
                 e->last.allreduce_ms += ms;
             }
         }
+    if (herr == 10) {
+        CU(cudaMemset(e->err.p, 0, 4));
+        return fail(GMRM_ECUDA, "step kernel: dynamic shared memory does not start at or below address %u", kTabBase);
+    }
     if (herr != 0) {
         CU(cudaMemset(e->err.p, 0, 4));
         return fail(GMRM_EREPLAY, "replay variates exhausted (code %d): the chain asked for a draw the reference did not make", herr);

@@ -10,47 +10,6 @@ namespace gmrm {
 // =====================================================================================
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
-// Replace the LOW word of a 64-bit register pair, keeping the high word where it is.  With the
-// high word 0 the pair reads as the denormal double x * 2^-1074.  Writing it this way (and not as
-// a fresh {x, 0} pack) is what lets ptxas keep one persistent zero register per multiplier, so
-// that a genotype costs exactly one shift + one DFMA (checked with cuobjdump).
-__device__ __forceinline__ void set_lo(double& D, uint32_t x) {
-    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tmov.b64 %0, {%1, hi};\n\t}" : "+d"(D) : "r"(x));
-}
-
 __device__ __forceinline__ double warp_sum_fixed(double v) {   // fixed xor tree: reproducible
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -70,69 +29,91 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* red) {
     return t;
 }
 
-__device__ __forceinline__ void tile_offset_to_slot_byte(int E4, int off, int& ls, int& b) {
-    const int nw = E4 / 4, wbytes = nw * kLanesPerTile * 4;
-    if (off < wbytes) {
-        const int wi = off / (kLanesPerTile * 4), rem = off % (kLanesPerTile * 4);
-        ls = rem / 4; b = wi * 4 + rem % 4;
-        return;
-    }
-    off -= wbytes;
-    int bb = 4 * nw;
-    if (E4 & 2) {
-        if (off < kLanesPerTile * 2) { ls = off / 2; b = bb + off % 2; return; }
-        off -= kLanesPerTile * 2;
-        bb += 2;
-    }
-    ls = off; b = bb;
-}
-
-// The groups (registers) of one lane-slot of one tile.
-template <int E4>
-struct SlotRegs {
-    static constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
-    uint32_t w[NW > 0 ? NW : 1];
-    uint32_t h, b;
-    __device__ __forceinline__ void load(const uint8_t* tile, int ls) {   // generic / shared / global pointer
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = *reinterpret_cast<const uint32_t*>(tile + i * kLanesPerTile * 4 + ls * 4);
-        h = 0; b = 0;
-        if (NH) h = *reinterpret_cast<const uint16_t*>(tile + NW * kLanesPerTile * 4 + ls * 2);
-        if (NB) b = *(tile + NW * kLanesPerTile * 4 + NH * kLanesPerTile * 2 + ls);
-    }
-    // 2-bit field of individual k of the slot
-    __device__ __forceinline__ uint32_t field(int k) const {
-        if (k < 16 * NW) return (w[k / 16] >> (2 * (k % 16))) & 3u;
-        k -= 16 * NW;
-        if (NH) { if (k < 8) return (h >> (2 * k)) & 3u; k -= 8; }
-        return (b >> (2 * k)) & 3u;
-    }
-};
-
 // =====================================================================================
-// .bed ingestion: transcode PLINK bytes <-> tile-planar dosage bytes (bit-exact, invertible)
+// .bed ingestion: PLINK bytes <-> base-3 quad bytes + missing lists (bit-exact, invertible)
 // =====================================================================================
-__global__ void transcode_kernel(const uint8_t* __restrict__ src, int nmark, Layout L, uint8_t* __restrict__ dst) {
+__global__ void transcode_kernel(const uint8_t* __restrict__ plink, int nmark, Layout L, uint8_t* __restrict__ dst,
+                                 uint32_t* __restrict__ miss_counts) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (o >= L.col_stride || j >= nmark) return;
-    const int c = (int)(o / L.tile_bytes), off = (int)(o % L.tile_bytes);
-    int ls, b;
-    tile_offset_to_slot_byte(L.E4, off, ls, b);
-    const int64_t idx = ((int64_t)c * kLanesPerTile + ls) * L.E4 + b;
     uint8_t v = 0;
-    if (idx < L.mbytes) v = plink_to_dosage(src[(int64_t)j * L.mbytes + idx]);
+    if (o < L.mbytes) {
+        uint32_t mm;
+        v = plink_to_tri(plink[(int64_t)j * L.mbytes + o], &mm);
+        if (mm) atomicAdd(&miss_counts[j], (uint32_t)__popc(mm));
+    }
     dst[(int64_t)j * L.col_stride + o] = v;
 }
 
-__global__ void untranscode_kernel(const uint8_t* __restrict__ tiles, int nmark, Layout L, uint8_t* __restrict__ dst) {
+// Missing-genotype lists (CSR over markers), ascending individual index, from the staged PLINK bytes.
+// One warp per marker walks the column in byte order.  Pad individuals of the last byte are listed too
+// (the round trip keeps arbitrary pad bits); their residual slots are 0 and their NA bits clear.
+__global__ void fill_missing_kernel(const uint8_t* __restrict__ plink, int nmark, Layout L, const uint32_t* __restrict__ off,
+                                    uint32_t* __restrict__ out) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nmark) return;
+    if (off[j + 1] == off[j]) return;
+    const uint8_t* col = plink + (int64_t)j * L.mbytes;
+    uint32_t base = off[j];
+    for (int64_t idx0 = 0; idx0 < L.mbytes; idx0 += 32) {
+        const int64_t idx = idx0 + lane;
+        const uint32_t x = idx < L.mbytes ? col[idx] : 0xffu;
+        const uint32_t m = x & (~x >> 1) & 0x55u;            // code 01: low bit set, high bit clear
+        const uint32_t n = __popc(m);
+        uint32_t incl = n;                                   // inclusive warp scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        uint32_t w = base + incl - n;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (m & (1u << (2 * k))) out[w++] = (uint32_t)(idx * 4 + k);
+        base += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+__global__ void untranscode_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L, uint8_t* __restrict__ out) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int j = blockIdx.y;
     if (idx >= L.mbytes || j >= nmark) return;
-    const int64_t s = idx / L.E4;
-    const int b = (int)(idx % L.E4), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
-    const uint8_t y = tiles[(int64_t)j * L.col_stride + (int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, b)];
-    dst[(int64_t)j * L.mbytes + idx] = dosage_to_plink(y);
+    out[(int64_t)j * L.mbytes + idx] = fields_to_plink(tri_to_fields(bed[(int64_t)j * L.col_stride + idx]), 0u);
+}
+// second half of the inverse: listed individuals get code 01 back (dosage 0 was written as 11: clear its high bit)
+__global__ void unmiss_kernel(int nmark, Layout L, const uint32_t* __restrict__ off, const uint32_t* __restrict__ midx,
+                              uint8_t* __restrict__ out) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nmark) return;
+    for (uint32_t i = off[j] + lane; i < off[j + 1]; i += 32) {
+        const uint32_t ind = midx[i];
+        const uintptr_t a = (uintptr_t)(out + (int64_t)j * L.mbytes + (ind >> 2));
+        const uint32_t bit = (uint32_t)((a & 3) * 8) + 2 * (ind & 3) + 1;
+        atomicAnd(reinterpret_cast<uint32_t*>(a & ~(uintptr_t)3), ~(1u << bit));
+    }
+}
+
+// test hooks: the reference's table values of one column / one NA mask, individual by individual
+__global__ void decode_column_kernel(const uint8_t* __restrict__ col, Layout L, double* __restrict__ a, double* __restrict__ b) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.N) return;
+    const uint32_t d = (tri_to_fields(col[i >> 2]) >> (2 * (i & 3))) & 3u;
+    if (a) a[i] = (double)d;               // dotp_lut_a of a non-missing code
+    if (b) b[i] = 1.0;                     // dotp_lut_b
+}
+__global__ void decode_missing_kernel(const uint32_t* __restrict__ midx, uint32_t nmiss, int N, double* __restrict__ a, double* __restrict__ b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nmiss) return;
+    const uint32_t ind = midx[i];
+    if (ind >= (uint32_t)N) return;
+    if (a) a[ind] = 0.0;                   // missing: a = b = 0 (lut/mk_lut.cpp:25-32)
+    if (b) b[ind] = 0.0;
+}
+__global__ void decode_namask_kernel(const uint8_t* __restrict__ mask4, Layout L, double* __restrict__ na) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.N) return;
+    na[i] = ((mask4[i >> 2] >> (i & 3)) & 1u) ? 1.0 : 0.0;   // na_lut (lut/mk_lut_na.cpp:25-29)
 }
 
 // Synthetic PLINK bytes: per-marker MAF ~ U(lo, hi), dosage ~ Binomial(2, p).
@@ -165,92 +146,46 @@ __global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int 
     dst[(int64_t)j * L.mbytes + idx] = byte;
 }
 
-// Missing-genotype lists (CSR over shard-local markers), ascending individual index.
-// One warp per marker walks the column in PLINK byte order.
-__device__ __forceinline__ uint32_t missing_fields(const uint8_t* col, const Layout& L, int64_t idx) {
-    const int64_t s = idx / L.E4;
-    const int b = (int)(idx % L.E4), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
-    const uint32_t y = col[(int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, b)];
-    uint32_t m = y & (y >> 1) & 0x55u;            // field == 3
-    const int64_t i0 = idx * 4;
-    if (i0 + 3 >= L.N) {                          // drop pad individuals of the last byte
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (i0 + k >= L.N) m &= ~(1u << (2 * k));
-    }
-    return m;
-}
-
-__global__ void count_missing_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L, uint32_t* __restrict__ counts) {
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (j >= nmark) return;
-    const uint8_t* col = bed + (int64_t)j * L.col_stride;
-    uint32_t n = 0;
-    for (int64_t idx = lane; idx < L.mbytes; idx += 32) n += __popc(missing_fields(col, L, idx));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
-    if (lane == 0) counts[j] = n;
-}
-
-__global__ void fill_missing_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L, const uint32_t* __restrict__ off,
-                                    uint32_t* __restrict__ out) {
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (j >= nmark) return;
-    const uint8_t* col = bed + (int64_t)j * L.col_stride;
-    uint32_t base = off[j];
-    for (int64_t idx0 = 0; idx0 < L.mbytes; idx0 += 32) {
-        const int64_t idx = idx0 + lane;
-        const uint32_t m = idx < L.mbytes ? missing_fields(col, L, idx) : 0u;
-        const uint32_t n = __popc(m);
-        uint32_t incl = n;                        // inclusive warp scan
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        uint32_t w = base + incl - n;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-            if (m & (1u << (2 * k))) out[w++] = (uint32_t)(idx * 4 + k);
-        base += __shfl_sync(0xffffffffu, incl, 31);
-    }
-}
-
-// test hooks: the reference's table values of one column / one NA mask, individual by individual
-__global__ void decode_column_kernel(const uint8_t* __restrict__ col, Layout L, double* __restrict__ a, double* __restrict__ b) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L.N) return;
-    const int64_t s = i / L.E;
-    const int k = (int)(i % L.E), c = (int)(s / kLanesPerTile), ls = (int)(s % kLanesPerTile);
-    const uint32_t y = col[(int64_t)c * L.tile_bytes + tile_byte_offset(L.E4, ls, k / 4)];
-    const uint32_t d = (y >> (2 * (k % 4))) & 3u;        // 0,1,2 = dosage, 3 = missing
-    if (a) a[i] = d == 3 ? 0.0 : (double)d;              // dotp_lut_a
-    if (b) b[i] = d == 3 ? 0.0 : 1.0;                    // dotp_lut_b (for a NA mask tile: na_lut)
-}
-
 // =====================================================================================
 // marker statistics, PhenMgr::compute_markers_statistics (phenotype.cpp:466-556), from integer
 // counts of each dosage under the trait's NA mask: the sums of the
 // reference's loops are sums of small integers, hence these counts exactly.
 // =====================================================================================
-constexpr int kStatsMaxT = 32;
 __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
-                                                    const uint8_t* __restrict__ namask2, const int32_t* __restrict__ nonas,
+                                                    const uint8_t* __restrict__ mask4, const uint32_t* __restrict__ miss_off,
+                                                    const uint32_t* __restrict__ miss_idx, const int32_t* __restrict__ nonas,
                                                     int T, double* __restrict__ mave, double* __restrict__ msig) {
     const int j = blockIdx.x;
     if (j >= nmark) return;
+    __shared__ uint8_t fld[kTabEntries];     // base-3 byte -> 2-bit dosage fields
+    __shared__ uint8_t exp4[16];             // NA nibble -> 2-bit fields (01 = observed)
+    __shared__ int red[3][4];
+    for (int e = threadIdx.x; e < kTabEntries; e += blockDim.x) fld[e] = (uint8_t)tri_to_fields(e);
+    if (threadIdx.x < 16) {
+        const uint32_t m = threadIdx.x;
+        exp4[m] = (uint8_t)((m & 1u) | ((m & 2u) << 1) | ((m & 4u) << 2) | ((m & 8u) << 3));
+    }
+    __syncthreads();
     const uint32_t* col = reinterpret_cast<const uint32_t*>(bed + (int64_t)j * L.col_stride);
     const int nwords = (int)(L.col_stride / 4);
-    __shared__ int red[3][4];
+    const uint32_t m0 = miss_off[j], m1 = miss_off[j + 1];
     for (int t = 0; t < T; t++) {
-        const uint32_t* nm = reinterpret_cast<const uint32_t*>(namask2 + (int64_t)t * L.col_stride);
+        const uint8_t* nmb = mask4 + (int64_t)t * L.col_stride;
+        const uint32_t* nm = reinterpret_cast<const uint32_t*>(nmb);
         int n0 = 0, n1 = 0, n2 = 0;
         for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-            const uint32_t w = col[i], m = nm[i];
-            const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+            const uint32_t w = col[i], mw = nm[i];
+            const uint32_t f = fld[w & 0xffu] | (fld[(w >> 8) & 0xffu] << 8) | (fld[(w >> 16) & 0xffu] << 16) | (fld[w >> 24] << 24);
+            const uint32_t m = exp4[mw & 0xfu] | (exp4[(mw >> 8) & 0xfu] << 8) | (exp4[(mw >> 16) & 0xfu] << 16) | (exp4[(mw >> 24) & 0xfu] << 24);
+            const uint32_t lo = f & 0x55555555u, hi = (f >> 1) & 0x55555555u;
             n1 += __popc(lo & ~hi & m);
             n2 += __popc(hi & ~lo & m);
             n0 += __popc(~(lo | hi) & 0x55555555u & m);
+        }
+        // missing genotypes were stored as dosage 0: take the observed ones out of n0
+        for (uint32_t i = m0 + threadIdx.x; i < m1; i += blockDim.x) {
+            const uint32_t ind = miss_idx[i];
+            n0 -= (nmb[ind >> 2] >> (ind & 3)) & 1;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -277,47 +212,27 @@ __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ 
 // =====================================================================================
 // residual helpers
 // =====================================================================================
-// Phenotype::offset_epsilon twice (bayes.cpp:351,359): eps += mu_old*na; eps -= mu_new*na; and the
-// per-tile sum of eps that the sampler turns into sum b*eps.
-// A tile is the contiguous range of individuals [tile*128*E, (tile+1)*128*E): one block walks it with
-// coalesced accesses; na01 is the per-individual 0/1 NA indicator.
-__global__ void __launch_bounds__(256) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ na01, Layout L,
-                                                         const double* __restrict__ mu_old, const double* __restrict__ mu_new,
-                                                         double* __restrict__ spart) {
-    const int t = blockIdx.y, per = kLanesPerTile * L.E;
-    __shared__ double red[8];
-    const int64_t base = (int64_t)t * L.npad + (int64_t)blockIdx.x * per;
-    const double a = mu_old ? mu_old[t] : 0.0, b = mu_new ? -mu_new[t] : 0.0;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < per; i += 256) {
-        double v = eps[base + i];
-        const double m = na01[base + i] ? 1.0 : 0.0;
-        v += a * m;            // phenotype.cpp:408
-        v += b * m;
-        eps[base + i] = v;
-        s += v;
-    }
-    const double tot = block_sum_fixed(s, red);
-    if (threadIdx.x == 0) spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
+// Phenotype::offset_epsilon twice (bayes.cpp:351,359): eps += mu_old*na; eps -= mu_new*na
+__global__ void __launch_bounds__(256) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ mask4, Layout L,
+                                                         const double* __restrict__ mu_old, const double* __restrict__ mu_new) {
+    const int t = blockIdx.y;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L.npad) return;
+    if (!((mask4[(int64_t)t * L.col_stride + (i >> 2)] >> (i & 3)) & 1u)) return;
+    double v = eps[(int64_t)t * L.npad + i];
+    v += mu_old[t];            // phenotype.cpp:408 (na == 1)
+    v += -mu_new[t];
+    eps[(int64_t)t * L.npad + i] = v;
 }
 
 // Multi-GPU exchange (replaces the per-marker Allgatherv + local recompute of bayes.cpp:500-547): after the
-// all-reduce of the shards' residual deltas, add what the OTHER shards changed, clear the local delta, refresh
-// the per-tile sums.
+// all-reduce of the shards' residual deltas, add what the OTHER shards changed and clear the local delta.
 __global__ void __launch_bounds__(256) eps_merge_kernel(double* __restrict__ eps, double* __restrict__ loc,
-                                                        const double* __restrict__ tot, Layout L, double* __restrict__ spart) {
-    const int t = blockIdx.y, per = kLanesPerTile * L.E;
-    __shared__ double red[8];
-    const int64_t base = (int64_t)t * L.npad + (int64_t)blockIdx.x * per;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < per; i += 256) {
-        const double v = eps[base + i] + (tot[base + i] - loc[base + i]);
-        eps[base + i] = v;
-        loc[base + i] = 0.0;
-        s += v;
-    }
-    const double r = block_sum_fixed(s, red);
-    if (threadIdx.x == 0) spart[(int64_t)t * L.nsm + blockIdx.x] = r;
+                                                        const double* __restrict__ tot, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    eps[i] = eps[i] + (tot[i] - loc[i]);
+    loc[i] = 0.0;
 }
 
 // sum_{i<n} eps_i^2 per trait (Phenotype::epsilon_sumsqr, phenotype.cpp:251-261)
@@ -331,316 +246,440 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 }
 
 // =====================================================================================
-// K1: streamed decode-and-reduce of the step's V columns against the residuals.
+// K1: one marker-step of one GPU -- apply the previous step's published updates, build the look-up
+// tables of this CTA's rows, stream the step's V columns through them (layout.h).
 //
-// One CTA per tile (SM).  Warp 4*kWPS is the producer: one lane issues one cp.async.bulk per
-// (marker, tile) into an 8-stage shared-memory ring, completion on mbarriers.  The other 4*kWPS
-// warps are consumers: warp w serves sub-partition w&3 and takes every kWPS-th batch of 8 markers.
-// A consumer lane owns E consecutive individuals: their weights w_k stay in registers for the whole
-// launch, a marker costs E x (shift + DFMA) per lane (layout.h), then an 8-marker select-free
-// transposed butterfly leaves one per-warp partial per marker, written to partial[r][t][tile*4+sp].
+// One CTA per SM: NW consumer warps + 1 producer warp.  CTA c owns rows [row_begin(c), row_begin(c+1)) of
+// every column and of the residuals.  The rows are taken in passes of <= rows_per_pass rows (as many
+// (row, trait) table slots as shared memory holds):
+//   update: every thread owns up to 2 quads of the CTA's rows per round; for each published marker of the
+//           previous step (rank order) it adds  v[dosage]  to its 4 residuals -- one PRMT + LDS.64 + DADD per
+//           individual, NA / missing individuals are routed to a zero entry
+//   build : half-warp <-> (slot, byte k, third d3 of the 81 entries); lane l owns the quad 4l+k of the row:
+//           reads its 4 residuals, writes 27 entries  sum_k d_k eps_k  (conflict-free 8-byte stores)
+//   feed  : the producer warp copies, for every batch of 16 markers, the pass's rows of each marker
+//           (<= 256 contiguous bytes) into an 8-stage shared-memory ring with cp.async.bulk (TMA),
+//           completion on mbarriers; it runs ahead across passes
+//   stream: consumer warp w takes batches w, w+NW, ... of 16 markers; in a batch, half-warp h works on marker
+//           2i+h of pair i = 0..7; lane l reads word l of each row from the ring and per byte does
+//           PRMT -> LDS.64 -> DADD  into the pair's accumulator; a 16-lane transposed butterfly leaves one
+//           total per marker, added to the marker's partial sum in shared memory (each marker is always
+//           served by the same lane: plain read-modify-write).
+// At the end the CTA writes partial[v][t][cta] and its sum of residuals spart[t][cta]; the sampler kernel
+// adds the nsm partials of a marker in a fixed order.
 // =====================================================================================
-template <int E4, int T, int WPS, int BATCH>
-__global__ void __launch_bounds__((4 * WPS + 1) * 32, 1) dot_kernel(const DotParams p) {
-    constexpr int TILE = kLanesPerTile * E4;
-    constexpr int E = 4 * E4;
-    constexpr int NW = E4 / 4, NH = (E4 % 4) / 2, NB = E4 % 2;
-    constexpr int RING = dot_ring_tiles(WPS);
-    constexpr int STAGES = RING / BATCH;
-    constexpr int NTHREADS = (4 * WPS + 1) * 32;
-    constexpr int LOGB = BATCH == 8 ? 3 : 2;
-    static_assert(BATCH == 8 || BATCH == 4, "batch of 4 or 8 markers");
-    static_assert(STAGES % WPS == 0, "a stage must always serve the same consumer group");
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ring = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + RING * TILE);
-    uint64_t* empty = full + STAGES;
-    int32_t* scols = reinterpret_cast<int32_t*>(empty + STAGES);     // the step's columns, padded with -1
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel, not as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void consumer_sync(int nthreads) {      // named barrier 1: the consumer warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nb = (p.V + BATCH - 1) / BATCH;
+struct PubStage { double v[4]; };   // increment by dosage: (a - mave*b) * dbeta*msig for a = 0,1,2 (b = 1); v[3] = 0
+struct PubInfo { int32_t col; uint32_t nmiss; };
 
-    for (int i = threadIdx.x; i < nb * BATCH; i += NTHREADS) scols[i] = i < p.V ? p.cols[i] : -1;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+template <int IMM>
+__device__ __forceinline__ double lds_f64_imm(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int IMM>
+__device__ __forceinline__ uint32_t lds_u32_imm(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
+    return v;
+}
+template <int K>
+__device__ __forceinline__ uint32_t tab_addr(uint32_t word, uint32_t low) {   // byte K of word -> e*256 + low
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(word), "r"(low), "n"(0x5504 | (K << 4)));
+    return d;
+}
+template <int K>
+__device__ __forceinline__ uint32_t byte_into(uint32_t word, uint32_t base) { // (base & ~0xff) | byte K of word
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(word), "r"(base), "n"(0x7650 | K));
+    return d;
+}
+__host__ __device__ constexpr int tab_imm(int slot, int k) {
+    return (int)kTabBase + slot * kSlotBytes + (k >> 1) * kRegionBytes + (k & 1) * 128;
+}
+// ring geometry: a batch of 16 markers; the rows of one marker are contiguous; an even row count gets 64 B of
+// padding so that the two half-warps (markers 2i and 2i+1) read disjoint banks
+__host__ __device__ constexpr int ring_marker_stride(int nr) { return nr * kRowBytes + ((nr & 1) ? 0 : kRowBytes); }
+constexpr int kRingStages = 8;
+constexpr int kRingStageBytes = kBatch * ring_marker_stride(kMaxSlots);    // 16 x 320
+
+// acc[t] += table(slot SLOT + t, byte K)[e] for the T traits of a row: one LDS.64 + one DADD each
+template <int SLOT, int K, int T, int TT = 0>
+__device__ __forceinline__ void lookup_traits(double (&acc)[T], uint32_t a) {
+    if constexpr (TT < T) {
+        acc[TT] += lds_f64_imm<tab_imm(SLOT + TT, K)>(a);
+        lookup_traits<SLOT, K, T, TT + 1>(acc, a);
     }
-    __syncthreads();
+}
 
-    if (warp == 4 * WPS) {
-        if (p.debug == 2) return;                     // debug: compute only, nothing is fed
-        // ---------------- producer: lane j < BATCH issues the copy of marker j of every batch ----------------
-        const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * TILE;
-        for (int b = 0; b < nb; b++) {
-            const int s = b % STAGES;
-            if (b >= STAGES) mbar_wait(&empty[s], (uint32_t)((b / STAGES) - 1) & 1u);
-            const int col = lane < BATCH ? scols[b * BATCH + lane] : -1;
-            const uint32_t nvalid = __popc(__ballot_sync(0xffffffffu, col >= 0));
-            if (lane == 0) mbar_expect_tx(&full[s], nvalid * TILE);
-            __syncwarp();
-            if (col >= 0) bulk_g2s(ring + (s * BATCH + lane) * TILE, tile0 + (int64_t)col * p.col_stride, TILE, &full[s]);
-        }
-        return;
+// ---- (a) pending updates: Phenotype::update_epsilon (phenotype.cpp:326-329,375-390) for every published marker
+// of the previous step, in virtual-rank order, restricted to this CTA's rows.  All NT threads of the CTA work.
+template <int T, int NT>
+__device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* stage, PubInfo* info, uint32_t* lut,
+                              uint32_t* bitmap, int* wcnt) {
+    constexpr int NWALL = NT / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nq = nr * kRowBytes;                      // quads of my rows
+    // base-3 byte -> byte offsets (8 * dosage) of its four individuals into a PubStage
+    for (int e = tid; e < kTabEntries; e += NT) {
+        const uint32_t f = tri_to_fields(e);
+        lut[e] = ((f & 3u) << 3) | (((f >> 2) & 3u) << 11) | (((f >> 4) & 3u) << 19) | (((f >> 6) & 3u) << 27);
     }
-
-    // ---------------- consumers ----------------
-    const int sp = warp & 3, q = warp >> 2;
-    const int ls = sp * 32 + lane;
-    const int64_t slot = (int64_t)blockIdx.x * kLanesPerTile + ls;
-
-    // weights of this lane's E individuals, group by group (layout.h: w_k = 2^1000 (eps_k - eps_{k+1}/4))
-    double wgt[E][T];
-#pragma unroll
+    const uint32_t lut_u32 = smem_u32(lut), stage_u32 = smem_u32(stage);
     for (int t = 0; t < T; t++) {
-        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + slot * E;
-        double ev[E + 1];
+        const int tt = p.t0 + t;
+        double* eps_t = p.eps + (int64_t)tt * p.npad + (int64_t)rb * kRowInd;
+        const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride + (int64_t)rb * kRowBytes;
+        for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
+            double e[2][4], e0[2][4];
+            uint32_t nmask[2];                          // 0x18 in byte k: individual k is not observed -> zero entry
+            bool have[2];
 #pragma unroll
-        for (int k = 0; k < E; k++) ev[k] = e[k];
-        ev[E] = 0.0;
+            for (int qq = 0; qq < 2; qq++) {
+                const int q = q0 + qq * NT + tid;
+                have[qq] = q < nq;
+                const uint32_t na = have[qq] ? mask_t[q] : 0u;
+                nmask[qq] = ((na & 1u) ? 0u : 0x18u) | ((na & 2u) ? 0u : 0x1800u) | ((na & 4u) ? 0u : 0x180000u) | ((na & 8u) ? 0u : 0x18000000u);
 #pragma unroll
-        for (int k = 0; k < E; k++) {
-            // last genotype of a group has no successor inside the group
-            const bool last = (k < 16 * NW) ? ((k % 16) == 15) : (NH && k < 16 * NW + 8) ? (k == 16 * NW + 7) : (k == E - 1);
-            wgt[k][t] = group_weight(ev[k], last ? 0.0 : ev[k + 1]);
+                for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * q + k] : 0.0; e0[qq][k] = e[qq][k]; }
+            }
+            bool touched = false;
+            for (int v_lo = 0; v_lo < p.pV; v_lo += NT) {
+                // ordered compaction of the window's published entries (rank order is preserved)
+                const int v = v_lo + tid;
+                PubEntry pe{0.0, 0.0};
+                if (v < p.pV) pe = p.pub[(int64_t)v * p.Ttot + tt];
+                const bool on = pe.lam != 0.0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, on);
+                __syncthreads();
+                if (lane == 0) wcnt[warp] = __popc(bal);
+                __syncthreads();
+                int ord = __popc(bal & ((1u << lane) - 1u)), total = 0;
+                for (int w = 0; w < NWALL; w++) { const int c = wcnt[w]; if (w < warp) ord += c; total += c; }
+                for (int r0 = 0; r0 < total; r0 += kPubCap) {
+                    const int n = min(kPubCap, total - r0);
+                    __syncthreads();
+                    if (on && ord >= r0 && ord < r0 + n) {
+                        PubStage& s = stage[ord - r0];
+                        const double mdb = -pe.mave;               // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
+                        s.v[0] = (mdb * 1.0 + 0.0) * pe.lam;
+                        s.v[1] = (mdb * 1.0 + 1.0) * pe.lam;
+                        s.v[2] = (mdb * 1.0 + 2.0) * pe.lam;
+                        s.v[3] = 0.0;
+                        const int col = p.pcols[v];
+                        info[ord - r0].col = col;
+                        info[ord - r0].nmiss = p.miss_off[col + 1] - p.miss_off[col];
+                    }
+                    __syncthreads();
+                    touched = true;
+                    for (int g0 = 0; g0 < n; g0 += 8) {
+                        uint32_t by[8][2];
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+#pragma unroll
+                            for (int qq = 0; qq < 2; qq++) {
+                                by[j][qq] = 0;
+                                if (g0 + j < n && have[qq])
+                                    by[j][qq] = p.bed[(int64_t)info[g0 + j].col * p.col_stride + (int64_t)rb * kRowBytes + q0 + qq * NT + tid];
+                            }
+                        const uint32_t gbase = stage_u32 + (uint32_t)g0 * 32u;   // 256-aligned: stage is, g0 is a multiple of 8
+#define GMRM_APPLY(J)                                                                                              \
+    if (g0 + J < n) {                                                                                             \
+        const bool hasmiss = info[g0 + J].nmiss != 0; /* CTA-uniform */                                           \
+        if (hasmiss) {                                                                                            \
+            for (int i = tid; i < nr * 8; i += NT) bitmap[i] = 0u;                                                \
+            __syncthreads();                                                                                      \
+            const uint32_t mo = p.miss_off[info[g0 + J].col];                                                     \
+            for (uint32_t i = tid; i < info[g0 + J].nmiss; i += NT) {                                             \
+                const int64_t loc = (int64_t)p.miss_idx[mo + i] - (int64_t)rb * kRowInd;                          \
+                if (loc >= 0 && loc < (int64_t)nr * kRowInd) atomicOr(&bitmap[loc >> 5], 1u << (loc & 31));       \
+            }                                                                                                     \
+            __syncthreads();                                                                                      \
+        }                                                                                                         \
+        _Pragma("unroll") for (int qq = 0; qq < 2; qq++) {                                                        \
+            if (have[qq]) {                                                                                       \
+                uint32_t off;                                                                                     \
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(lut_u32 + by[J][qq] * 4u));              \
+                off |= nmask[qq];                                                                                 \
+                if (hasmiss) {   /* missing here: a = b = 0, no change */                                         \
+                    const int q = q0 + qq * NT + tid;                                                             \
+                    const uint32_t sk = (bitmap[q >> 3] >> ((q & 7) * 4)) & 0xfu;                                 \
+                    off |= ((sk & 1u) ? 0x18u : 0u) | ((sk & 2u) ? 0x1800u : 0u) | ((sk & 4u) ? 0x180000u : 0u) | ((sk & 8u) ? 0x18000000u : 0u); \
+                }                                                                                                 \
+                e[qq][0] += lds_f64_imm<J * 32>(byte_into<0>(off, gbase));   /* * na (phenotype.cpp:388) */       \
+                e[qq][1] += lds_f64_imm<J * 32>(byte_into<1>(off, gbase));                                        \
+                e[qq][2] += lds_f64_imm<J * 32>(byte_into<2>(off, gbase));                                        \
+                e[qq][3] += lds_f64_imm<J * 32>(byte_into<3>(off, gbase));                                        \
+            }                                                                                                     \
+        }                                                                                                         \
+        if (hasmiss) __syncthreads();                                                                             \
+    }
+                        GMRM_APPLY(0) GMRM_APPLY(1) GMRM_APPLY(2) GMRM_APPLY(3) GMRM_APPLY(4) GMRM_APPLY(5) GMRM_APPLY(6) GMRM_APPLY(7)
+#undef GMRM_APPLY
+                    }
+                }
+            }
+            if (touched) {
+#pragma unroll
+                for (int qq = 0; qq < 2; qq++) {
+                    if (!have[qq]) continue;
+                    const int q = q0 + qq * NT + tid;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) eps_t[4 * q + k] = e[qq][k];
+                    if (p.delta) {
+                        double* d = p.delta + (int64_t)tt * p.npad + (int64_t)rb * kRowInd + 4 * q;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) d[k] += e[qq][k] - e0[qq][k];   // what this shard changed since the last exchange
+                    }
+                }
+            }
         }
     }
+}
 
-    // accumulator slot j of this lane holds marker j ^ P (P = lane bits 4,3[,2] reversed): makes the
-    // transposed butterfly below select-free
-    int P = 0;
+// ---- (b) tables of rows [row0, row0 + nrp) for T traits, by the NC consumer threads; es[t] accumulates this
+// thread's share of sum eps
+template <int T, int NC>
+__device__ __forceinline__ void build_tables(const StepParams& p, int row0, int nrp, double (&es)[T]) {
+    const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+    const int nunits = nrp * T * 4 * 3;
+    for (int u = hw; u < nunits; u += NC / 16) {
+        const int d3 = u % 3, line = u / 3, k = line & 3, slot = line >> 2, rr = slot / T, t = slot - rr * T;
+        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + ((int64_t)(row0 + rr) * kRowBytes + 4 * l16 + k) * 4;
+        const double2 e01 = *reinterpret_cast<const double2*>(e), e23 = *reinterpret_cast<const double2*>(e + 2);
+        if (d3 == 0) {
+            const double s4 = (e01.x + e01.y) + (e23.x + e23.y);
 #pragma unroll
-    for (int i = 0; i < LOGB; i++) P |= ((lane >> (4 - i)) & 1) << (LOGB - 1 - i);
-    // shared-memory offsets (from the stage base) of this lane's word / half / byte of accumulator slot j
-    uint32_t offw[BATCH], offh[BATCH], offb[BATCH];
-#pragma unroll
-    for (int j = 0; j < BATCH; j++) {
-        offw[j] = (uint32_t)((j ^ P) * TILE + ls * 4);
-        offh[j] = (uint32_t)((j ^ P) * TILE + NW * kLanesPerTile * 4 + ls * 2);
-        offb[j] = (uint32_t)((j ^ P) * TILE + NW * kLanesPerTile * 4 + NH * kLanesPerTile * 2 + ls);
-    }
-    double D[BATCH];        // one persistent (lo = shifted word, hi = 0) multiplier pair per accumulator
-#pragma unroll
-    for (int j = 0; j < BATCH; j++) D[j] = p.zeros[j * NTHREADS + threadIdx.x];
-    const uint32_t ring_u32 = smem_u32(ring);
-
-    for (int b = q; b < nb; b += WPS) {
-        const int s = b % STAGES;
-        if (p.debug != 2) mbar_wait(&full[s], (uint32_t)(b / STAGES) & 1u);
-        const uint32_t st = ring_u32 + (uint32_t)(s * BATCH * TILE);
-        uint32_t gw[BATCH][NW > 0 ? NW : 1], gh[BATCH], gb[BATCH];
-#pragma unroll
-        for (int j = 0; j < BATCH; j++) {
-#pragma unroll
-            for (int wi = 0; wi < NW; wi++)
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gw[j][wi]) : "r"(st + offw[j] + wi * kLanesPerTile * 4));
-            gh[j] = 0; gb[j] = 0;
-            if (NH) asm volatile("ld.shared.u16 %0, [%1];" : "=r"(gh[j]) : "r"(st + offh[j]));
-            if (NB) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(gb[j]) : "r"(st + offb[j]));
+            for (int tt = 0; tt < T; tt++)
+                if (tt == t) es[tt] += s4;
         }
+        const double x0[3] = {0.0, e01.x, e01.x + e01.x}, x1[3] = {0.0, e01.y, e01.y + e01.y};
+        const double x2[3] = {0.0, e23.x, e23.x + e23.x};
+        const double x3 = d3 == 0 ? 0.0 : (d3 == 1 ? e23.y : e23.y + e23.y);
+        const uint32_t base = (uint32_t)tab_imm(slot, k) + (uint32_t)(27 * d3) * 256u + (uint32_t)l16 * 8u;
+#pragma unroll
+        for (int d2 = 0; d2 < 3; d2++) {
+            const double hi = x2[d2] + x3;
+#pragma unroll
+            for (int d1 = 0; d1 < 3; d1++)
+#pragma unroll
+                for (int d0 = 0; d0 < 3; d0++) {
+                    const double val = (x0[d0] + x1[d1]) + hi;
+                    asm volatile("st.shared.f64 [%0], %1;" ::"r"(base + (uint32_t)(d0 + 3 * d1 + 9 * d2) * 256u), "d"(val) : "memory");
+                }
+        }
+    }
+}
+
+// ---- (c) stream the V columns through the tables of NR rows.  gb0 = ring sequence number of this pass's batch 0.
+template <int NR, int T, int NW>
+__device__ __forceinline__ void stream_rows(const StepParams& p, double* part, uint32_t ring_u32, uint64_t* full, uint64_t* empty,
+                                            const volatile int* issued, int gb0) {
+    constexpr int STRIDE = ring_marker_stride(NR);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = lane >> 4, l16 = lane & 15;
+    const uint32_t low = (uint32_t)l16 * 8u;
+    const int nb = (p.V + kBatch - 1) / kBatch;
+    const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
+    const int own = ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1);   // pair whose total this lane ends up with
+    const uint32_t lane_off = (uint32_t)(h * STRIDE + l16 * 4);
+
+    for (int b = warp; b < nb; b += NW) {
+        const int gb = gb0 + b, s = gb % kRingStages;
+        // Several consumers can be more than one ring revolution ahead of the producer; a parity wait is only
+        // meaningful once the stage's barrier has reached this batch's phase, i.e. once the batch has been issued.
+        for (uint32_t spins = 0; *issued <= gb; ++spins)
+            if (spins > (1u << 26)) __trap();
+        mbar_wait(&full[s], (uint32_t)(gb / kRingStages) & 1u);
+        const uint32_t st = ring_u32 + (uint32_t)(s * kRingStageBytes) + lane_off;
+        uint32_t W[8][NR];
+#define GMRM_LOADW(I)                                                                                   \
+    {                                                                                                   \
+        W[I][0] = lds_u32_imm<I * 2 * STRIDE>(st);                                                      \
+        if constexpr (NR > 1) W[I][NR > 1 ? 1 : 0] = lds_u32_imm<I * 2 * STRIDE + 64>(st);              \
+        if constexpr (NR > 2) W[I][NR > 2 ? 2 : 0] = lds_u32_imm<I * 2 * STRIDE + 128>(st);             \
+        if constexpr (NR > 3) W[I][NR > 3 ? 3 : 0] = lds_u32_imm<I * 2 * STRIDE + 192>(st);             \
+    }
+        GMRM_LOADW(0) GMRM_LOADW(1) GMRM_LOADW(2) GMRM_LOADW(3) GMRM_LOADW(4) GMRM_LOADW(5) GMRM_LOADW(6) GMRM_LOADW(7)
+#undef GMRM_LOADW
+        double acc[8][T];
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int t = 0; t < T; t++) acc[i][t] = 0.0;
+
+#define GMRM_LOOKUP(RR, K)                                                    \
+    _Pragma("unroll") for (int i = 0; i < 8; i++)                             \
+        lookup_traits<RR * T, K, T>(acc[i], tab_addr<K>(W[i][RR], low));
+#define GMRM_ROW(RR)                                                          \
+    if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_LOOKUP(RR, 1) GMRM_LOOKUP(RR, 2) GMRM_LOOKUP(RR, 3) }
+        // release the stage once its words are in registers (the comparison makes the arrive wait for the last load;
+        // bytes are < 81, so it is never true)
         __syncwarp();
-        if (lane == 0 && p.debug != 2) mbar_arrive(&empty[s]);     // registers hold the batch: the stage can be refilled
-        if (p.debug == 1) continue;                   // debug: feed only, no arithmetic
+        if (lane == 0 || W[7][NR - 1] == 0xffffffffu) mbar_arrive(&empty[s]);
+        GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3)
+#undef GMRM_ROW
+#undef GMRM_LOOKUP
 
-        double acc[BATCH][T];
-#pragma unroll
-        for (int j = 0; j < BATCH; j++)
-#pragma unroll
-            for (int t = 0; t < T; t++) acc[j][t] = 0.0;
-
-#pragma unroll
-        for (int wi = 0; wi < NW; wi++)
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-#pragma unroll
-                for (int j = 0; j < BATCH; j++) {
-                    set_lo(D[j], gw[j][wi] << (30 - 2 * k));
-#pragma unroll
-                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[wi * 16 + k][t], acc[j][t]);
-                }
-        if (NH) {
-#pragma unroll
-            for (int k = 0; k < 8; k++)
-#pragma unroll
-                for (int j = 0; j < BATCH; j++) {
-                    set_lo(D[j], gh[j] << (30 - 2 * k));
-#pragma unroll
-                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + k][t], acc[j][t]);
-                }
-        }
-        if (NB) {
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-#pragma unroll
-                for (int j = 0; j < BATCH; j++) {
-                    set_lo(D[j], gb[j] << (30 - 2 * k));
-#pragma unroll
-                    for (int t = 0; t < T; t++) acc[j][t] = fma(D[j], wgt[16 * NW + 8 * NH + k][t], acc[j][t]);
-                }
-        }
-
-        // transposed butterfly: BATCH markers x 32 lanes -> total of marker P in every lane sharing P
+        // 16-lane transposed butterfly: 8 pair accumulators -> the total of pair `own` (fixed order: reproducible)
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            double a[BATCH];
+            double b4[4], b2[2], b1;
 #pragma unroll
-            for (int j = 0; j < BATCH; j++) a[j] = acc[j][t];
-#pragma unroll
-            for (int i = 0; i < LOGB; i++) {
-                const int half = BATCH >> (i + 1);
-#pragma unroll
-                for (int j = 0; j < half; j++) a[j] += __shfl_xor_sync(0xffffffffu, a[j + half], 16 >> i);
+            for (int j = 0; j < 4; j++) {
+                const double keep = hi8 ? acc[4 + j][t] : acc[j][t], send = hi8 ? acc[j][t] : acc[4 + j][t];
+                b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
             }
 #pragma unroll
-            for (int o = 16 >> LOGB; o > 0; o >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], o);
-            const int r = b * BATCH + P;
-            if ((lane & ((32 >> LOGB) - 1)) == 0 && r < p.V)
-                p.partial[((int64_t)r * p.Ttot + p.t0 + t) * p.nsl + blockIdx.x * 4 + sp] = a[0] * kDotUnscale;
-        }
-    }
-}
-
-// =====================================================================================
-// K1 (single-trait fast path): table-lookup dot product.
-//
-// The shift+DFMA kernel above is bounded by instruction issue, not by the FP64 pipe: on sm_100a any
-// integer instruction issued between two DFMAs costs about as much as the DFMA itself
-// (tools/pipe_micro.cu: 48 DFMA/clk/SM alone, 30 with one shift each), so one trait cannot get past
-// ~30 genotypes/clk/SM that way.  Here a group of 4 consecutive individuals (one byte of the column)
-// is handled by ONE shared-memory lookup and ONE add:
-//     table[q][byte] = sum_k field_k(byte) * eps[4q + k]          256 doubles per byte position
-// The tile of a CTA (128*E4 bytes per column) is cut into chunks of <= 112 bytes; a pass builds the
-// tables of one chunk (224 KB of shared memory) and streams that chunk of all V columns through
-// them: lane l of a warp loads word l of the chunk (one coalesced <= 112-byte row per marker) and
-// looks its 4 bytes up; 8 markers are reduced across lanes by a transposed butterfly.  Chunk c of
-// pass p is tile (p*nsm + cta) / chunks_per_tile ..., i.e. in one pass the CTAs together read one
-// contiguous nsm*CB-byte run of every column.  Per-marker partials are accumulated across passes
-// in partial[r][t][cta] (each CTA owns its slot: plain read-modify-write).
-// =====================================================================================
-constexpr int kTabWarps = 16;
-constexpr int kTabThreads = kTabWarps * 32;
-constexpr int kTabMaxCW = 28;      // words per chunk: 28 * 4 bytes * 2 KB of table = 224 KB
-constexpr int kTabBatch = 16;      // markers per warp batch (loads in flight per warp, width of the butterfly)
-
-struct TabGeom { int cw, cwp, npass; };
-__host__ __device__ inline TabGeom tab_geom(int tile_bytes) {
-    TabGeom g;
-    const int words = tile_bytes / 4;
-    g.npass = (words + kTabMaxCW - 1) / kTabMaxCW;
-    g.cw = (words + g.npass - 1) / g.npass;          // words per chunk (last chunk may be shorter)
-    g.cwp = (g.cw + 3) & ~3;                         // padded so that the byte stride keeps lanes on distinct banks
-    return g;
-}
-
-template <int E4>
-__global__ void __launch_bounds__(kTabThreads, 1) dot_table_kernel(const DotParams p, Layout L) {
-    constexpr int E = 4 * E4;
-    constexpr int TILE = kLanesPerTile * E4;
-    extern __shared__ __align__(16) uint8_t tsmem[];
-    double* tab = reinterpret_cast<double*>(tsmem);          // [256][4][cwp]
-    const TabGeom G = tab_geom(TILE);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int RS = 4 * G.cwp;                                // doubles between consecutive byte values
-    constexpr int B = kTabBatch;
-    const int nbat = (p.V + B - 1) / B;
-    const double* eps = p.eps + (int64_t)p.t0 * p.npad;
-    const uint32_t tab_u32 = smem_u32(tab);
-    const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4, hi2 = lane & 2;
-    // marker of the batch whose total this lane holds after the butterfly
-    const int own = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-
-    for (int pass = 0; pass < G.npass; pass++) {
-        // unit u = (tile, chunk) handled by this CTA in this pass: neighbouring CTAs take neighbouring chunks
-        // of the same tile, so that in one pass the grid reads one contiguous run of every column
-        const int u = pass * gridDim.x + blockIdx.x;
-        const int tile = u / G.npass, chunk = u % G.npass;
-        const int w0 = chunk * G.cw;                         // first word of this chunk inside the tile
-        const int cw = min(G.cw, TILE / 4 - w0);             // words in this chunk
-        if (pass) __syncthreads();                           // everyone is done with the previous tables
-        // ---- build: 4 threads per (byte position) quad, 64 byte values each
-        for (int item = threadIdx.x; item < cw * 16; item += kTabThreads) {
-            const int quad = item % (cw * 4), sub = item / (cw * 4);
-            const int wl = quad >> 2, j = quad & 3;          // word (lane) and byte inside the word
-            int ls, bb;
-            tile_offset_to_slot_byte(E4, (w0 + wl) * 4 + j, ls, bb);
-            const double* e = eps + ((int64_t)tile * kLanesPerTile + ls) * E + 4 * bb;
-            const double e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
-            double p01[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) p01[i] = (double)(i & 3) * e0 + (double)(i >> 2) * e1;
-            double* dst = tab + j * G.cwp + wl;
-#pragma unroll
-            for (int hb = 0; hb < 4; hb++) {
-                const int h = sub * 4 + hb;                  // high nibble of the byte value
-                const double p23 = (double)(h & 3) * e2 + (double)(h >> 2) * e3;
-#pragma unroll
-                for (int i = 0; i < 16; i++) dst[(int64_t)(h * 16 + i) * RS] = p01[i] + p23;
-            }
-        }
-        __syncthreads();
-
-        // ---- stream the chunk of all V columns through the tables
-        const uint8_t* chunk0 = p.bed + (int64_t)tile * TILE + (int64_t)w0 * 4 + lane * 4;
-        const bool active = lane < cw;
-        // inactive lanes (word 0 -> table[0] == 0) are parked on columns whose banks the active lanes of their
-        // half-warp do not use
-        const int colw = active ? lane : (lane & 15) % (cw < 16 ? cw : 16);
-        uint32_t lb[4];                                      // shared-memory byte address of table[0][j][lane]
-#pragma unroll
-        for (int j = 0; j < 4; j++) lb[j] = tab_u32 + (uint32_t)((j * G.cwp + colw) * 8);
-        const uint32_t bstride = (uint32_t)(RS * 8);
-
-        uint32_t wn[B];
-        auto fetch = [&](int bi) {
-#pragma unroll
-            for (int jj = 0; jj < B; jj++) {
-                const int r = bi * B + jj;
-                const int col = r < p.V ? p.cols[r] : -1;
-                wn[jj] = (active && col >= 0) ? __ldg(reinterpret_cast<const uint32_t*>(chunk0 + (int64_t)col * p.col_stride)) : 0u;
-            }
-        };
-        if (warp < nbat) fetch(warp);
-        for (int bi = warp; bi < nbat; bi += kTabWarps) {
-            uint32_t w[B];
-#pragma unroll
-            for (int jj = 0; jj < B; jj++) w[jj] = wn[jj];
-            if (bi + kTabWarps < nbat) fetch(bi + kTabWarps);          // prefetch the next batch of this warp
-            double a[B];
-#pragma unroll
-            for (int jj = 0; jj < B; jj++) {
-                double v0, v1, v2, v3;
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v0) : "r"(lb[0] + (w[jj] & 0xffu) * bstride));
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v1) : "r"(lb[1] + ((w[jj] >> 8) & 0xffu) * bstride));
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v2) : "r"(lb[2] + ((w[jj] >> 16) & 0xffu) * bstride));
-                asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v3) : "r"(lb[3] + (w[jj] >> 24) * bstride));
-                a[jj] = (v0 + v1) + (v2 + v3);               // inactive lanes hold word 0: table[0] == 0
-            }
-            // transposed butterfly over the 16 markers of the batch (fixed order: reproducible)
-            double b8[8], b4[4], b2[2], b1;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const double send = hi16 ? a[i] : a[i + 8], keep = hi16 ? a[i + 8] : a[i];
-                b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const double send = hi8 ? b8[i] : b8[i + 4], keep = hi8 ? b8[i + 4] : b8[i];
-                b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-                const double send = hi4 ? b4[i] : b4[i + 2], keep = hi4 ? b4[i + 2] : b4[i];
-                b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            for (int j = 0; j < 2; j++) {
+                const double keep = hi4 ? b4[2 + j] : b4[j], send = hi4 ? b4[j] : b4[2 + j];
+                b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
             }
             {
-                const double send = hi2 ? b2[0] : b2[1], keep = hi2 ? b2[1] : b2[0];
+                const double keep = hi2 ? b2[1] : b2[0], send = hi2 ? b2[0] : b2[1];
                 b1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-            const int r = bi * B + own;
-            if ((lane & 1) == 0 && r < p.V)                  // one slot per unit: plain stores, no read-modify-write
-                p.partial[((int64_t)r * p.Ttot + p.t0) * p.nsl + u] = b1;
+            const int v = b * kBatch + 2 * own + h;
+            if ((l16 & 1) == 0 && v < p.V) part[v * T + t] += b1;
         }
+    }
+}
+
+// NW consumer warps: 16 (96 registers per thread) or 23 (80 registers; only for T <= 2, whose accumulators fit)
+template <int T, int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, 1) step_kernel(const StepParams p) {
+    constexpr int NT = (NW + 1) * 32, NC = NW * 32;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint32_t b0 = smem_u32(smem_raw);
+    if (b0 > kTabBase) {                                  // the LDS immediates assume tables at absolute address kTabBase
+        if (threadIdx.x == 0) atomicExch(p.err, 10);
+        return;
+    }
+    const int nsm = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rb = (int)((int64_t)cta * p.nrows / nsm), re = (int)((int64_t)(cta + 1) * p.nrows / nsm), nr = re - rb;
+    const int nrmax = (p.nrows + nsm - 1) / nsm;
+    const int slots = p.V > 0 ? p.rows_per_pass * T : 0;
+    // shared memory carve-up (absolute addresses: kTabBase is 1024, every block below stays 256-aligned until `part`)
+    uint8_t* tabs = smem_raw + (kTabBase - b0);
+    PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)slots * kSlotBytes);        // 256-aligned (kSlotBytes = 162 * 256)
+    uint8_t* ring = reinterpret_cast<uint8_t*>(stage + kPubCap);
+    double* part = reinterpret_cast<double*>(ring + (p.V > 0 ? kRingStages * kRingStageBytes : 0));
+    PubInfo* info = reinterpret_cast<PubInfo*>(part + (size_t)p.V * T);
+    uint32_t* lut = reinterpret_cast<uint32_t*>(info + kPubCap);
+    uint32_t* bitmap = lut + 82;
+    double* red = reinterpret_cast<double*>(bitmap + ((nrmax * 8 + 1) & ~1));
+    int* wcnt = reinterpret_cast<int*>(red + 32);
+    uint64_t* full = reinterpret_cast<uint64_t*>(wcnt + 32);
+    uint64_t* empty = full + kRingStages;
+    volatile int* issued = reinterpret_cast<volatile int*>(empty + kRingStages);   // batches the producer has issued so far
+
+    if (tid == 0 && p.V > 0) {
+        *issued = 0;
+        for (int s = 0; s < kRingStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
+    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, rb, nr, stage, info, lut, bitmap, wcnt);
+    __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
+    if (p.V == 0) return;
+
+    const int rpp = p.rows_per_pass;
+    const int npass = (nr + rpp - 1) / rpp;
+    const int nb = (p.V + kBatch - 1) / kBatch;
+    double es[T];
+#pragma unroll
+    for (int t = 0; t < T; t++) es[t] = 0.0;
+
+    if (warp == NW) {
+        // ---------------- producer: lane j < 16 issues the copy of marker j of every batch, pass after pass ----------------
+        const uint32_t ring_u32 = smem_u32(ring);
+        for (int pass = 0; pass < npass; pass++) {
+            const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
+            const int nrp = r_hi - r_lo;
+            const uint32_t bytes = (uint32_t)nrp * kRowBytes, stride = (uint32_t)ring_marker_stride(nrp);
+            const uint8_t* src0 = p.bed + (int64_t)r_lo * kRowBytes;
+            for (int b = 0; b < nb; b++) {
+                const int gb = pass * nb + b, s = gb % kRingStages;
+                if (gb >= kRingStages) mbar_wait(&empty[s], (uint32_t)((gb / kRingStages) - 1) & 1u);
+                const int v = b * kBatch + lane;
+                int col = 0;
+                if (lane < kBatch && v < p.V) col = max(p.cols[v], 0);
+                if (lane == 0) mbar_expect_tx(&full[s], bytes * kBatch);
+                __syncwarp();
+                if (lane < kBatch)
+                    bulk_g2s(ring_u32 + (uint32_t)(s * kRingStageBytes) + (uint32_t)lane * stride, src0 + (int64_t)col * p.col_stride, bytes, &full[s]);
+                if (lane == 0) {
+                    __threadfence_block();
+                    *issued = gb + 1;
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers ----------------
+        const uint32_t ring_u32 = smem_u32(ring);
+        for (int pass = 0; pass < npass; pass++) {
+            const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
+            const int nrp = r_hi - r_lo;
+            if (pass) consumer_sync(NC);                  // everyone is done with the previous tables
+            build_tables<T, NC>(p, r_lo, nrp, es);
+            consumer_sync(NC);
+            const int gb0 = pass * nb;
+            switch (nrp) {
+            case 1: stream_rows<1, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
+            default: break;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < p.V * T; i += NT) {
+        const int v = i / T, t = i - v * T;
+        p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+        const double tot = block_sum_fixed(es[t], red);
+        if (tid == 0) p.spart[(int64_t)(p.t0 + t) * nsm + cta] = tot;
     }
 }
 
@@ -651,16 +690,16 @@ struct DotPieces { double dpa, dpb; };
 
 // sum a*eps and sum b*eps of trait t for the marker of virtual rank r (all lanes get the result)
 __device__ __forceinline__ DotPieces finish_dot(const SampleParams& p, int r, int col, int t, int lane) {
-    const double* part = p.partial + ((int64_t)r * p.T + t) * p.nsl;
+    const double* part = p.partial + ((int64_t)r * p.T + t) * p.nsm;
     double s = 0.0;
-    for (int i0 = lane; i0 < p.nsl; i0 += 32 * 8) {          // 8 independent loads per round, fixed summation order
+    for (int i0 = lane; i0 < p.nsm; i0 += 32 * 8) {          // 8 independent loads per round, fixed summation order
         double x[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) x[j] = i0 + 32 * j < p.nsl ? part[i0 + 32 * j] : 0.0;
+        for (int j = 0; j < 8; j++) x[j] = i0 + 32 * j < p.nsm ? part[i0 + 32 * j] : 0.0;
 #pragma unroll
         for (int j = 0; j < 8; j++) s += x[j];
     }
-    const double coded = warp_sum_fixed(s);                 // sum d*eps with missing coded 3
+    const double coded = warp_sum_fixed(s);                 // sum a*eps (missing genotypes are stored as dosage 0)
     double sa = 0.0;
     for (int i0 = lane; i0 < p.nsm; i0 += 32 * 8) {
         double x[8];
@@ -675,11 +714,10 @@ __device__ __forceinline__ DotPieces finish_dot(const SampleParams& p, int r, in
     for (uint32_t i = m0 + lane; i < m1; i += 32) sm += p.eps[(int64_t)t * p.npad + p.miss_idx[i]];
     const double smiss = m1 > m0 ? warp_sum_fixed(sm) : 0.0;
     DotPieces d;
-    d.dpa = coded - 3.0 * smiss;     // a = 0 at missing (lut_a)
+    d.dpa = coded;                   // a = 0 at missing (lut_a)
     d.dpb = sall - smiss;            // b = 0 at missing (lut_b)
     return d;
 }
-
 // Per-(trait, group) pieces of the sampler that do not depend on the marker (bayes.cpp:403-405,413-416,
 // 429-431), evaluated once per iteration instead of once per marker:
 //   gc[0..K)   denom[k-1] = (N-1) + sige_g * cvai[k]            (k >= 1; slot 0 holds inv2sige)
@@ -772,138 +810,6 @@ __global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, 
         if (lane == 0) out[(int64_t)v * p.T + t] = p.msig[mi] * (d.dpa - p.mave[mi] * d.dpb);
     }
 }
-
-// =====================================================================================
-// K3: apply the step's published updates to the residuals.
-// Phenotype::update_epsilon, phenotype.cpp:326-329,375-390:  eps += (a - mave*b) * (dbeta*msig) * na
-//
-// One CTA per (tile, trait), 4 x kUpdSplit warps.  Warp w serves the lane-slots of sub-partition
-// w & 3 (same mapping as K1) and takes every kUpdSplit-th published marker, in rank order, prefetching
-// kUpdPF columns ahead; its increments stay in registers.  The splits are then combined through shared
-// memory in a fixed order (reproducible), masked by the NA mask and added to eps; the per-tile sum of
-// eps that K2 needs is refreshed on the way.
-// =====================================================================================
-struct UpdEntry {           // one published marker, staged in shared memory
-    double v[4];            // increment by genotype code: (a - mave*b) * dbeta*msig for dosage 0,1,2; 0 where missing
-};
-
-template <int E4>
-__global__ void __launch_bounds__(kUpdThreads, 1) update_kernel(const UpdateParams p, Layout L) {
-    constexpr int E = 4 * E4;
-    extern __shared__ __align__(16) uint8_t usmem[];
-    double* dlt = reinterpret_cast<double*>(usmem);                                  // [kUpdSplit][128][E + 1]
-    UpdEntry* ent = reinterpret_cast<UpdEntry*>(usmem + sizeof(double) * kUpdSplit * (E + 1) * kLanesPerTile);
-    int32_t* ecol = reinterpret_cast<int32_t*>(ent + kUpdCap);                        // column of each staged entry
-    __shared__ int npub;
-    __shared__ int wcnt[kUpdCap / 32];
-    __shared__ double red[kUpdThreads / 32];
-    const int t = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sp = warp & 3, u = warp >> 2, ls = sp * 32 + lane;
-    const uint8_t* tile0 = p.bed + (int64_t)blockIdx.x * L.tile_bytes;
-    const uint32_t ent_u32 = smem_u32(ent);
-
-    double d[E];
-#pragma unroll
-    for (int k = 0; k < E; k++) d[k] = 0.0;
-    bool any = false;
-
-    // rounds of kUpdCap virtual ranks: their published entries (rank order) fit the staging area
-    for (int v_lo = 0; v_lo < p.V; v_lo += kUpdCap) {
-        const int v_hi = min(p.V, v_lo + kUpdCap);
-        __syncthreads();
-        // ordered compaction of the round's published entries by the whole CTA: thread tid looks at virtual
-        // ranks v_lo + tid + i*kUpdThreads (all loads in flight at once), warp counts are scanned through
-        // shared memory, rank order is preserved
-        constexpr int NI = kUpdCap / kUpdThreads;
-        PubEntry pe[NI];
-        uint32_t bal[NI];
-#pragma unroll
-        for (int i = 0; i < NI; i++) {
-            const int v = v_lo + i * kUpdThreads + threadIdx.x;
-            pe[i] = v < v_hi ? p.pub[(int64_t)v * p.T + t] : PubEntry{0.0, 0.0};
-        }
-#pragma unroll
-        for (int i = 0; i < NI; i++) {
-            bal[i] = __ballot_sync(0xffffffffu, pe[i].lam != 0.0);
-            if (lane == 0) wcnt[i * (kUpdThreads / 32) + warp] = __popc(bal[i]);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int i = 0; i < NI * (kUpdThreads / 32); i++) { const int c = wcnt[i]; wcnt[i] = acc; acc += c; }
-            npub = acc;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < NI; i++) {
-            if (pe[i].lam != 0.0) {
-                const int idx = wcnt[i * (kUpdThreads / 32) + warp] + __popc(bal[i] & ((1u << lane) - 1u));
-                // reference arithmetic: (mdb*b + a) * bs_  with mdb = -mave, bs_ = dbeta*msig (phenotype.cpp:328-329,388)
-                const double mdb = -pe[i].mave;
-                ent[idx].v[0] = (mdb * 1.0 + 0.0) * pe[i].lam;
-                ent[idx].v[1] = (mdb * 1.0 + 1.0) * pe[i].lam;
-                ent[idx].v[2] = (mdb * 1.0 + 2.0) * pe[i].lam;
-                ent[idx].v[3] = 0.0;                 // missing: a = b = 0
-                ecol[idx] = p.cols[v_lo + i * kUpdThreads + threadIdx.x];
-            }
-        }
-        __syncthreads();
-        const int n = npub;
-        if (n == 0) continue;
-        any = true;
-
-        SlotRegs<E4> g[kUpdPF], gn[kUpdPF];
-        const int mine = (n - u + kUpdSplit - 1) / kUpdSplit;      // entries i = u, u + S, u + 2S, ...
-        auto fetch = [&](SlotRegs<E4>* dst, int c0) {
-#pragma unroll
-            for (int j = 0; j < kUpdPF; j++)
-                if (c0 + j < mine) dst[j].load(tile0 + (int64_t)ecol[u + (c0 + j) * kUpdSplit] * p.col_stride, ls);
-        };
-        fetch(gn, 0);
-        for (int c0 = 0; c0 < mine; c0 += kUpdPF) {
-#pragma unroll
-            for (int j = 0; j < kUpdPF; j++) g[j] = gn[j];
-            fetch(gn, c0 + kUpdPF);                                  // prefetch the next chunk
-#pragma unroll
-            for (int j = 0; j < kUpdPF; j++) {
-                if (c0 + j >= mine) break;
-                const uint32_t eb = ent_u32 + (uint32_t)((u + (c0 + j) * kUpdSplit) * sizeof(UpdEntry));
-#pragma unroll
-                for (int k = 0; k < E; k++) {
-                    double val;                      // v[code]: one shared-memory read (4 addresses: broadcast, no conflict)
-                    asm("ld.shared.f64 %0, [%1];" : "=d"(val) : "r"(eb + g[j].field(k) * 8u));
-                    d[k] += val;
-                }
-            }
-        }
-    }
-    if (!__syncthreads_or(any)) return;              // nothing published for this trait: eps and its sums stand
-    // increments of split u for slot ls, padded rows (E+1) keep both the writes and the reads below conflict-free
-#pragma unroll
-    for (int k = 0; k < E; k++) dlt[((int64_t)u * kLanesPerTile + ls) * (E + 1) + k] = d[k];
-    __syncthreads();
-
-    // combine the splits in fixed order and apply: the tile is a contiguous range of individuals -> coalesced
-    constexpr int PER = kLanesPerTile * E;
-    const int64_t base = (int64_t)t * p.npad + (int64_t)blockIdx.x * PER;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < PER; i += kUpdThreads) {
-        const int sl = i / E, k = i - sl * E;
-        double inc = 0.0;
-#pragma unroll
-        for (int uu = 0; uu < kUpdSplit; uu++) inc += dlt[((int64_t)uu * kLanesPerTile + sl) * (E + 1) + k];
-        double e = p.eps[base + i];
-        if (p.na01[base + i]) {                      // * na  (phenotype.cpp:388)
-            e += inc;
-            if (p.delta) p.delta[base + i] += inc;   // multi-GPU: what this shard changed since the last exchange
-        }
-        p.eps[base + i] = e;
-        s += e;
-    }
-    const double tot = block_sum_fixed(s, red);
-    if (threadIdx.x == 0) p.spart[(int64_t)t * L.nsm + blockIdx.x] = tot;
-}
-
 // =====================================================================================
 // per-iteration prologue / epilogue
 // =====================================================================================
@@ -1005,18 +911,28 @@ __global__ void global_draw_kernel(const GlobalDrawParams p) {
 // =====================================================================================
 // launchers
 // =====================================================================================
-void launch_transcode(const uint8_t* src, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s) {
+void launch_transcode(const uint8_t* plink, int nmark, const Layout& L, uint8_t* dst, uint32_t* miss_counts, cudaStream_t s) {
     if (nmark <= 0) return;
     dim3 grid((unsigned)((L.col_stride + 255) / 256), (unsigned)nmark);
-    transcode_kernel<<<grid, 256, 0, s>>>(src, nmark, L, dst);
+    transcode_kernel<<<grid, 256, 0, s>>>(plink, nmark, L, dst, miss_counts);
 }
-void launch_decode_column(const uint8_t* col, const Layout& L, double* a, double* b, cudaStream_t s) {
-    decode_column_kernel<<<(unsigned)((L.N + 255) / 256), 256, 0, s>>>(col, L, a, b);
+void launch_fill_missing(const uint8_t* plink, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s) {
+    if (nmark <= 0) return;
+    fill_missing_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(plink, nmark, L, off, idx);
 }
-void launch_untranscode(const uint8_t* tiles, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s) {
+void launch_untranscode(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* miss_off, const uint32_t* miss_idx,
+                        uint8_t* plink_out, cudaStream_t s) {
     if (nmark <= 0) return;
     dim3 grid((unsigned)((L.mbytes + 255) / 256), (unsigned)nmark);
-    untranscode_kernel<<<grid, 256, 0, s>>>(tiles, nmark, L, dst);
+    untranscode_kernel<<<grid, 256, 0, s>>>(bed, nmark, L, plink_out);
+    unmiss_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(nmark, L, miss_off, miss_idx, plink_out);
+}
+void launch_decode_column(const uint8_t* col, const Layout& L, const uint32_t* miss_idx, uint32_t nmiss, double* a, double* b, cudaStream_t s) {
+    decode_column_kernel<<<(unsigned)((L.N + 255) / 256), 256, 0, s>>>(col, L, a, b);
+    if (nmiss) decode_missing_kernel<<<(nmiss + 255) / 256, 256, 0, s>>>(miss_idx, nmiss, L.N, a, b);
+}
+void launch_decode_namask(const uint8_t* mask4, const Layout& L, double* na, cudaStream_t s) {
+    decode_namask_kernel<<<(unsigned)((L.N + 255) / 256), 256, 0, s>>>(mask4, L, na);
 }
 void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, const Layout& L, uint32_t seed, double maf_lo,
                            double maf_hi, double missing_rate, cudaStream_t s) {
@@ -1024,105 +940,81 @@ void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, con
     dim3 grid((unsigned)((L.mbytes + 255) / 256), (unsigned)nmark);
     generate_plink_kernel<<<grid, 256, 0, s>>>(dst, nmark, first_global_marker, L, seed, maf_lo, maf_hi, missing_rate);
 }
-void launch_count_missing(const uint8_t* bed, int nmark, const Layout& L, uint32_t* counts, cudaStream_t s) {
+void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
+                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s) {
     if (nmark <= 0) return;
-    count_missing_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(bed, nmark, L, counts);
+    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, mask4, miss_off, miss_idx, nonas, T, mave, msig);
 }
-void launch_fill_missing(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s) {
-    if (nmark <= 0) return;
-    fill_missing_kernel<<<(nmark + 3) / 4, 128, 0, s>>>(bed, nmark, L, off, idx);
+void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s) {
+    dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)T);
+    eps_offset_kernel<<<grid, 256, 0, s>>>(eps, mask4, L, mu_old, mu_new);
 }
-void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* namask2, const int32_t* nonas, int T,
-                  double* mave, double* msig, cudaStream_t s) {
-    if (nmark <= 0) return;
-    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, namask2, nonas, T, mave, msig);
-}
-
-#define GMRM_DISPATCH_E4(E4v, CALL)                 \
-    switch (E4v) {                                  \
-    case 1: { constexpr int E4 = 1; CALL; } break;  \
-    case 2: { constexpr int E4 = 2; CALL; } break;  \
-    case 3: { constexpr int E4 = 3; CALL; } break;  \
-    case 4: { constexpr int E4 = 4; CALL; } break;  \
-    case 5: { constexpr int E4 = 5; CALL; } break;  \
-    case 6: { constexpr int E4 = 6; CALL; } break;  \
-    case 7: { constexpr int E4 = 7; CALL; } break;  \
-    case 8: { constexpr int E4 = 8; CALL; } break;  \
-    default: break;                                 \
-    }
-
-void launch_eps_offset(double* eps, const uint8_t* na01, const Layout& L, int T, const double* mu_old,
-                       const double* mu_new, double* spart, cudaStream_t s) {
-    dim3 grid((unsigned)L.nsm, (unsigned)T);
-    eps_offset_kernel<<<grid, 256, 0, s>>>(eps, na01, L, mu_old, mu_new, spart);
-}
-void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s) {
-    dim3 grid((unsigned)L.nsm, (unsigned)T);
-    eps_merge_kernel<<<grid, 256, 0, s>>>(eps, loc, tot, L, spart);
+void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s) {
+    const int64_t n = (int64_t)T * L.npad;
+    eps_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(eps, loc, tot, n);
 }
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);
 }
 
-template <int E4, int T, int WPS, int BATCH>
-static int dot_launch_v(const DotParams& p, int nsm, cudaStream_t s) {
-    const int nbpad = (p.V + BATCH - 1) / BATCH * BATCH;
-    const int smem = dot_ring_tiles(WPS) * kLanesPerTile * E4 + 2 * (dot_ring_tiles(WPS) / BATCH) * (int)sizeof(uint64_t) + nbpad * (int)sizeof(int32_t);
-    static int attr = 0;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(dot_kernel<E4, T, WPS, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        attr = smem;
-    }
-    dot_kernel<E4, T, WPS, BATCH><<<nsm, (4 * WPS + 1) * 32, smem, s>>>(p);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
-}
-// variants (consumer warps per sub-partition, markers per batch): 0 = (2,8) default, 1 = (4,4), 2 = (2,4), 3 = (3,4).
-// All are instantiated for single-trait runs (the headline path); multi-trait launches use the default.
-template <int E4, int T>
-static int dot_launch_t(const DotParams& p, int nsm, cudaStream_t s) {
-    if (T == 1) {
-        if (p.variant == 1) return dot_launch_v<E4, 1, 4, 4>(p, nsm, s);
-        if (p.variant == 2) return dot_launch_v<E4, 1, 2, 4>(p, nsm, s);
-        if (p.variant == 3) return dot_launch_v<E4, 1, 3, 4>(p, nsm, s);
-        return dot_launch_v<E4, 1, 2, 8>(p, nsm, s);
-    }
-    return dot_launch_v<E4, T, 2, 4>(p, nsm, s);     // multi-trait: widest register budget (168 / thread)
-}
-template <int E4>
-static int dot_launch_e(int T, const DotParams& p, int nsm, cudaStream_t s) {
-    switch (T) {
-    case 1: return dot_launch_t<E4, 1>(p, nsm, s);
-    case 2: return dot_launch_t<E4, 2>(p, nsm, s);
-    case 3: return dot_launch_t<E4, 3>(p, nsm, s);
-    case 4: return dot_launch_t<E4, 4>(p, nsm, s);
-    }
-    return -1;
-}
-// T in 1..4 per launch (the engine chunks more traits)
-int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s) {
-    int rc = -1;
-    GMRM_DISPATCH_E4(L.E4, (rc = dot_launch_e<E4>(T, p, L.nsm, s)));
-    return rc;
+constexpr int kMaxDynSmem = 232448;   // 227 KB: the most one CTA can opt into on sm_100
+
+int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
+    const int nrmax = L.max_rows_per_cta();
+    const int64_t bytes = (int64_t)kTabBase + (int64_t)(V > 0 ? rows_per_pass * T : 0) * kSlotBytes + (int64_t)kPubCap * 32 +
+                          (V > 0 ? (int64_t)kRingStages * kRingStageBytes : 0) + (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 +
+                          (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4 + 2 * kRingStages * 8 + 16;
+    return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 
-template <int E4>
-static int dot_table_launch_t(const DotParams& p, const Layout& L, cudaStream_t s) {
-    const TabGeom G = tab_geom(L.tile_bytes);
-    const int smem = 256 * 4 * G.cwp * (int)sizeof(double);
-    static int attr = 0;
-    if (smem > attr) {
-        if (cudaFuncSetAttribute(dot_table_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        attr = smem;
+void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass) {
+    *traits_per_launch = 0; *rows_per_pass = 0;
+    for (int tc = Ttot < kMaxSlots ? Ttot : kMaxSlots; tc >= 1; tc--) {
+        int rpp = kMaxSlots / tc;
+        while (rpp >= 1 && step_smem_bytes(L, V, tc, rpp) < 0) rpp--;
+        if (rpp < 1) continue;
+        const int nchunks = (Ttot + tc - 1) / tc;
+        const int bal = (Ttot + nchunks - 1) / nchunks;        // balanced chunks: 6 traits -> 3 + 3, not 5 + 1
+        int rb = kMaxSlots / bal;
+        while (rb >= 1 && step_smem_bytes(L, V, bal, rb) < 0) rb--;
+        if (rb < 1) { *traits_per_launch = tc; *rows_per_pass = rpp; }
+        else { *traits_per_launch = bal; *rows_per_pass = rb; }
+        const int nrmax = L.max_rows_per_cta();
+        if (*rows_per_pass > nrmax && nrmax >= 1) *rows_per_pass = nrmax;
+        return;
     }
-    dot_table_kernel<E4><<<L.nsm, kTabThreads, smem, s>>>(p, L);
+}
+
+template <int T>
+static int step_launch_t(const Layout& L, const StepParams& p, cudaStream_t s) {
+    const int smem = step_smem_bytes(L, p.V, T, p.rows_per_pass);
+    if (smem < 0) return -3;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(step_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
+        if constexpr (T <= 2)
+            if (cudaFuncSetAttribute(step_kernel<T, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
+        attr = true;
+    }
+    if constexpr (T <= 2) {
+        if (p.nwarps == 23) {
+            step_kernel<T, 23><<<L.nsm, 24 * 32, smem, s>>>(p);
+            return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+        }
+    }
+    step_kernel<T, 16><<<L.nsm, 17 * 32, smem, s>>>(p);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
-// one trait (p.t0) per launch; partial[r][t][unit] with p.nsl == nsm * passes
-int dot_table_passes(const Layout& L) { return tab_geom(L.tile_bytes).npass; }
-int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s) {
-    int rc = -1;
-    GMRM_DISPATCH_E4(L.E4, (rc = dot_table_launch_t<E4>(p, L, s)));
-    return rc;
+// T = traits of this launch (1..4); p.rows_per_pass * T <= kMaxSlots
+int launch_step(const Layout& L, int T, const StepParams& p, cudaStream_t s) {
+    if (p.V > 0 && (p.rows_per_pass < 1 || p.rows_per_pass * T > kMaxSlots)) return -4;
+    switch (T) {
+    case 1: return step_launch_t<1>(L, p, s);
+    case 2: return step_launch_t<2>(L, p, s);
+    case 3: return step_launch_t<3>(L, p, s);
+    case 4: return step_launch_t<4>(L, p, s);
+    }
+    return -5;
 }
 
 void launch_sample(const SampleParams& p, cudaStream_t s) {
@@ -1132,24 +1024,6 @@ void launch_sample(const SampleParams& p, cudaStream_t s) {
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
     if (p.V <= 0) return;
     finish_dots_kernel<<<(p.V + 3) / 4, 128, 0, s>>>(p, out);
-}
-
-template <int E4>
-static int update_launch_t(const UpdateParams& p, const Layout& L, cudaStream_t s) {
-    const int smem = (int)sizeof(double) * kUpdSplit * (4 * E4 + 1) * kLanesPerTile + kUpdCap * (int)(sizeof(UpdEntry) + sizeof(int32_t));
-    static int attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        if (cudaFuncSetAttribute(update_kernel<E4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
-        attr = smem;
-    }
-    dim3 grid((unsigned)L.nsm, (unsigned)p.T);
-    update_kernel<E4><<<grid, kUpdThreads, smem, s>>>(p, L);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
-}
-int launch_update(const Layout& L, const UpdateParams& p, cudaStream_t s) {
-    int rc = -1;
-    GMRM_DISPATCH_E4(L.E4, (rc = update_launch_t<E4>(p, L, s)));
-    return rc;
 }
 
 void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin, int shuffle, uint32_t seed,

@@ -1,5 +1,5 @@
-// sm_100a kernels of the Gibbs marker loop.  See layout.h for the HBM layout and the decode
-// algebra, DESIGN.md for the roofline of each kernel.
+// sm_100a kernels of the Gibbs marker loop.  See layout.h for the HBM layout and the table geometry,
+// DESIGN.md for the roofline of each kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -10,40 +10,42 @@
 
 namespace gmrm {
 
-// ------------------------------------------------------------------------------------------
-// dot kernel geometry
-// shared-memory ring of the dot kernel: 64 tiles (<= 64 KB; 48 when 3 consumer warps share a sub-partition so
-// that a stage always serves the same warp), cut into stages of BATCH markers
-__host__ __device__ constexpr int dot_ring_tiles(int wps) { return wps == 3 ? 48 : 64; }
-constexpr int kDotMaxThreads = 17 * 32; // 4 consumer warps per sub-partition + 1 producer warp, the widest variant
-constexpr int kDotMaxBatch = 8;
-constexpr int kUpdSplit = 4;                              // warps per sub-partition in the update kernel
-constexpr int kUpdCap = 2048;                             // virtual ranks staged per round of the update kernel
-constexpr int kUpdPF = 4;                                 // columns each update warp prefetches ahead
-constexpr int kUpdThreads = kLanesPerTile * kUpdSplit;
+constexpr int kBatch = 16;             // markers per warp batch (8 pairs: one marker per half-warp)
+constexpr int kPubCap = 128;           // published updates staged per round of the update phase
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
     double lam;     // dbeta * msig   (0 == nothing to apply)
     double mave;
 };
 
-struct DotParams {
+// One marker-step on one GPU: (a) apply the updates published by the previous step to this CTA's rows of
+// the residuals, (b) build the look-up tables of those rows, (c) stream the step's V columns through them.
+struct StepParams {
     const uint8_t* bed;
     int64_t col_stride;
+    int32_t nrows;
     const int32_t* cols;     // [V] shard-local column of each virtual rank this step, -1 = none
-    int32_t V;
-    const double* eps;       // [T][npad]
+    int32_t V;               // 0: update only
+    double* eps;             // [Ttot][npad]
     int64_t npad;
-    double* partial;         // [V][Ttot][nsl]
-    int32_t nsl;             // nsm * 4
     int32_t Ttot, t0;        // this launch handles traits t0 .. t0+T-1 of Ttot
-    const double* zeros;     // >= kDotMaxThreads * kDotMaxBatch zeros (opaque to ptxas, see set_lo)
-    int32_t debug;           // 0 normal; 1 feed only (no arithmetic); 2 compute only (no TMA, no barriers) -- profiling aids
-    int32_t variant;         // (consumer warps / sub-partition, markers / batch): 0 = (2,8), 1 = (4,4), 2 = (2,4), 3 = (3,4)
+    int32_t rows_per_pass;   // table slots / T
+    double* partial;         // [V][Ttot][nsm]   per-CTA partial sums of sum a*eps
+    double* spart;           // [Ttot][nsm]      per-CTA sums of eps
+    // pending updates (previous step), applied in virtual-rank order
+    const int32_t* pcols;    // [pV]
+    int32_t pV;
+    const PubEntry* pub;     // [pV][Ttot]
+    const uint8_t* mask4;    // [Ttot][col_stride] NA nibble of every quad (bit k: individual 4q+k observed)
+    const uint32_t* miss_off;
+    const uint32_t* miss_idx;
+    double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
+    int32_t* err;
+    int32_t nwarps;          // consumer warps of the step kernel: 16 or 23
 };
 
 struct SampleParams {
-    int32_t V, T, G, K, N, nsl, nsm;
+    int32_t V, T, G, K, N, nsm;
     int32_t it;
     uint32_t seed;
     int32_t r0;              // global index of this shard's first virtual rank
@@ -52,8 +54,8 @@ struct SampleParams {
     int32_t marker_begin;    // global index of the shard's first marker
     int32_t Mloc;
     const int32_t* cols;     // [V]
-    const double* partial;   // [V][T][nsl]
-    const double* spart;     // [T][nsm]  per-tile sum of eps
+    const double* partial;   // [V][T][nsm]
+    const double* spart;     // [T][nsm]
     const uint32_t* miss_off;// [Mloc+1]
     const uint32_t* miss_idx;
     const double* eps;
@@ -63,11 +65,7 @@ struct SampleParams {
     double* betas;           // [T][Mloc]
     int32_t* comp;
     const int32_t* group;    // [Mloc] group of each shard-local marker
-    const double* cva;       // [G*K]
-    const double* cvai;
     const double* sigmag;    // [T][G]
-    const double* sigmae;    // [T]
-    const double* pi;        // [T][G*K]
     const double* gc;        // [T][G][4K] per-iteration sampler constants (group_consts_kernel)
     const int32_t* nonas;    // [T]
     int32_t* cass;           // [T][G*K]
@@ -78,41 +76,26 @@ struct SampleParams {
     int64_t* npublished;
 };
 
-struct UpdateParams {
-    const uint8_t* bed;
-    int64_t col_stride;
-    const int32_t* cols;     // [V]
-    int32_t V, T;
-    const PubEntry* pub;     // [V][T]
-    const uint32_t* miss_off;// to pick the exact path for markers with missing genotypes
-    const uint8_t* namask2;  // [T][col_stride] tile layout, field 01 = observed
-    const uint8_t* na01;     // [T][npad] 1 = observed, per individual
-    double* eps;             // [T][npad]
-    int64_t npad;
-    double* spart;           // [T][nsm]
-    double* delta;           // [T][npad] or nullptr: accumulates the applied increments (multi-GPU exchange)
-    int32_t exact;           // 1: always use the reference-order arithmetic
-};
-
 // launchers (kernels.cu)
-void launch_transcode(const uint8_t* src, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s);
-void launch_decode_column(const uint8_t* col, const Layout& L, double* a, double* b, cudaStream_t s);
-void launch_untranscode(const uint8_t* tiles, int nmark, const Layout& L, uint8_t* dst, cudaStream_t s);
+void launch_transcode(const uint8_t* plink, int nmark, const Layout& L, uint8_t* dst, uint32_t* miss_counts, cudaStream_t s);
+void launch_fill_missing(const uint8_t* plink, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s);
+void launch_untranscode(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* miss_off, const uint32_t* miss_idx,
+                        uint8_t* plink_out, cudaStream_t s);
+void launch_decode_column(const uint8_t* col, const Layout& L, const uint32_t* miss_idx, uint32_t nmiss, double* a, double* b, cudaStream_t s);
+void launch_decode_namask(const uint8_t* mask4, const Layout& L, double* na, cudaStream_t s);
 void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, const Layout& L, uint32_t seed,
                            double maf_lo, double maf_hi, double missing_rate, cudaStream_t s);
-void launch_count_missing(const uint8_t* bed, int nmark, const Layout& L, uint32_t* counts, cudaStream_t s);
-void launch_fill_missing(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s);
-void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* namask2, const int32_t* nonas, int T,
-                  double* mave, double* msig, cudaStream_t s);
-void launch_eps_offset(double* eps, const uint8_t* na01, const Layout& L, int T, const double* mu_old,
-                       const double* mu_new, double* spart, cudaStream_t s);
-void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, double* spart, cudaStream_t s);
+void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
+                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s);
+void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s);
+void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
-int launch_dot(const Layout& L, int T, const DotParams& p, cudaStream_t s);
-int launch_dot_table(const Layout& L, const DotParams& p, cudaStream_t s);
-int dot_table_passes(const Layout& L);
+// dynamic shared memory the step kernel needs, or -1 if (V, T, rows_per_pass, rows per CTA) do not fit
+int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass);
+// traits per launch and rows per pass for a step of V markers (0 rows = does not fit)
+void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass);
+int launch_step(const Layout& L, int T, const StepParams& p, cudaStream_t s);
 void launch_sample(const SampleParams& p, cudaStream_t s);
-int launch_update(const Layout& L, const UpdateParams& p, cudaStream_t s);
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s);
 void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin, int shuffle,
                     uint32_t seed, int it, const int32_t* rep_perm, cudaStream_t s);

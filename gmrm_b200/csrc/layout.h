@@ -1,27 +1,32 @@
-// HBM layout of the genotype matrix ("tile-planar 2-bit dosage") and the decode algebra the
-// kernels use.  Host + device.
+// HBM layout of the genotype matrix ("base-3 quads") and the geometry of the table-lookup dot
+// product.  Host + device.
 //
 // Reference layout (Bayes::load_genotype, src/bayes.cpp:867-900): marker-major, ceil(N/4) bytes
-// per marker, individual 4i+k in bits 2k..2k+1 of byte i, PLINK codes 00 = dosage 2, 01 = missing,
+// per marker, individual 4q+k in bits 2k..2k+1 of byte q, PLINK codes 00 = dosage 2, 01 = missing,
 // 10 = dosage 1, 11 = dosage 0 (decode tables src/lut/mk_lut.cpp:25-32).
 //
-// Device layout.  The individuals are cut into `nsm` tiles (one per SM / CTA); a tile has 128
-// lane-slots (4 SM sub-partitions x 32 lanes); a lane-slot owns E = 4*E4 CONSECUTIVE individuals
-//     individual i  ->  slot s = i / E,  position k = i % E
-// i.e. E4 consecutive bytes of the PLINK column.  A column is stored tile after tile
-// (column stride = nsm * 128 * E4 bytes); inside a tile the E4 bytes of a slot are split into
-// register-sized GROUPS -- E4/4 32-bit words, then a 16-bit half if E4 & 2, then a byte if E4 & 1 --
-// and stored plane by plane (all 128 slots' word 0, then word 1, ..., then the halves, then the
-// bytes), so that a warp's load of one group is one contiguous, conflict-free 128/64/32-byte run
-// and one tile is one contiguous cp.async.bulk of 128*E4 bytes.
+// Device layout.  Same byte order as the .bed column (byte q <-> individuals 4q..4q+3, a "quad"),
+// but the byte holds the quad's dosages in base 3:
+//     e = d0 + 3 d1 + 9 d2 + 27 d3      (d = allele count 0,1,2;  e in 0..80)
+// A missing genotype is stored as dosage 0 and listed in a per-marker CSR list of individuals
+// (miss_off / miss_idx), which makes the transcode invertible bit for bit and gives
+//     sum a*eps = sum_q table_q[e_q]          sum b*eps = sum eps - sum_{missing} eps.
+// Columns are padded with zero bytes to a whole number of ROWS of 64 bytes (16 words, 256
+// individuals); the residuals are padded with zeros likewise (npad = 256 * nrows).
 //
-// Codes are re-coded so that the 2-bit field IS the dosage:  0,1,2 = allele count, 3 = missing.
-// That makes a group register  g = sum_k d_k 4^k  and lets the dot product be taken WITHOUT
-// extracting fields:  with  X_k = (g << (30-2k)) mod 2^32 = 2^30 * sum_{j<=k} d_j 4^(j-k)
-//     sum_k X_k * w_k = 2^30 * sum_j d_j eps_j      when  w_k = eps_k - eps_{k+1}/4   (eps_n := 0)
-// (the sum telescopes).  X_k is fed to the FP64 pipe as the denormal double (hi = 0, lo = X_k)
-// = X_k * 2^-1074, and w_k is pre-scaled by 2^1000, so one marker costs one shift and one DFMA per
-// genotype and the partial sums come out scaled by 2^-44 exactly.  See DESIGN.md "decode algebra".
+// Why base 3: the dot product is taken by table look-up -- one shared-memory read and one fp64 add
+// per QUAD instead of one multiply-add per genotype (on sm_100a the per-genotype
+// fp64 path is limited to ~30 genotypes/clk/SM by issue, the look-up path to 64 by shared-memory
+// bandwidth).  A quad's table has 81 entries x 8 B; with 2-bit codes it would need 256 (3.2x the
+// shared memory, 3.2x the build work, 3x the passes).
+//
+// Table geometry in shared memory (one CTA per SM).  A CTA owns a contiguous range of rows.  The
+// tables of one (row, trait) SLOT take kSlotBytes = 2 regions x 81 entries x 256 B:
+//     address(slot, k, e, l) = kTabBase + slot*kSlotBytes + (k>>1)*kRegionBytes + e*256 + (k&1)*128 + l*8
+// for byte k (0..3) of word l (0..15) of the row.  For a fixed k the 16 lanes of a half-warp hit 16
+// distinct 8-byte bank pairs whatever their e: every look-up is conflict-free.  e*256 + l*8 is formed
+// by ONE byte-permute (PRMT) of the genotype word with the lane constant l*8; the rest is the
+// immediate offset of the LDS instruction.  That requires absolute shared addresses, hence kTabBase.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -34,72 +39,68 @@
 
 namespace gmrm {
 
-constexpr int kLanesPerTile = 128;   // 4 sub-partitions x 32 lanes
-constexpr int kMaxE4 = 8;            // <= 32 individuals per lane-slot (two 32-bit words)
-constexpr double kWeightScale = 1.0715086071862673e+301;   // 2^1000
-constexpr double kDotUnscale = 17592186044416.0;           // 2^44  (= 2^1074 / 2^30 / 2^1000)
+constexpr int kRowBytes = 64;                        // bytes of one column per row
+constexpr int kRowWords = 16;
+constexpr int kRowInd = 256;                         // individuals per row
+constexpr int kTabEntries = 81;
+constexpr int kRegionBytes = kTabEntries * 256;      // 20,736
+constexpr int kSlotBytes = 2 * kRegionBytes;         // 41,472
+constexpr int kMaxSlots = 4;                         // (row, trait) slots per pass: 165,888 B of tables
+constexpr uint32_t kTabBase = 1024;                  // absolute shared-memory address of slot 0
 
 struct Layout {
     int32_t N = 0;        // individuals
     int32_t mbytes = 0;   // ceil(N/4): bytes per PLINK column
-    int32_t nsm = 0;      // tiles per column
-    int32_t E4 = 0;       // bytes per lane-slot
-    int32_t E = 0;        // individuals per lane-slot
-    int32_t tile_bytes = 0;
-    int64_t col_stride = 0;
-    int64_t npad = 0;     // nsm * 128 * E individuals incl. padding
+    int32_t nrows = 0;    // rows per column
+    int32_t nsm = 0;      // CTAs sharing the rows (one per SM)
+    int64_t col_stride = 0;   // nrows * 64
+    int64_t npad = 0;         // nrows * 256 individuals incl. padding
 
-    GMRM_HD int nwords() const { return E4 / 4; }
-    GMRM_HD int nhalf() const { return (E4 % 4) / 2; }
-    GMRM_HD int nbyte() const { return E4 % 2; }
+    GMRM_HD int row_begin(int cta) const { return (int)((int64_t)cta * nrows / nsm); }
+    GMRM_HD int max_rows_per_cta() const { return (nrows + nsm - 1) / nsm; }
 };
-
-// Smallest E4 such that nsm tiles cover N individuals.  Returns 0 if N does not fit.
-inline int choose_E4(int64_t N, int nsm) {
-    const int64_t per4 = (int64_t)nsm * kLanesPerTile * 4;
-    const int64_t e4 = (N + per4 - 1) / per4;
-    return e4 < 1 ? 1 : (e4 > kMaxE4 ? 0 : (int)e4);
-}
 
 inline Layout make_layout(int32_t N, int nsm) {
     Layout L;
     L.N = N;
     L.mbytes = (N + 3) / 4;
+    L.nrows = (L.mbytes + kRowBytes - 1) / kRowBytes;
     L.nsm = nsm;
-    L.E4 = choose_E4(N, nsm);
-    L.E = 4 * L.E4;
-    L.tile_bytes = kLanesPerTile * L.E4;
-    L.col_stride = (int64_t)nsm * L.tile_bytes;
-    L.npad = (int64_t)nsm * kLanesPerTile * L.E;
+    L.col_stride = (int64_t)L.nrows * kRowBytes;
+    L.npad = (int64_t)L.nrows * kRowInd;
     return L;
 }
 
-// Offset, inside a tile, of byte b (0..E4-1) of lane-slot ls (0..127).
-GMRM_HD int tile_byte_offset(int E4, int ls, int b) {
-    const int nw = E4 / 4;
-    if (b < 4 * nw) return (b / 4) * (kLanesPerTile * 4) + ls * 4 + (b % 4);
-    int off = nw * kLanesPerTile * 4;
-    b -= 4 * nw;
-    if (E4 & 2) {
-        if (b < 2) return off + ls * 2 + b;
-        off += kLanesPerTile * 2;
-        b -= 2;
+// PLINK byte (4 codes) -> base-3 quad byte + 4-bit mask of missing genotypes, and back.
+GMRM_HD uint8_t plink_to_tri(uint8_t x, uint32_t* missmask) {
+    uint32_t e = 0, mm = 0, w = 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t c = (x >> (2 * k)) & 3u;
+        const uint32_t d = c == 0 ? 2u : (c == 2 ? 1u : 0u);   // 00 -> 2, 10 -> 1, 11 -> 0, 01 (missing) -> 0 + flag
+        e += d * w;
+        w *= 3;
+        if (c == 1) mm |= 1u << k;
     }
-    return off + ls + b;
+    *missmask = mm;
+    return (uint8_t)e;
 }
-
-// PLINK byte (4 codes) -> dosage byte (4 fields: 0,1,2 = allele count, 3 = missing), and back.
-//   00->10, 01->11, 10->01, 11->00 :  out_hi = ~in_hi, out_lo = in_hi ^ in_lo
-GMRM_HD uint8_t plink_to_dosage(uint8_t x) {
-    return (uint8_t)(((~x) & 0xAA) | (((x >> 1) ^ x) & 0x55));
+// base-3 quad byte -> the four dosages as 2-bit fields (field k = dosage of individual 4q+k)
+GMRM_HD uint32_t tri_to_fields(uint32_t e) {
+    const uint32_t d3 = e / 27u, r3 = e - 27u * d3, d2 = r3 / 9u, r2 = r3 - 9u * d2, d1 = r2 / 3u, d0 = r2 - 3u * d1;
+    return d0 | (d1 << 2) | (d2 << 4) | (d3 << 6);
 }
-GMRM_HD uint8_t dosage_to_plink(uint8_t y) {
-    return (uint8_t)(((~y) & 0xAA) | ((((~y) >> 1) ^ y) & 0x55));
-}
-
-// Weights of one group of n genotypes: w_k = 2^1000 * (eps_k - eps_{k+1}/4), eps_n := 0.
-GMRM_HD double group_weight(double eps_k, double eps_k1) {
-    return kWeightScale * (eps_k - 0.25 * eps_k1);
+// dosage fields + missing mask -> PLINK byte
+GMRM_HD uint8_t fields_to_plink(uint32_t f, uint32_t missmask) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t d = (f >> (2 * k)) & 3u;
+        uint32_t c = d == 2 ? 0u : (d == 1 ? 2u : 3u);
+        if ((missmask >> k) & 1u) c = 1u;
+        x |= c << (2 * k);
+    }
+    return (uint8_t)x;
 }
 
 }  // namespace gmrm

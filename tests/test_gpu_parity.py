@@ -62,7 +62,7 @@ def test_decode_matches_reference_tables(api, oracle):
     # all 256 byte values in every byte position class, against dotp_lut_a/b as shipped by the reference
     raw = np.fromfile(os.path.join(GOLDEN, "lut_ref.bin"))
     lut_a, lut_b, lut_na = raw[:1024], raw[1024:2048], raw[2048:]
-    N = 7000                              # two tiles, E4 = 7: word, half and byte groups all in use
+    N = 7000                              # 28 rows over two CTAs
     mbytes = N // 4
     M = 256
     bed = np.empty((M, mbytes), dtype=np.uint8)
@@ -119,7 +119,7 @@ def test_marker_stats_dot_and_update(api, oracle, tmp_path, N, M, T, nsm, na, mi
         want = np.array([oracle.dot(inp["bed"][j], eps[t], mave_o[j], msig_o[j]) for j in range(M)])
         scale = np.abs(want).max()
         assert np.abs(got[:, t] - want).max() <= 1e-12 * scale
-    # a few published updates, then dots again (exercises K3 and the per-tile sums)
+    # a few published updates, then dots again (exercises the update phase of the step kernel and the residual sums)
     for n in range(6):
         t = n % T
         j = int(rng.integers(0, M))
@@ -138,20 +138,20 @@ def test_marker_stats_dot_and_update(api, oracle, tmp_path, N, M, T, nsm, na, mi
     e.close()
 
 
-@pytest.mark.parametrize("kernel,variant", [(1, 0), (0, 0), (0, 1), (0, 2), (0, 3)])
-@pytest.mark.parametrize("N,nsm", [(128 * 28 - 1, 1), (5000, 2), (20000, 0), (128 * 32, 1), (128 * 20 - 2, 1), (777, 1)])
-def test_dot_kernel_variants(api, oracle, tmp_path, monkeypatch, kernel, variant, N, nsm):
-    """Both dot kernels (GMRM_DOT_KERNEL: 1 = table lookup, 0 = shift+DFMA with its (consumer warps, batch)
-    variants, GMRM_DOT_VARIANT) against the oracle, with a marker count that is not a multiple of the batch."""
-    monkeypatch.setenv("GMRM_DOT_KERNEL", str(kernel))
-    monkeypatch.setenv("GMRM_DOT_VARIANT", str(variant))
-    M = 203
-    inp = make_case(oracle, tmp_path, N=N, M=M, missing_rate=0.01, seed=variant + 3)
+@pytest.mark.parametrize("N,nsm,T,M", [(1024 * 5 - 1, 1, 1, 203), (1024 * 13, 1, 1, 40), (256 * 7 + 3, 2, 2, 77), (20000, 0, 1, 203),
+                                        (777, 1, 3, 33), (256 * 4, 1, 4, 50), (256 * 3 - 2, 1, 5, 19), (3000, 1, 7, 21),
+                                        (256 * 11 + 9, 3, 2, 130), (100000, 0, 1, 48)])
+def test_step_kernel_shapes(api, oracle, tmp_path, N, nsm, T, M):
+    """The table-lookup step kernel against the oracle's dot products over the shapes that change its code path:
+    1..5 rows per pass, several passes per CTA, CTAs without rows, 1..5 traits per launch and trait chunks (T=7),
+    marker counts that are not a multiple of the 16-marker batch."""
+    inp = make_case(oracle, tmp_path, N=N, M=M, T=T, na_rate=0.01 if T > 1 else 0.0, missing_rate=0.01, seed=N % 31 + T)
     e = engine_for(api, inp, nsm=nsm)
-    got = e.dot_products(np.arange(M, dtype=np.int32))[:, 0]
-    mave_o, msig_o = oracle.marker_stats(inp["bed"], N, inp["mask4"][0], int(inp["nonas"][0]))
-    want = np.array([oracle.dot(inp["bed"][j], inp["eps0"][0], mave_o[j], msig_o[j]) for j in range(M)])
-    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+    got = e.dot_products(np.arange(M, dtype=np.int32))
+    for t in range(T):
+        mave_o, msig_o = oracle.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
+        want = np.array([oracle.dot(inp["bed"][j], inp["eps0"][t], mave_o[j], msig_o[j]) for j in range(M)])
+        assert np.abs(got[:, t] - want).max() <= 1e-12 * np.abs(want).max()
     e.close()
 
 
