@@ -126,9 +126,11 @@ struct gmrm_engine {
     struct MissChunk { int begin = 0, count = 0; std::vector<uint32_t> cnt; DevBuf<uint32_t>* idx = nullptr; uint64_t total = 0; };
     std::vector<MissChunk> miss_chunks;
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
-    int step_warps = 16;             // consumer warps of the step kernel (GMRM_STEP_WARPS=23: measured alternative)
+    int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
+    int step_warps = 16;             // consumer warps of the step kernel (GMRM_STEP_WARPS=20: measured alternative)
     DevBuf<PubEntry> pub;
     DevBuf<int64_t> npub;
+    DevBuf<unsigned long long> prof;   // GMRM_STEP_PROF=1: cycle counters of the step kernel
     // replay staging
     DevBuf<int32_t> rep_perm;
     DevBuf<double> rep_u, rep_z, rep_small;
@@ -187,7 +189,11 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->marker_begin = S;
     e->Mloc = Slast + Mlast - S;
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
-    if (const char* v = getenv("GMRM_STEP_WARPS")) e->step_warps = atoi(v) == 23 ? 23 : 16;
+    if (const char* v = getenv("GMRM_STEP_WARPS")) e->step_warps = atoi(v) == 20 ? 20 : 16;
+    if (const char* v = getenv("GMRM_STEP_PF")) e->step_pf = atoi(v);
+    if (getenv("GMRM_STEP_PROF")) {
+        if (e->prof.alloc(8) != 0 || e->prof.zero(nullptr) != 0) { delete e; return GMRM_ECUDA; }
+    }
     step_plan(e->L, e->Vl, c->T, &e->step_tc, &e->step_rpp);
     if (e->step_tc < 1 || e->step_rpp < 1) {
         const int vl = e->Vl;
@@ -241,6 +247,12 @@ void gmrm_destroy(gmrm_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
+    if (e->prof.p) {
+        unsigned long long h[8];
+        if (cudaMemcpy(h, e->prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[3] && h[6])
+            fprintf(stderr, "step prof (cycles per batch): consumer wait-issue %.0f wait-data %.0f compute %.0f (%llu batches); producer wait-empty %.0f issue %.0f (%llu batches)\n",
+                    (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3], h[3], (double)h[4] / h[6], (double)h[5] / h[6], h[6]);
+    }
     delete e;
 }
 
@@ -484,7 +496,8 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const int
         p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
         p.delta = e->cfg.world_size > 1 ? e->delta.p : nullptr;
         p.err = e->err.p;
-        p.nwarps = e->step_warps;
+        p.prof = e->prof.p;
+        p.pf = e->step_pf;
         const int rc = launch_step(e->L, std::min(tc, T - t0), p, e->stream);
         if (rc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         if (nlaunch) (*nlaunch)++;

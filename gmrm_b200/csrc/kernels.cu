@@ -249,60 +249,31 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // K1: one marker-step of one GPU -- apply the previous step's published updates, build the look-up
 // tables of this CTA's rows, stream the step's V columns through them (layout.h).
 //
-// One CTA per SM: NW consumer warps + 1 producer warp.  CTA c owns rows [row_begin(c), row_begin(c+1)) of
-// every column and of the residuals.  The rows are taken in passes of <= rows_per_pass rows (as many
-// (row, trait) table slots as shared memory holds):
+// One CTA per SM, 16 warps.  CTA c owns rows [row_begin(c), row_begin(c+1)) of every column and of the
+// residuals.  The rows are taken in passes of <= rows_per_pass rows (as many (row, trait) table slots as
+// shared memory holds):
 //   update: every thread owns up to 2 quads of the CTA's rows per round; for each published marker of the
 //           previous step (rank order) it adds  v[dosage]  to its 4 residuals -- one PRMT + LDS.64 + DADD per
 //           individual, NA / missing individuals are routed to a zero entry
 //   build : half-warp <-> (slot, byte k, third d3 of the 81 entries); lane l owns the quad 4l+k of the row:
 //           reads its 4 residuals, writes 27 entries  sum_k d_k eps_k  (conflict-free 8-byte stores)
-//   feed  : the producer warp copies, for every batch of 16 markers, the pass's rows of each marker
-//           (<= 256 contiguous bytes) into an 8-stage shared-memory ring with cp.async.bulk (TMA),
-//           completion on mbarriers; it runs ahead across passes
-//   stream: consumer warp w takes batches w, w+NW, ... of 16 markers; in a batch, half-warp h works on marker
-//           2i+h of pair i = 0..7; lane l reads word l of each row from the ring and per byte does
-//           PRMT -> LDS.64 -> DADD  into the pair's accumulator; a 16-lane transposed butterfly leaves one
-//           total per marker, added to the marker's partial sum in shared memory (each marker is always
-//           served by the same lane: plain read-modify-write).
+//   stream: warp w takes batches w, w+16, ... of 16 markers; in a batch, half-warp h works on marker 2i+h of
+//           pair i = 0..7; lane l loads word l of each of the pass's rows straight from HBM/L2 into registers,
+//           one batch ahead of its use (and prefetches into L2 further ahead), and per byte does
+//           PRMT -> LDS.64 -> DADD  into the pair's accumulator; a 16-lane transposed butterfly leaves one total
+//           per marker, added to the marker's partial sum in shared memory (each marker is always served by the
+//           same lane: plain read-modify-write).
+//   (A shared-memory ring fed by a producer warp -- cp.async.bulk or cp.async -- was measured and dropped: with
+//   227 KB of tables + partials only 32-40 KB are left for it, and the producer hand-off costs more than the
+//   register double-buffer; profiles/README.md.)
 // At the end the CTA writes partial[v][t][cta] and its sum of residuals spart[t][cta]; the sampler kernel
 // adds the nsm partials of a marker in a fixed order.
 // =====================================================================================
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel, not as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void consumer_sync(int nthreads) {      // named barrier 1: the consumer warps only
-    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-}
-
 struct PubStage { double v[4]; };   // increment by dosage: (a - mave*b) * dbeta*msig for a = 0,1,2 (b = 1); v[3] = 0
 struct PubInfo { int32_t col; uint32_t nmiss; };
 
@@ -333,12 +304,6 @@ __device__ __forceinline__ uint32_t byte_into(uint32_t word, uint32_t base) { //
 __host__ __device__ constexpr int tab_imm(int slot, int k) {
     return (int)kTabBase + slot * kSlotBytes + (k >> 1) * kRegionBytes + (k & 1) * 128;
 }
-// ring geometry: a batch of 16 markers; the rows of one marker are contiguous; an even row count gets 64 B of
-// padding so that the two half-warps (markers 2i and 2i+1) read disjoint banks
-__host__ __device__ constexpr int ring_marker_stride(int nr) { return nr * kRowBytes + ((nr & 1) ? 0 : kRowBytes); }
-constexpr int kRingStages = 8;
-constexpr int kRingStageBytes = kBatch * ring_marker_stride(kMaxSlots);    // 16 x 320
-
 // acc[t] += table(slot SLOT + t, byte K)[e] for the T traits of a row: one LDS.64 + one DADD each
 template <int SLOT, int K, int T, int TT = 0>
 __device__ __forceinline__ void lookup_traits(double (&acc)[T], uint32_t a) {
@@ -507,37 +472,60 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
     }
 }
 
-// ---- (c) stream the V columns through the tables of NR rows.  gb0 = ring sequence number of this pass's batch 0.
-template <int NR, int T, int NW>
-__device__ __forceinline__ void stream_rows(const StepParams& p, double* part, uint32_t ring_u32, uint64_t* full, uint64_t* empty,
-                                            const volatile int* issued, int gb0) {
-    constexpr int STRIDE = ring_marker_stride(NR);
+constexpr int kStepWarps = 16, kStepThreads = kStepWarps * 32;     // 128 registers per thread
+
+// ---- (c) stream the V columns through the tables of NR rows
+template <int NR, int T>
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
     const uint32_t low = (uint32_t)l16 * 8u;
     const int nb = (p.V + kBatch - 1) / kBatch;
+    int b = warp;
+    if (b >= nb) return;
+    const uint8_t* base = p.bed + (int64_t)row0 * kRowBytes + l16 * 4;
+
+    auto loadcols = [&](int bb) -> int {
+        const int v = bb * kBatch + l16;
+        return (bb < nb && v < p.V) ? max(p.cols[v], 0) : 0;
+    };
+    uint32_t Wn[8][NR];
+    auto issue = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int col = __shfl_sync(0xffffffffu, c, 2 * i + h);
+            const uint8_t* ptr = base + (int64_t)col * p.col_stride;
+#pragma unroll
+            for (int rr = 0; rr < NR; rr++) Wn[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
+        }
+    };
+    issue(loadcols(b));
+    int cn = loadcols(b + kStepWarps);
+    // L2 prefetch kPfAhead batches ahead of the register loads (which run one batch ahead): the 16 warps then keep
+    // ~192 KB per SM in flight towards HBM instead of 64 KB
+    constexpr int kPfAhead = 4;
+    int pcol = p.pf ? loadcols(b + kPfAhead * kStepWarps) : 0;
+    const uint8_t* pf_base = p.bed + (int64_t)row0 * kRowBytes;
+    const int pf_off_a = (lane >> 4) * 128, pf_off_b = (lane >> 4) ? NR * kRowBytes - 1 : 256;
     const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
     const int own = ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1);   // pair whose total this lane ends up with
-    const uint32_t lane_off = (uint32_t)(h * STRIDE + l16 * 4);
 
-    for (int b = warp; b < nb; b += NW) {
-        const int gb = gb0 + b, s = gb % kRingStages;
-        // Several consumers can be more than one ring revolution ahead of the producer; a parity wait is only
-        // meaningful once the stage's barrier has reached this batch's phase, i.e. once the batch has been issued.
-        for (uint32_t spins = 0; *issued <= gb; ++spins)
-            if (spins > (1u << 26)) __trap();
-        mbar_wait(&full[s], (uint32_t)(gb / kRingStages) & 1u);
-        const uint32_t st = ring_u32 + (uint32_t)(s * kRingStageBytes) + lane_off;
+    for (; b < nb; b += kStepWarps) {
         uint32_t W[8][NR];
-#define GMRM_LOADW(I)                                                                                   \
-    {                                                                                                   \
-        W[I][0] = lds_u32_imm<I * 2 * STRIDE>(st);                                                      \
-        if constexpr (NR > 1) W[I][NR > 1 ? 1 : 0] = lds_u32_imm<I * 2 * STRIDE + 64>(st);              \
-        if constexpr (NR > 2) W[I][NR > 2 ? 2 : 0] = lds_u32_imm<I * 2 * STRIDE + 128>(st);             \
-        if constexpr (NR > 3) W[I][NR > 3 ? 3 : 0] = lds_u32_imm<I * 2 * STRIDE + 192>(st);             \
-    }
-        GMRM_LOADW(0) GMRM_LOADW(1) GMRM_LOADW(2) GMRM_LOADW(3) GMRM_LOADW(4) GMRM_LOADW(5) GMRM_LOADW(6) GMRM_LOADW(7)
-#undef GMRM_LOADW
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int rr = 0; rr < NR; rr++) W[i][rr] = Wn[i][rr];
+        if (b + kStepWarps < nb) {
+            issue(cn);
+            cn = loadcols(b + 2 * kStepWarps);
+        }
+        if (p.pf && b + kPfAhead * kStepWarps < nb) {
+            const uint8_t* a = pf_base + (int64_t)pcol * p.col_stride;
+            if (pf_off_a < NR * kRowBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_a));
+            if (pf_off_b < NR * kRowBytes && NR > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_b));
+            pcol = loadcols(b + (kPfAhead + 1) * kStepWarps);
+        }
         double acc[8][T];
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -549,11 +537,7 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, double* part, u
         lookup_traits<RR * T, K, T>(acc[i], tab_addr<K>(W[i][RR], low));
 #define GMRM_ROW(RR)                                                          \
     if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_LOOKUP(RR, 1) GMRM_LOOKUP(RR, 2) GMRM_LOOKUP(RR, 3) }
-        // release the stage once its words are in registers (the comparison makes the arrive wait for the last load;
-        // bytes are < 81, so it is never true)
-        __syncwarp();
-        if (lane == 0 || W[7][NR - 1] == 0xffffffffu) mbar_arrive(&empty[s]);
-        GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3)
+        GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3) GMRM_ROW(4)
 #undef GMRM_ROW
 #undef GMRM_LOOKUP
 
@@ -582,93 +566,52 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, double* part, u
     }
 }
 
-// NW consumer warps: 16 (96 registers per thread) or 23 (80 registers; only for T <= 2, whose accumulators fit)
-template <int T, int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) step_kernel(const StepParams p) {
-    constexpr int NT = (NW + 1) * 32, NC = NW * 32;
+template <int T>
+__global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams p) {
+    constexpr int NT = kStepThreads;
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint32_t b0 = smem_u32(smem_raw);
     if (b0 > kTabBase) {                                  // the LDS immediates assume tables at absolute address kTabBase
         if (threadIdx.x == 0) atomicExch(p.err, 10);
         return;
     }
-    const int nsm = gridDim.x, cta = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nsm = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
     const int rb = (int)((int64_t)cta * p.nrows / nsm), re = (int)((int64_t)(cta + 1) * p.nrows / nsm), nr = re - rb;
     const int nrmax = (p.nrows + nsm - 1) / nsm;
     const int slots = p.V > 0 ? p.rows_per_pass * T : 0;
-    // shared memory carve-up (absolute addresses: kTabBase is 1024, every block below stays 256-aligned until `part`)
+    // shared memory carve-up (absolute addresses: kTabBase is 1024; `stage` stays 256-aligned)
     uint8_t* tabs = smem_raw + (kTabBase - b0);
-    PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)slots * kSlotBytes);        // 256-aligned (kSlotBytes = 162 * 256)
-    uint8_t* ring = reinterpret_cast<uint8_t*>(stage + kPubCap);
-    double* part = reinterpret_cast<double*>(ring + (p.V > 0 ? kRingStages * kRingStageBytes : 0));
+    PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)slots * kSlotBytes);        // kSlotBytes = 162 * 256
+    double* part = reinterpret_cast<double*>(stage + kPubCap);
     PubInfo* info = reinterpret_cast<PubInfo*>(part + (size_t)p.V * T);
     uint32_t* lut = reinterpret_cast<uint32_t*>(info + kPubCap);
     uint32_t* bitmap = lut + 82;
     double* red = reinterpret_cast<double*>(bitmap + ((nrmax * 8 + 1) & ~1));
     int* wcnt = reinterpret_cast<int*>(red + 32);
-    uint64_t* full = reinterpret_cast<uint64_t*>(wcnt + 32);
-    uint64_t* empty = full + kRingStages;
-    volatile int* issued = reinterpret_cast<volatile int*>(empty + kRingStages);   // batches the producer has issued so far
 
-    if (tid == 0 && p.V > 0) {
-        *issued = 0;
-        for (int s = 0; s < kRingStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
     if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, rb, nr, stage, info, lut, bitmap, wcnt);
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     if (p.V == 0) return;
 
-    const int rpp = p.rows_per_pass;
-    const int npass = (nr + rpp - 1) / rpp;
-    const int nb = (p.V + kBatch - 1) / kBatch;
     double es[T];
 #pragma unroll
     for (int t = 0; t < T; t++) es[t] = 0.0;
-
-    if (warp == NW) {
-        // ---------------- producer: lane j < 16 issues the copy of marker j of every batch, pass after pass ----------------
-        const uint32_t ring_u32 = smem_u32(ring);
-        for (int pass = 0; pass < npass; pass++) {
-            const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
-            const int nrp = r_hi - r_lo;
-            const uint32_t bytes = (uint32_t)nrp * kRowBytes, stride = (uint32_t)ring_marker_stride(nrp);
-            const uint8_t* src0 = p.bed + (int64_t)r_lo * kRowBytes;
-            for (int b = 0; b < nb; b++) {
-                const int gb = pass * nb + b, s = gb % kRingStages;
-                if (gb >= kRingStages) mbar_wait(&empty[s], (uint32_t)((gb / kRingStages) - 1) & 1u);
-                const int v = b * kBatch + lane;
-                int col = 0;
-                if (lane < kBatch && v < p.V) col = max(p.cols[v], 0);
-                if (lane == 0) mbar_expect_tx(&full[s], bytes * kBatch);
-                __syncwarp();
-                if (lane < kBatch)
-                    bulk_g2s(ring_u32 + (uint32_t)(s * kRingStageBytes) + (uint32_t)lane * stride, src0 + (int64_t)col * p.col_stride, bytes, &full[s]);
-                if (lane == 0) {
-                    __threadfence_block();
-                    *issued = gb + 1;
-                }
-            }
-        }
-    } else {
-        // ---------------- consumers ----------------
-        const uint32_t ring_u32 = smem_u32(ring);
-        for (int pass = 0; pass < npass; pass++) {
-            const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
-            const int nrp = r_hi - r_lo;
-            if (pass) consumer_sync(NC);                  // everyone is done with the previous tables
-            build_tables<T, NC>(p, r_lo, nrp, es);
-            consumer_sync(NC);
-            const int gb0 = pass * nb;
-            switch (nrp) {
-            case 1: stream_rows<1, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
-            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
-            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
-            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, NW>(p, part, ring_u32, full, empty, issued, gb0); break;
-            default: break;
-            }
+    const int rpp = p.rows_per_pass;
+    const int npass = (nr + rpp - 1) / rpp;
+    for (int pass = 0; pass < npass; pass++) {
+        const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
+        const int nrp = r_hi - r_lo;
+        if (pass) __syncthreads();                        // everyone is done with the previous tables
+        build_tables<T, NT>(p, r_lo, nrp, es);
+        __syncthreads();
+        switch (nrp) {
+        case 1: stream_rows<1, T>(p, r_lo, part); break;
+        case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part); break;
+        case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part); break;
+        case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part); break;
+        case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part); break;
+        default: break;
         }
     }
     __syncthreads();
@@ -962,14 +905,13 @@ constexpr int kMaxDynSmem = 232448;   // 227 KB: the most one CTA can opt into o
 int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
     const int nrmax = L.max_rows_per_cta();
     const int64_t bytes = (int64_t)kTabBase + (int64_t)(V > 0 ? rows_per_pass * T : 0) * kSlotBytes + (int64_t)kPubCap * 32 +
-                          (V > 0 ? (int64_t)kRingStages * kRingStageBytes : 0) + (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 +
-                          (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4 + 2 * kRingStages * 8 + 16;
+                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4;
     return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 
 void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass) {
     *traits_per_launch = 0; *rows_per_pass = 0;
-    for (int tc = Ttot < kMaxSlots ? Ttot : kMaxSlots; tc >= 1; tc--) {
+    for (int tc = Ttot < 4 ? Ttot : 4; tc >= 1; tc--) {   // step_kernel<T> is instantiated for T = 1..4
         int rpp = kMaxSlots / tc;
         while (rpp >= 1 && step_smem_bytes(L, V, tc, rpp) < 0) rpp--;
         if (rpp < 1) continue;
@@ -991,18 +933,10 @@ static int step_launch_t(const Layout& L, const StepParams& p, cudaStream_t s) {
     if (smem < 0) return -3;
     static bool attr = false;
     if (!attr) {
-        if (cudaFuncSetAttribute(step_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
-        if constexpr (T <= 2)
-            if (cudaFuncSetAttribute(step_kernel<T, 23>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
         attr = true;
     }
-    if constexpr (T <= 2) {
-        if (p.nwarps == 23) {
-            step_kernel<T, 23><<<L.nsm, 24 * 32, smem, s>>>(p);
-            return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
-        }
-    }
-    step_kernel<T, 16><<<L.nsm, 17 * 32, smem, s>>>(p);
+    step_kernel<T><<<L.nsm, kStepThreads, smem, s>>>(p);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 // T = traits of this launch (1..4); p.rows_per_pass * T <= kMaxSlots

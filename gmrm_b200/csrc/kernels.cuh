@@ -41,7 +41,8 @@ struct StepParams {
     const uint32_t* miss_idx;
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     int32_t* err;
-    int32_t nwarps;          // consumer warps of the step kernel: 16 or 23
+    int32_t pf;              // 1: L2 prefetch ahead of the streaming loads
+    unsigned long long* prof;   // debug (GMRM_STEP_PROF): 8 cycle counters, see stream_rows / producers
 };
 
 struct SampleParams {

@@ -45,7 +45,7 @@ constexpr int kRowInd = 256;                         // individuals per row
 constexpr int kTabEntries = 81;
 constexpr int kRegionBytes = kTabEntries * 256;      // 20,736
 constexpr int kSlotBytes = 2 * kRegionBytes;         // 41,472
-constexpr int kMaxSlots = 4;                         // (row, trait) slots per pass: 165,888 B of tables
+constexpr int kMaxSlots = 5;                         // (row, trait) slots per pass: 207,360 B of tables
 constexpr uint32_t kTabBase = 1024;                  // absolute shared-memory address of slot 0
 
 struct Layout {
