@@ -490,7 +490,7 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const int
     for (int t0 = 0; t0 < T; t0 += tc) {
         StepParams p{};
         p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.nrows = e->L.nrows; p.cols = cols; p.V = V;
-        p.eps = e->eps.p; p.npad = e->L.npad; p.Ttot = T; p.t0 = t0; p.rows_per_pass = rpp;
+        p.eps = e->eps.p; p.npad = e->L.npad; p.Ttot = T; p.t0 = t0; p.rows_per_pass = rpp; p.npass = step_npass(e->L, rpp);
         p.partial = partial; p.spart = e->spart.p;
         p.pcols = pcols; p.pV = pV; p.pub = e->pub.p; p.mask4 = e->mask4.p;
         p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;

@@ -313,36 +313,69 @@ __device__ __forceinline__ void lookup_traits(double (&acc)[T], uint32_t a) {
     }
 }
 
+// Row ownership.  The rows of a column are cut into npass contiguous ranges (one per pass); in pass q the range is
+// split evenly over the CTAs, so that during a pass the grid reads ONE contiguous run of every column (neighbouring
+// CTAs read neighbouring 256..320-byte chunks: DRAM pages are used whole).  A CTA therefore owns npass short row
+// ranges; `pr` lists them, local rows are numbered range after range.
+constexpr int kMaxPasses = 64;
+struct PassRows { int start[kMaxPasses], count[kMaxPasses], base[kMaxPasses]; int npass, total; };
+__device__ __forceinline__ void pass_rows(int nrows, int npass, int nsm, int cta, int q, int& start, int& count) {
+    const int lo = (int)((int64_t)nrows * q / npass), hi = (int)((int64_t)nrows * (q + 1) / npass), n = hi - lo;
+    // the CTAs that get the extra row of an uneven split differ from pass to pass (rotation), so that a CTA's total
+    // stays within one row of the average
+    const int c = (cta + q * (nsm / npass)) % nsm;
+    const int a = (int)((int64_t)n * c / nsm), b = (int)((int64_t)n * (c + 1) / nsm);
+    start = lo + a; count = b - a;
+}
+__device__ __forceinline__ int global_row(const PassRows& pr, int local_row) {
+    int q = 0;
+    while (q + 1 < pr.npass && local_row >= pr.base[q + 1]) q++;
+    return pr.start[q] + (local_row - pr.base[q]);
+}
+
+// bytes of the table area; an update-only launch (V == 0) sizes it for staging kPubCap published columns
+__host__ __device__ inline int step_area_bytes(int V, int T, int rows_per_pass, int npass) {
+    if (V > 0) return rows_per_pass * T * kSlotBytes;
+    const long long want = (long long)kPubCap * npass * rows_per_pass * kRowBytes;
+    return (int)(want < 163840 ? want : 163840);
+}
+
 // ---- (a) pending updates: Phenotype::update_epsilon (phenotype.cpp:326-329,375-390) for every published marker
 // of the previous step, in virtual-rank order, restricted to this CTA's rows.  All NT threads of the CTA work.
 template <int T, int NT>
-__device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* stage, PubInfo* info, uint32_t* lut,
-                              uint32_t* bitmap, int* wcnt) {
+__device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage* stage, PubInfo* info, uint32_t* lut,
+                              uint32_t* bitmap, int* wcnt, uint8_t* bytes, int bytes_cap) {
     constexpr int NWALL = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nq = nr * kRowBytes;                      // quads of my rows
+    const int nr = pr.total, nq = nr * kRowBytes;       // quads of my rows
     // base-3 byte -> byte offsets (8 * dosage) of its four individuals into a PubStage
     for (int e = tid; e < kTabEntries; e += NT) {
         const uint32_t f = tri_to_fields(e);
         lut[e] = ((f & 3u) << 3) | (((f >> 2) & 3u) << 11) | (((f >> 4) & 3u) << 19) | (((f >> 6) & 3u) << 27);
     }
     const uint32_t lut_u32 = smem_u32(lut), stage_u32 = smem_u32(stage);
+    // published markers handled per round: their bytes of this CTA's rows are staged in shared memory (the table
+    // area, free at this point) with all loads in flight at once -- the columns were streamed a step ago and are
+    // mostly out of L2, so fetching them entry by entry would expose one HBM round trip per 8 entries
+    const int cap = max(1, min(kPubCap, bytes_cap / max(nq, 1)));
     for (int t = 0; t < T; t++) {
         const int tt = p.t0 + t;
-        double* eps_t = p.eps + (int64_t)tt * p.npad + (int64_t)rb * kRowInd;
-        const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride + (int64_t)rb * kRowBytes;
+        double* eps_t = p.eps + (int64_t)tt * p.npad;
+        const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride;
         for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
             double e[2][4], e0[2][4];
             uint32_t nmask[2];                          // 0x18 in byte k: individual k is not observed -> zero entry
+            int gq[2];                                  // global quad (byte of the column) of local quad q
             bool have[2];
 #pragma unroll
             for (int qq = 0; qq < 2; qq++) {
                 const int q = q0 + qq * NT + tid;
                 have[qq] = q < nq;
-                const uint32_t na = have[qq] ? mask_t[q] : 0u;
+                gq[qq] = have[qq] ? global_row(pr, q >> 6) * kRowBytes + (q & 63) : 0;
+                const uint32_t na = have[qq] ? mask_t[gq[qq]] : 0u;
                 nmask[qq] = ((na & 1u) ? 0u : 0x18u) | ((na & 2u) ? 0u : 0x1800u) | ((na & 4u) ? 0u : 0x180000u) | ((na & 8u) ? 0u : 0x18000000u);
 #pragma unroll
-                for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * q + k] : 0.0; e0[qq][k] = e[qq][k]; }
+                for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * (int64_t)gq[qq] + k] : 0.0; e0[qq][k] = e[qq][k]; }
             }
             bool touched = false;
             for (int v_lo = 0; v_lo < p.pV; v_lo += NT) {
@@ -357,8 +390,8 @@ __device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* sta
                 __syncthreads();
                 int ord = __popc(bal & ((1u << lane) - 1u)), total = 0;
                 for (int w = 0; w < NWALL; w++) { const int c = wcnt[w]; if (w < warp) ord += c; total += c; }
-                for (int r0 = 0; r0 < total; r0 += kPubCap) {
-                    const int n = min(kPubCap, total - r0);
+                for (int r0 = 0; r0 < total; r0 += cap) {
+                    const int n = min(cap, total - r0);
                     __syncthreads();
                     if (on && ord >= r0 && ord < r0 + n) {
                         PubStage& s = stage[ord - r0];
@@ -373,6 +406,27 @@ __device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* sta
                     }
                     __syncthreads();
                     touched = true;
+                    if (q0 == 0 || nq > 2 * NT) {            // (re)stage: once per round unless the rows need several quad chunks
+                        const int npiece = n * nr * 4;       // 16-byte pieces: entry x local row x 4
+                        for (int i0 = tid; i0 < npiece; i0 += 8 * NT) {
+                            uint4 v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int i = i0 + j * NT;
+                                if (i < npiece) {
+                                    const int en = i / (nr * 4), rem = i - en * (nr * 4), lr = rem >> 2, part = rem & 3;
+                                    const uint8_t* src = p.bed + (int64_t)info[en].col * p.col_stride + (int64_t)global_row(pr, lr) * kRowBytes + part * 16;
+                                    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src));
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int i = i0 + j * NT;
+                                if (i < npiece) *reinterpret_cast<uint4*>(bytes + (size_t)i * 16) = v[j];   // == entry*nq + lr*64 + part*16
+                            }
+                        }
+                        __syncthreads();
+                    }
                     for (int g0 = 0; g0 < n; g0 += 8) {
                         uint32_t by[8][2];
 #pragma unroll
@@ -380,8 +434,7 @@ __device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* sta
 #pragma unroll
                             for (int qq = 0; qq < 2; qq++) {
                                 by[j][qq] = 0;
-                                if (g0 + j < n && have[qq])
-                                    by[j][qq] = p.bed[(int64_t)info[g0 + j].col * p.col_stride + (int64_t)rb * kRowBytes + q0 + qq * NT + tid];
+                                if (g0 + j < n && have[qq]) by[j][qq] = bytes[(size_t)(g0 + j) * nq + q0 + qq * NT + tid];
                             }
                         const uint32_t gbase = stage_u32 + (uint32_t)g0 * 32u;   // 256-aligned: stage is, g0 is a multiple of 8
 #define GMRM_APPLY(J)                                                                                              \
@@ -392,8 +445,12 @@ __device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* sta
             __syncthreads();                                                                                      \
             const uint32_t mo = p.miss_off[info[g0 + J].col];                                                     \
             for (uint32_t i = tid; i < info[g0 + J].nmiss; i += NT) {                                             \
-                const int64_t loc = (int64_t)p.miss_idx[mo + i] - (int64_t)rb * kRowInd;                          \
-                if (loc >= 0 && loc < (int64_t)nr * kRowInd) atomicOr(&bitmap[loc >> 5], 1u << (loc & 31));       \
+                const int ind = (int)p.miss_idx[mo + i], grow = ind >> 8;                                         \
+                for (int qp = 0; qp < pr.npass; qp++)                                                             \
+                    if (grow >= pr.start[qp] && grow < pr.start[qp] + pr.count[qp]) {                             \
+                        const int loc = (pr.base[qp] + grow - pr.start[qp]) * kRowInd + (ind & 255);              \
+                        atomicOr(&bitmap[loc >> 5], 1u << (loc & 31));                                            \
+                    }                                                                                             \
             }                                                                                                     \
             __syncthreads();                                                                                      \
         }                                                                                                         \
@@ -424,11 +481,10 @@ __device__ void apply_pending(const StepParams& p, int rb, int nr, PubStage* sta
 #pragma unroll
                 for (int qq = 0; qq < 2; qq++) {
                     if (!have[qq]) continue;
-                    const int q = q0 + qq * NT + tid;
 #pragma unroll
-                    for (int k = 0; k < 4; k++) eps_t[4 * q + k] = e[qq][k];
+                    for (int k = 0; k < 4; k++) eps_t[4 * (int64_t)gq[qq] + k] = e[qq][k];
                     if (p.delta) {
-                        double* d = p.delta + (int64_t)tt * p.npad + (int64_t)rb * kRowInd + 4 * q;
+                        double* d = p.delta + (int64_t)tt * p.npad + 4 * (int64_t)gq[qq];
 #pragma unroll
                         for (int k = 0; k < 4; k++) d[k] += e[qq][k] - e0[qq][k];   // what this shard changed since the last exchange
                     }
@@ -576,32 +632,40 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         return;
     }
     const int nsm = gridDim.x, cta = blockIdx.x, tid = threadIdx.x;
-    const int rb = (int)((int64_t)cta * p.nrows / nsm), re = (int)((int64_t)(cta + 1) * p.nrows / nsm), nr = re - rb;
-    const int nrmax = (p.nrows + nsm - 1) / nsm;
-    const int slots = p.V > 0 ? p.rows_per_pass * T : 0;
+    const int npass = p.npass;
     // shared memory carve-up (absolute addresses: kTabBase is 1024; `stage` stays 256-aligned)
     uint8_t* tabs = smem_raw + (kTabBase - b0);
-    PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)slots * kSlotBytes);        // kSlotBytes = 162 * 256
+    const int area = step_area_bytes(p.V, T, p.rows_per_pass, npass);                        // tables / update staging
+    PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)area);                      // 256-aligned
     double* part = reinterpret_cast<double*>(stage + kPubCap);
     PubInfo* info = reinterpret_cast<PubInfo*>(part + (size_t)p.V * T);
     uint32_t* lut = reinterpret_cast<uint32_t*>(info + kPubCap);
-    uint32_t* bitmap = lut + 82;
-    double* red = reinterpret_cast<double*>(bitmap + ((nrmax * 8 + 1) & ~1));
+    PassRows& pr = *reinterpret_cast<PassRows*>(lut + 82);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(&pr + 1);
+    double* red = reinterpret_cast<double*>(bitmap + ((npass * p.rows_per_pass * 8 + 1) & ~1));
     int* wcnt = reinterpret_cast<int*>(red + 32);
 
+    if (tid == 0) {
+        int tot = 0;
+        for (int q = 0; q < npass; q++) {
+            pass_rows(p.nrows, npass, nsm, cta, q, pr.start[q], pr.count[q]);
+            pr.base[q] = tot;
+            tot += pr.count[q];
+        }
+        pr.npass = npass; pr.total = tot;
+    }
+    __syncthreads();
+    const int nr = pr.total;
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
-    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, rb, nr, stage, info, lut, bitmap, wcnt);
+    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area);
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     if (p.V == 0) return;
 
     double es[T];
 #pragma unroll
     for (int t = 0; t < T; t++) es[t] = 0.0;
-    const int rpp = p.rows_per_pass;
-    const int npass = (nr + rpp - 1) / rpp;
     for (int pass = 0; pass < npass; pass++) {
-        const int r_lo = rb + (int)((int64_t)nr * pass / npass), r_hi = rb + (int)((int64_t)nr * (pass + 1) / npass);
-        const int nrp = r_hi - r_lo;
+        const int r_lo = pr.start[pass], nrp = pr.count[pass];
         if (pass) __syncthreads();                        // everyone is done with the previous tables
         build_tables<T, NT>(p, r_lo, nrp, es);
         __syncthreads();
@@ -902,10 +966,20 @@ void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double*
 
 constexpr int kMaxDynSmem = 232448;   // 227 KB: the most one CTA can opt into on sm_100
 
+// passes of a step: the fewest such that a CTA never gets more than rows_per_pass rows in one
+int step_npass(const Layout& L, int rows_per_pass) {
+    const int64_t cap = (int64_t)rows_per_pass * L.nsm;
+    int np = (int)((L.nrows + cap - 1) / cap);
+    if (np < 1) np = 1;
+    // even split of ceil(nrows/np) rows over nsm CTAs must fit rows_per_pass
+    while (((L.nrows + np - 1) / np + L.nsm - 1) / L.nsm > rows_per_pass) np++;
+    return np;
+}
 int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
-    const int nrmax = L.max_rows_per_cta();
-    const int64_t bytes = (int64_t)kTabBase + (int64_t)(V > 0 ? rows_per_pass * T : 0) * kSlotBytes + (int64_t)kPubCap * 32 +
-                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4;
+    if (step_npass(L, rows_per_pass) > kMaxPasses) return -1;
+    const int nrmax = step_npass(L, rows_per_pass) * rows_per_pass;   // bound on the rows one CTA owns
+    const int64_t bytes = (int64_t)kTabBase + (int64_t)step_area_bytes(V, T, rows_per_pass, step_npass(L, rows_per_pass)) + (int64_t)kPubCap * 32 +
+                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4;
     return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 

@@ -30,6 +30,7 @@ struct StepParams {
     int64_t npad;
     int32_t Ttot, t0;        // this launch handles traits t0 .. t0+T-1 of Ttot
     int32_t rows_per_pass;   // table slots / T
+    int32_t npass;           // step_npass(L, rows_per_pass)
     double* partial;         // [V][Ttot][nsm]   per-CTA partial sums of sum a*eps
     double* spart;           // [Ttot][nsm]      per-CTA sums of eps
     // pending updates (previous step), applied in virtual-rank order
@@ -92,6 +93,7 @@ void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
 // dynamic shared memory the step kernel needs, or -1 if (V, T, rows_per_pass, rows per CTA) do not fit
+int step_npass(const Layout& L, int rows_per_pass);
 int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass);
 // traits per launch and rows per pass for a step of V markers (0 rows = does not fit)
 void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass);
