@@ -20,6 +20,7 @@ struct Options {
     std::vector<double> S;
     // supersets (defaults reproduce the reference: one exchange per marker-step)
     int vranks = 0;          // --vranks: total virtual ranks; 0 = 1024 per GPU
+    int gpus = 1;            // --gpus: GPUs of this node sharing the chain (one host thread each)
     int sync_rate = 1;       // --sync-rate
     unsigned burn_in = 0;    // --burn-in: iterations left out of the posterior-mean summary (.mbet)
     bool check_inputs = false;   // --check-inputs: parse everything, print a summary, no GPU work

@@ -1,0 +1,185 @@
+// gmrm_b200_cli -- drop-in for the Gibbs mode of the reference executable (src/main.cpp:8-24, Bayes::process
+// src/bayes.cpp:318-677): same flags, inputs, outputs and stdout lines; the marker loop runs on B200s through the
+// C ABI (include/gmrm_b200.h).  One host thread per GPU plays the role of one MPI rank of the reference.
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <algorithm>
+#include <cstring>
+#include <iostream>
+#include <mutex>
+#include <thread>
+
+#include "gmrm_b200.h"
+#include "host.hpp"
+
+namespace {
+
+class Barrier {
+public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m_);
+        const int gen = gen_;
+        if (++count_ == n_) { count_ = 0; gen_++; cv_.notify_all(); }
+        else cv_.wait(lk, [&] { return gen != gen_; });
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    int n_, count_ = 0, gen_ = 0;
+};
+
+void ck(int rc, const char* what) {
+    if (rc != 0) {
+        printf("FATAL  : %s: %s\n", what, gmrm_last_error());
+        exit(EXIT_FAILURE);
+    }
+}
+double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Shared {
+    host::Options opt;
+    host::Dims dims;
+    std::vector<host::Phen> phens;
+    std::vector<int32_t> group_index;
+    uint8_t nccl_id[128];
+    int vranks = 0;
+};
+
+void worker(int rank, Shared* sh, Barrier* bar) {
+    const host::Options& o = sh->opt;
+    const int ngpu = o.gpus, T = (int)sh->phens.size(), G = o.ngroups, K = o.nmixtures, N = sh->dims.N, Mt = sh->dims.Mt;
+    gmrm_config cfg{};
+    cfg.device = rank; cfg.N = N; cfg.Mt = Mt; cfg.T = T; cfg.G = G; cfg.K = K;
+    cfg.world_size = ngpu; cfg.world_rank = rank; cfg.vranks = sh->vranks; cfg.sync_rate = o.sync_rate;
+    cfg.shuffle = o.shuffle ? 1 : 0; cfg.seed = o.seed;
+    gmrm_engine* e = nullptr;
+    ck(gmrm_create(&cfg, &e), "gmrm_create");
+    if (ngpu > 1) {
+        if (rank == 0) ck(gmrm_comm_unique_id(sh->nccl_id), "gmrm_comm_unique_id");
+        bar->wait();
+        ck(gmrm_comm_init(e, sh->nccl_id), "gmrm_comm_init");
+    }
+    int32_t S = 0, M = 0;
+    ck(gmrm_shard_info(e, &S, &M, nullptr, nullptr, nullptr), "gmrm_shard_info");
+
+    // ---- genotypes (Bayes::load_genotype, bayes.cpp:867-900): this rank's block, in chunks
+    const double t_load = now();
+    {
+        host::BedReader bed(o.bed_file, N);
+        const int chunk = std::max(1, (int)((256u << 20) / (size_t)bed.mbytes()));
+        std::vector<uint8_t> buf((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
+        for (int done = 0; done < M; done += chunk) {
+            const int n = std::min(chunk, M - done);
+            bed.read(S + done, n, buf.data());
+            ck(gmrm_upload_bed(e, buf.data(), S + done, n), "gmrm_upload_bed");
+        }
+        ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
+    }
+    if (rank == 0) printf("INFO   : time to load genotype data = %.3f seconds.\n", now() - t_load);
+    for (int t = 0; t < T; t++) ck(gmrm_set_phenotype(e, t, sh->phens[t].eps.data(), sh->phens[t].mask4.data(), sh->phens[t].nonas), "gmrm_set_phenotype");
+    ck(gmrm_set_groups(e, sh->group_index.data(), o.cva.data()), "gmrm_set_groups");
+    const double t_stats = now();
+    ck(gmrm_compute_marker_stats(e), "gmrm_compute_marker_stats");
+    if (rank == 0) printf("INFO   : Time to compute the markers' statistics: %.2f seconds.\n", now() - t_stats);
+    ck(gmrm_init_chain(e, nullptr), "gmrm_init_chain");
+
+    // ---- output files (bayes.cpp:322-324): rank 0 deletes and creates, the others open
+    std::vector<host::OutFiles*> outs(T, nullptr);
+    if (rank == 0)
+        for (int t = 0; t < T; t++) outs[t] = new host::OutFiles(o.out_dir, sh->phens[t].stem, true);
+    bar->wait();
+    if (rank != 0)
+        for (int t = 0; t < T; t++) outs[t] = new host::OutFiles(o.out_dir, sh->phens[t].stem, false);
+
+    std::vector<double> sigmag((size_t)T * G), sigmae(T), pi((size_t)T * G * K), mu(T), betas(M);
+    std::vector<int32_t> m0((size_t)T * G), cass((size_t)T * G * K), comp(M);
+    std::vector<std::vector<double>> bmean(T, std::vector<double>(o.burn_in < o.iterations ? M : 0, 0.0));
+    gmrm_state st{sigmag.data(), sigmae.data(), pi.data(), mu.data(), m0.data(), cass.data()};
+    for (unsigned it = 1; it <= o.iterations; it++) {
+        const double ts = now();
+        ck(gmrm_run_iteration(e, (int32_t)it, nullptr), "gmrm_run_iteration");
+        ck(gmrm_get_state(e, &st), "gmrm_get_state");
+        gmrm_timing tm{};
+        gmrm_get_timing(e, &tm);
+        if (rank % 10 == 0)
+            for (int t = 0; t < T; t++) {
+                double sg = 0.0;
+                for (int g = 0; g < G; g++) sg += sigmag[(size_t)t * G + g];
+                printf("RESULT : i:%d r:%d p:%d  sum sigmaG = %20.15f  sigmaE = %20.15f\n", it, rank, t, sg, sigmae[t]);   // bayes.cpp:641
+            }
+        if (rank == 0) printf("RESULT : It %d  total proc time = %7.3f sec, with sync time = %7.3f\n", it, now() - ts, tm.exchange_ms * 1e-3);   // bayes.cpp:655
+        const bool save = it % o.thin == 0, mean = it > o.burn_in && !bmean[0].empty();
+        if (save || mean)
+            for (int t = 0; t < T; t++) {
+                ck(gmrm_get_betas(e, t, betas.data()), "gmrm_get_betas");
+                if (mean) for (int j = 0; j < M; j++) bmean[t][j] += betas[j];
+                if (!save) continue;
+                const unsigned nthinned = it / o.thin - 1;                                             // bayes.cpp:660
+                ck(gmrm_get_components(e, t, comp.data()), "gmrm_get_components");
+                if (rank == 0) {
+                    int m0_sum = 0;
+                    for (int g = 0; g < G; g++) m0_sum += m0[(size_t)t * G + g];
+                    outs[t]->write_csv(it, nthinned, &sigmag[(size_t)t * G], G, sigmae[t], m0_sum, &pi[(size_t)t * G * K], K);
+                }
+                outs[t]->write_bet((unsigned)Mt, it, nthinned, S, M, betas.data(), rank == 0);
+                outs[t]->write_cpn((unsigned)Mt, it, nthinned, S, M, comp.data(), rank == 0);
+            }
+    }
+    // ---- superset: posterior means of beta over the iterations after --burn-in, <stem>.mbet (Mt doubles)
+    if (o.burn_in > 0 && o.burn_in < o.iterations)
+        for (int t = 0; t < T; t++) {
+            const double inv = 1.0 / (double)(o.iterations - o.burn_in);
+            for (auto& v : bmean[t]) v *= inv;
+            const std::string path = (o.out_dir.empty() ? std::string() : o.out_dir + "/") + sh->phens[t].stem + ".mbet";
+            if (rank == 0) { FILE* f = fopen(path.c_str(), "wb"); if (f) fclose(f); }
+            bar->wait();
+            FILE* f = fopen(path.c_str(), "r+b");
+            if (f) { fseek(f, (long)S * 8, SEEK_SET); fwrite(bmean[t].data(), 8, M, f); fclose(f); }
+        }
+    bar->wait();
+    for (auto* p : outs) delete p;
+    gmrm_destroy(e);
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Shared sh;
+    sh.opt = host::parse_options(argc, argv, 0);
+    const host::Options& o = sh.opt;
+    sh.dims = host::read_dim_file(o.dim_file, o.truncm);
+    printf("INFO   : N = %d individuals, M = %d markers, %d trait(s), %d group(s) x %d mixtures\n", sh.dims.N, sh.dims.Mt, (int)o.phen_files.size(),
+           o.ngroups, o.nmixtures);
+    for (const auto& f : o.phen_files) sh.phens.push_back(host::read_phen_file(f, sh.dims.N, o.verbosity));
+    std::cout.flush();
+    if (o.group_index_file.empty()) {
+        printf("FATAL  : --group-index-file and --group-mixture-file are required\n");
+        return EXIT_FAILURE;
+    }
+    printf("INFO   : Reading groups from %s.\n", o.group_index_file.c_str());
+    sh.group_index = host::read_group_index_file(o.group_index_file, o.ngroups, sh.dims.Mt);
+    // virtual ranks: the run is the reference under `mpirun -n vranks`
+    int vr = o.vranks > 0 ? o.vranks : 1024 * o.gpus;
+    if (vr > sh.dims.Mt) vr = sh.dims.Mt;
+    vr -= vr % o.gpus;
+    if (vr < o.gpus) {
+        printf("FATAL  : %d markers cannot be shared by %d GPUs\n", sh.dims.Mt, o.gpus);
+        return EXIT_FAILURE;
+    }
+    sh.vranks = vr;
+    printf("INFO   : %d GPU(s), %d virtual ranks (markers in flight per step), sync rate %d\n", o.gpus, vr, o.sync_rate);
+    if (o.check_inputs) {
+        for (const auto& p : sh.phens) printf("INFO   : %s: %d observed, %d NA\n", p.path.c_str(), p.nonas, p.nas);
+        printf("INFO   : inputs parsed; --check-inputs given, no GPU work\n");
+        return 0;
+    }
+    fflush(stdout);
+    Barrier bar(o.gpus);
+    std::vector<std::thread> th;
+    for (int r = 0; r < o.gpus; r++) th.emplace_back(worker, r, &sh, &bar);
+    for (auto& t : th) t.join();
+    return 0;
+}

@@ -1,0 +1,100 @@
+"""Host side (gmrm_b200/gmrm_b200_cli): the reference's command line and file formats.
+CPU tests cover the parser and the input readers (--check-inputs does no GPU work); the GPU test runs the
+executable end to end and compares its .bet / .cpn / .csv files with the oracle following the same Philox streams."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from gmrm_b200 import synth
+
+CLI = os.path.join(ROOT, "gmrm_b200", "gmrm_b200_cli")
+
+
+def run(args, **kw):
+    return subprocess.run([CLI] + args, capture_output=True, text=True, timeout=600, **kw)
+
+
+@pytest.fixture(scope="module")
+def data(tmp_path_factory):
+    if not os.path.exists(CLI):
+        pytest.skip("gmrm_b200_cli not built")
+    tmp = tmp_path_factory.mktemp("cli")
+    d = synth.write_dataset(str(tmp), N=1003, M=300, n_traits=2, n_groups=2, na_rate=0.01, missing_rate=0.005, seed=3)
+    d["tmp"] = str(tmp)
+    return d
+
+
+def base_args(d, out):
+    p = d["paths"]
+    return ["--bed-file", p["bed"], "--dim-file", p["dim"], "--phen-files", ",".join(p["phen"]), "--group-index-file", p["gri"],
+            "--group-mixture-file", p["grm"], "--out-dir", out]
+
+
+def test_cli_echoes_options_and_counts_nas(data, oracle):
+    r = run(base_args(data, os.path.join(data["tmp"], "o1")) + ["--iterations", "3", "--seed", "5", "--check-inputs"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ardyh command line options:" in r.stdout and "--iterations 3" in r.stdout      # options.cpp:22,158-159
+    assert "Setting last 1 bits to NAs" in r.stdout                                        # phenotype.cpp:633-638 (N = 1003)
+    inp = oracle.load_inputs(data["paths"]["bed"], data["paths"]["dim"], data["paths"]["phen"], data["paths"]["gri"], data["paths"]["grm"])
+    for t, ph in enumerate(data["paths"]["phen"]):
+        assert f"{ph}: {int(inp['nonas'][t])} observed, {1003 - int(inp['nonas'][t])} NA" in r.stdout
+
+
+@pytest.mark.parametrize("args,msg", [(["--bogus", "1"], 'option "--bogus" unknown'),                       # options.cpp:152-155
+                                      (["--iterations"], "missing argument for last option"),               # options.cpp:169-172
+                                      (["--iterations", "0"], "strictly positive"),
+                                      ([], "no bed file provided")])
+def test_cli_rejects_bad_command_lines(data, args, msg):
+    r = run(args)
+    assert r.returncode == 1
+    assert msg in r.stdout
+
+
+def test_cli_needs_both_group_files(data):
+    p = data["paths"]
+    r = run(["--bed-file", p["bed"], "--dim-file", p["dim"], "--phen-files", p["phen"][0], "--group-index-file", p["gri"]])
+    assert r.returncode == 1 and "BOTH --group-index-file and --group-mixture-file" in r.stdout   # options.cpp:198-203
+
+
+def test_cli_rejects_unsorted_mixtures(data, tmp_path):
+    bad = tmp_path / "bad.grm"
+    bad.write_text("0.0 0.01 0.001 0.1\n0.0 0.001 0.01 0.1\n")
+    args = base_args(data, str(tmp_path / "o"))
+    args[args.index("--group-mixture-file") + 1] = str(bad)
+    r = run(args + ["--check-inputs"])
+    assert r.returncode == 1 and "ascending order" in r.stdout                              # options.cpp:278-281
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("vranks,thin", [(1, 1), (16, 2)])
+def test_cli_outputs_match_oracle(data, oracle, vranks, thin):
+    out = os.path.join(data["tmp"], f"out_{vranks}_{thin}")
+    iters, seed = 6, 4242
+    r = run(base_args(data, out) + ["--iterations", str(iters), "--seed", str(seed), "--vranks", str(vranks), "--output-thin-rate", str(thin),
+                                     "--burn-in", "2"])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("total proc time") == iters                                      # bayes.cpp:655
+    p = data["paths"]
+    inp = oracle.load_inputs(p["bed"], p["dim"], p["phen"], p["gri"], p["grm"])
+    res = oracle.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=inp["N"], R=vranks,
+                       iterations=iters, rng_mode=1, seed=seed)
+    saved = [i for i in range(1, iters + 1) if i % thin == 0]
+    for t in range(2):
+        stem = os.path.splitext(os.path.basename(p["phen"][t]))[0]
+        its, bet = oracle.read_bet(os.path.join(out, stem + ".bet"))
+        its_c, cpn = oracle.read_cpn(os.path.join(out, stem + ".cpn"))
+        assert list(its) == saved and list(its_c) == saved
+        for n, it in enumerate(saved):
+            assert np.array_equal(cpn[n], res["comp"][it - 1][t])
+            np.testing.assert_allclose(bet[n], res["betas"][it - 1][t], rtol=1e-8, atol=1e-13)
+        csv = oracle.read_csv(os.path.join(out, stem + ".csv"))
+        assert len(csv) == len(saved)
+        for n, it in enumerate(saved):
+            assert int(csv[n]["it"]) == it
+            np.testing.assert_allclose(csv[n]["sigmag"], res["sigmag"][it - 1][t], rtol=1e-8)
+            np.testing.assert_allclose(csv[n]["sigmae"], res["sigmae"][it - 1][t], rtol=1e-8)
+        mb = np.fromfile(os.path.join(out, stem + ".mbet"))
+        np.testing.assert_allclose(mb, np.mean([res["betas"][i][t] for i in range(2, iters)], axis=0), rtol=1e-8, atol=1e-13)
