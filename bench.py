@@ -37,6 +37,16 @@ WORKLOADS = {
 MIXTURES = (0.0, 1e-4, 1e-3, 1e-2)                           # example/test.grm
 
 
+def ncu_traffic_per_launch(vranks_per_gpu):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel launch, from the committed `ncu --set full`
+    capture of this same command (profiles/r1_step_kernel_traffic.json); None if no capture matches."""
+    p = os.path.join(ROOT, "profiles", "r1_step_kernel_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get("dram_bytes_per_launch") if d.get("vranks_per_gpu") == vranks_per_gpu else None
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -160,6 +170,19 @@ def run_ours(args):
     e.compute_marker_stats()
     e.init_chain(None)
     setup_s = time.time() - t0
+    # host -> HBM ingestion rate of gmrm_upload_bed (numpy host buffer: copy + transcode + missing lists) on a separate
+    # 2,048-marker engine: the one-time cost that the per-iteration e2e figure does not contain
+    upload_gbs = None
+    if rank == 0:
+        eu = api.Engine(N=N, Mt=2048, vranks=1, device=local)
+        eu.generate_bed(seed=2)
+        up_host = eu.download_bed()
+        t_up = time.perf_counter()
+        eu.upload_bed(up_host)
+        eu.finalize_bed()
+        upload_gbs = round(up_host.nbytes / (time.perf_counter() - t_up) / 1e9, 2)
+        eu.close()
+        del up_host
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,10 +253,10 @@ def run_ours(args):
                        "vranks_total": R, "sync_rate": args.sync_rate, "marker_steps_per_iter": steps_per_it,
                        "layout": f"base-3 quads (1 byte = 4 genotypes), {e.tiles} CTAs, {e.column_stride} B/column",
                        "l2": "inputs >> L2 (no flush needed)",
-                       "setup_s": round(setup_s, 1), "hbm_gbs_iter": it_bytes / (ms_per_step * 1e-3) / 1e9,
+                       "setup_s": round(setup_s, 1), "upload_bed_gbs": upload_gbs, "hbm_gbs_iter": it_bytes / (ms_per_step * 1e-3) / 1e9,
                        "hbm_frac_iter": it_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world)},
             "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic_per_launch(args.vranks_per_gpu), "peak_source": peak_src,
                          "dot_share_of_step": (sum(dot_ms) / len(dot_ms)) / (sum(dev_ms) / len(dev_ms)),
                          "alg_bytes_per_launch": alg_bytes_launch, "avg_launch_ms": avg_dot_ms,
                          "per_step_us": {"dot": 1e3 * sum(dot_ms) / len(dot_ms) / steps_per_it, "sample": 1e3 * sum(smp_ms) / len(smp_ms) / steps_per_it,
@@ -242,8 +265,9 @@ def run_ours(args):
                                          "allreduce": 1e3 * sum(ar_ms) / len(ar_ms) / steps_per_it, "step": 1e3 * ms_per_step / steps_per_it}},
             "e2e": {"value": M * T / e2e_s, "unit": "marker-updates/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": d2h // args.steps,
-                    "note": "per-iteration call through the C ABI + read-back of betas/components/state to host; "
-                            "genotypes are uploaded once per run, not per iteration"},
+                    "note": "per-iteration call through the C ABI (gmrm_run_iteration) + read-back of betas/components/state to host "
+                            "buffers (what the reference writes to .bet/.cpn/.csv); an iteration has no host inputs: genotypes and "
+                            "phenotypes are uploaded once per run (config.upload_bed_gbs is that path's measured rate)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "chain": {"sigmaE": float(st["sigmae"][0]), "sigmaG_sum": float(st["sigmag"][0].sum()),
@@ -348,7 +372,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ukb", choices=sorted(WORKLOADS))
     ap.add_argument("--markers", type=int, default=0, help="override M (debug)")
-    ap.add_argument("--vranks-per-gpu", type=int, default=1024)
+    ap.add_argument("--vranks-per-gpu", type=int, default=2048)
     ap.add_argument("--sync-rate", type=int, default=1)
     ap.add_argument("--cpu-markers", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -530,6 +530,24 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
 
 constexpr int kStepWarps = 16, kStepThreads = kStepWarps * 32;     // 128 registers per thread
 
+// L2 prefetch of this warp's first two batches of a pass (rows [row0, row0+nr) of their 16 columns each): issued
+// before the pass's tables are built (and at kernel start for pass 0), it takes the HBM round trip of the first
+// loads of a pass off the critical path.
+__device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0, int nr) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nb = (p.V + kBatch - 1) / kBatch;
+    if (warp >= kStepWarps) return;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int b = warp + k * kStepWarps, v = b * kBatch + (lane & 15);
+        if (b >= nb || v >= p.V) continue;
+        const uint8_t* a = p.bed + (int64_t)max(p.cols[v], 0) * p.col_stride + (int64_t)row0 * kRowBytes;
+        const int bytes = nr * kRowBytes, o1 = (lane >> 4) * 128, o2 = (lane >> 4) ? bytes - 1 : 256;
+        if (o1 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o1));
+        if (o2 < bytes && nr > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o2));
+    }
+}
+
 // ---- (c) stream the V columns through the tables of NR rows
 template <int NR, int T>
 __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part) {
@@ -656,6 +674,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     __syncthreads();
     const int nr = pr.total;
+    if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
     if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area);
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
@@ -677,6 +696,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part); break;
         default: break;
         }
+        if (p.pf && pass + 1 < npass && pr.count[pass + 1] > 0) prefetch_pass_head(p, pr.start[pass + 1], pr.count[pass + 1]);
     }
     __syncthreads();
     for (int i = tid; i < p.V * T; i += NT) {
