@@ -126,6 +126,7 @@ struct gmrm_engine {
     struct MissChunk { int begin = 0, count = 0; std::vector<uint32_t> cnt; DevBuf<uint32_t>* idx = nullptr; uint64_t total = 0; };
     std::vector<MissChunk> miss_chunks;
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
+    bool force_flush = false;        // GMRM_FORCE_FLUSH=1: update-only launch after every step (timing aid)
     int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
     int step_warps = 16;             // consumer warps of the step kernel (GMRM_STEP_WARPS=20: measured alternative)
     DevBuf<PubEntry> pub;
@@ -191,8 +192,9 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
     if (const char* v = getenv("GMRM_STEP_WARPS")) e->step_warps = atoi(v) == 20 ? 20 : 16;
     if (const char* v = getenv("GMRM_STEP_PF")) e->step_pf = atoi(v);
+    if (const char* v = getenv("GMRM_FORCE_FLUSH")) e->force_flush = atoi(v) != 0;
     if (getenv("GMRM_STEP_PROF")) {
-        if (e->prof.alloc(8) != 0 || e->prof.zero(nullptr) != 0) { delete e; return GMRM_ECUDA; }
+        if (e->prof.alloc(64) != 0 || e->prof.zero(nullptr) != 0) { delete e; return GMRM_ECUDA; }
     }
     step_plan(e->L, e->Vl, c->T, &e->step_tc, &e->step_rpp);
     if (e->step_tc < 1 || e->step_rpp < 1) {
@@ -248,10 +250,12 @@ void gmrm_destroy(gmrm_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaStreamSynchronize(e->stream);
     if (e->prof.p) {
-        unsigned long long h[8];
-        if (cudaMemcpy(h, e->prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[3] && h[6])
-            fprintf(stderr, "step prof (cycles per batch): consumer wait-issue %.0f wait-data %.0f compute %.0f (%llu batches); producer wait-empty %.0f issue %.0f (%llu batches)\n",
-                    (double)h[0] / h[3], (double)h[1] / h[3], (double)h[2] / h[3], h[3], (double)h[4] / h[6], (double)h[5] / h[6], h[6]);
+        unsigned long long h[64];
+        if (cudaMemcpy(h, e->prof.p, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[7]) {
+            fprintf(stderr, "step prof, mean cycles per launch over %llu launches of 2 CTAs:", h[7]);
+            for (int i = 8; i < 64; i++) if (h[i]) fprintf(stderr, " [%d] %.0f", i, (double)h[i] / h[7]);
+            fprintf(stderr, "\n");
+        }
     }
     delete e;
 }
@@ -701,6 +705,9 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         for (size_t i = old; i < e->dot_ev.size(); i++) CU(cudaEventCreate(&e->dot_ev[i]));
     }
 
+    if (e->prof.p)
+        if (const char* pv = getenv("GMRM_STEP_PROF"))
+            if (atoi(pv) == it) CU(cudaMemsetAsync(e->prof.p, 0, 64 * 8, s));   // count from iteration GMRM_STEP_PROF on
     int64_t launches = 0;
     CU(cudaEventRecord(e->ev[0], s));
     // ---- prologue (bayes.cpp:347-368)
@@ -732,7 +739,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
         pcols = cols;
         const bool exchange = multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
-        if (exchange || st == Mm - 1) {
+        if (exchange || st == Mm - 1 || e->force_flush) {
             if ((rc = launch_step_all(e, nullptr, 0, pcols, Vl, nullptr, &nl))) return rc;
             pcols = nullptr;
         }

@@ -344,7 +344,10 @@ __host__ __device__ inline int step_area_bytes(int V, int T, int rows_per_pass, 
 // of the previous step, in virtual-rank order, restricted to this CTA's rows.  All NT threads of the CTA work.
 template <int T, int NT>
 __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage* stage, PubInfo* info, uint32_t* lut,
-                              uint32_t* bitmap, int* wcnt, uint8_t* bytes, int bytes_cap) {
+                              uint32_t* bitmap, int* wcnt, uint8_t* bytes, int bytes_cap, bool profme) {
+    long long tk = profme ? clock64() : 0;
+    int nk = 40;
+#define GMRM_ATICK() if (profme && nk < 60) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     constexpr int NWALL = NT / 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nr = pr.total, nq = nr * kRowBytes;       // quads of my rows
@@ -377,36 +380,58 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
 #pragma unroll
                 for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * (int64_t)gq[qq] + k] : 0.0; e0[qq][k] = e[qq][k]; }
             }
+            GMRM_ATICK()   // [40] lut + eps/mask loads
             bool touched = false;
-            for (int v_lo = 0; v_lo < p.pV; v_lo += NT) {
-                // ordered compaction of the window's published entries (rank order is preserved)
-                const int v = v_lo + tid;
-                PubEntry pe{0.0, 0.0};
-                if (v < p.pV) pe = p.pub[(int64_t)v * p.Ttot + tt];
-                const bool on = pe.lam != 0.0;
-                const uint32_t bal = __ballot_sync(0xffffffffu, on);
+            // ordered compaction of the published entries, 4 windows of NT virtual ranks at a time: all their pub
+            // loads are in flight together and one scan orders them (rank order is preserved)
+            constexpr int kWin = 4;
+            for (int v_lo = 0; v_lo < p.pV; v_lo += kWin * NT) {
+                PubEntry pe[kWin];
+                int pc[kWin];                                // column of each entry, fetched with it (same round trip)
+                uint32_t bal[kWin];
+#pragma unroll
+                for (int w = 0; w < kWin; w++) {
+                    const int v = v_lo + w * NT + tid;
+                    pe[w] = PubEntry{0.0, 0.0};
+                    pc[w] = 0;
+                    if (v < p.pV) { pe[w] = p.pub[(int64_t)v * p.Ttot + tt]; pc[w] = p.pcols[v]; }
+                }
                 __syncthreads();
-                if (lane == 0) wcnt[warp] = __popc(bal);
+#pragma unroll
+                for (int w = 0; w < kWin; w++) {
+                    bal[w] = __ballot_sync(0xffffffffu, pe[w].lam != 0.0);
+                    if (lane == 0) wcnt[w * NWALL + warp] = __popc(bal[w]);
+                }
                 __syncthreads();
-                int ord = __popc(bal & ((1u << lane) - 1u)), total = 0;
-                for (int w = 0; w < NWALL; w++) { const int c = wcnt[w]; if (w < warp) ord += c; total += c; }
+                int ord[kWin], total = 0;
+#pragma unroll
+                for (int w = 0; w < kWin; w++) {
+                    int before = 0, all = 0;
+                    for (int x = 0; x < NWALL; x++) { const int c = wcnt[w * NWALL + x]; if (x < warp) before += c; all += c; }
+                    ord[w] = total + before + __popc(bal[w] & ((1u << lane) - 1u));
+                    total += all;
+                }
+                GMRM_ATICK()   // [41] pub loads + scan
                 for (int r0 = 0; r0 < total; r0 += cap) {
                     const int n = min(cap, total - r0);
                     __syncthreads();
-                    if (on && ord >= r0 && ord < r0 + n) {
-                        PubStage& s = stage[ord - r0];
-                        const double mdb = -pe.mave;               // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
-                        s.v[0] = (mdb * 1.0 + 0.0) * pe.lam;
-                        s.v[1] = (mdb * 1.0 + 1.0) * pe.lam;
-                        s.v[2] = (mdb * 1.0 + 2.0) * pe.lam;
-                        s.v[3] = 0.0;
-                        const int col = p.pcols[v];
-                        info[ord - r0].col = col;
-                        info[ord - r0].nmiss = p.miss_off[col + 1] - p.miss_off[col];
+#pragma unroll
+                    for (int w = 0; w < kWin; w++) {
+                        if (pe[w].lam != 0.0 && ord[w] >= r0 && ord[w] < r0 + n) {
+                            PubStage& s = stage[ord[w] - r0];
+                            const double mdb = -pe[w].mave;            // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
+                            s.v[0] = (mdb * 1.0 + 0.0) * pe[w].lam;
+                            s.v[1] = (mdb * 1.0 + 1.0) * pe[w].lam;
+                            s.v[2] = (mdb * 1.0 + 2.0) * pe[w].lam;
+                            s.v[3] = 0.0;
+                            info[ord[w] - r0].col = pc[w];       // nmiss is filled in with the column bytes below
+                        }
                     }
                     __syncthreads();
                     touched = true;
                     if (q0 == 0 || nq > 2 * NT) {            // (re)stage: once per round unless the rows need several quad chunks
+                        uint32_t mo0 = 0, mo1 = 0;           // missing-list bounds of entry `tid`, in flight with the bytes
+                        if (tid < n) { mo0 = p.miss_off[info[tid].col]; mo1 = p.miss_off[info[tid].col + 1]; }
                         const int npiece = n * nr * 4;       // 16-byte pieces: entry x local row x 4
                         for (int i0 = tid; i0 < npiece; i0 += 8 * NT) {
                             uint4 v[8];
@@ -425,8 +450,10 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                                 if (i < npiece) *reinterpret_cast<uint4*>(bytes + (size_t)i * 16) = v[j];   // == entry*nq + lr*64 + part*16
                             }
                         }
+                        if (tid < n) info[tid].nmiss = mo1 - mo0;
                         __syncthreads();
                     }
+                    GMRM_ATICK()   // [42] stage fill + column bytes
                     for (int g0 = 0; g0 < n; g0 += 8) {
                         uint32_t by[8][2];
 #pragma unroll
@@ -477,6 +504,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                     }
                 }
             }
+            GMRM_ATICK()   // [43] apply
             if (touched) {
 #pragma unroll
                 for (int qq = 0; qq < 2; qq++) {
@@ -528,7 +556,9 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
     }
 }
 
-constexpr int kStepWarps = 16, kStepThreads = kStepWarps * 32;     // 128 registers per thread
+constexpr int kStepWarps = GMRM_STEP_WARPS, kStepThreads = kStepWarps * 32;
+constexpr int kPairs = kBatch / 2;
+constexpr int kDepth = GMRM_STEP_DEPTH;      // batches of register prefetch
 
 // L2 prefetch of this warp's first two batches of a pass (rows [row0, row0+nr) of their 16 columns each): issued
 // before the pass's tables are built (and at kernel start for pass 0), it takes the HBM round trip of the first
@@ -539,10 +569,11 @@ __device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0
     if (warp >= kStepWarps) return;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const int b = warp + k * kStepWarps, v = b * kBatch + (lane & 15);
+        const int b = warp + k * kStepWarps, v = b * kBatch + (lane & (kBatch - 1)), g = lane / kBatch;
         if (b >= nb || v >= p.V) continue;
         const uint8_t* a = p.bed + (int64_t)max(p.cols[v], 0) * p.col_stride + (int64_t)row0 * kRowBytes;
-        const int bytes = nr * kRowBytes, o1 = (lane >> 4) * 128, o2 = (lane >> 4) ? bytes - 1 : 256;
+        const int bytes = nr * kRowBytes;
+        const int o1 = (32 / kBatch == 4 && g == 3) ? bytes - 1 : g * 128, o2 = 32 / kBatch == 4 ? 1 << 20 : (g ? bytes - 1 : 256);
         if (o1 < bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o1));
         if (o2 < bytes && nr > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + o2));
     }
@@ -560,82 +591,125 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
     const uint8_t* base = p.bed + (int64_t)row0 * kRowBytes + l16 * 4;
 
     auto loadcols = [&](int bb) -> int {
-        const int v = bb * kBatch + l16;
+        const int v = bb * kBatch + (l16 & (kBatch - 1));
         return (bb < nb && v < p.V) ? max(p.cols[v], 0) : 0;
     };
-    uint32_t Wn[8][NR];
-    auto issue = [&](int c) {
+    // register prefetch: Wn holds the next batch, Wn2 (GMRM_STEP_DEPTH == 2) the one after
+    uint32_t Wn[kPairs][NR], Wn2[kDepth == 2 ? kPairs : 1][NR];
+    auto issue = [&](int c, uint32_t (&dst)[kPairs][NR]) {
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
+        for (int i = 0; i < kPairs; i++) {
             const int col = __shfl_sync(0xffffffffu, c, 2 * i + h);
             const uint8_t* ptr = base + (int64_t)col * p.col_stride;
 #pragma unroll
-            for (int rr = 0; rr < NR; rr++) Wn[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
+            for (int rr = 0; rr < NR; rr++) dst[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
         }
     };
-    issue(loadcols(b));
-    int cn = loadcols(b + kStepWarps);
+    issue(loadcols(b), Wn);
+    if constexpr (kDepth == 2) issue(loadcols(b + kStepWarps), reinterpret_cast<uint32_t(&)[kPairs][NR]>(Wn2));
+    int cn = loadcols(b + kDepth * kStepWarps);
     // L2 prefetch kPfAhead batches ahead of the register loads (which run one batch ahead): the 16 warps then keep
     // ~192 KB per SM in flight towards HBM instead of 64 KB
     constexpr int kPfAhead = 4;
     int pcol = p.pf ? loadcols(b + kPfAhead * kStepWarps) : 0;
     const uint8_t* pf_base = p.bed + (int64_t)row0 * kRowBytes;
-    const int pf_off_a = (lane >> 4) * 128, pf_off_b = (lane >> 4) ? NR * kRowBytes - 1 : 256;
+    // lane -> (marker of the batch, 128-byte line of its chunk); the last lane group also touches the chunk's last byte
+    constexpr int kLG = 32 / kBatch;
+    const int pf_g = lane / kBatch;
+    const int pf_off_a = (kLG == 4 && pf_g == 3) ? NR * kRowBytes - 1 : pf_g * 128, pf_off_b = kLG == 4 ? 1 << 20 : (pf_g ? NR * kRowBytes - 1 : 256);
     const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
-    const int own = ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1);   // pair whose total this lane ends up with
+    // pair whose total this lane ends up with
+    const int own = kPairs == 8 ? ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1)
+                  : kPairs == 4 ? ((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1) : ((l16 >> 3) & 1);
 
     for (; b < nb; b += kStepWarps) {
-        uint32_t W[8][NR];
+        uint32_t W[kPairs][NR];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < kPairs; i++)
 #pragma unroll
-            for (int rr = 0; rr < NR; rr++) W[i][rr] = Wn[i][rr];
-        if (b + kStepWarps < nb) {
-            issue(cn);
-            cn = loadcols(b + 2 * kStepWarps);
-        }
+            for (int rr = 0; rr < NR; rr++) {
+                W[i][rr] = Wn[i][rr];
+                if constexpr (kDepth == 2) Wn[i][rr] = Wn2[i][rr];
+            }
+        const bool more = b + kDepth * kStepWarps < nb;          // warp-uniform
+        const int cnow = cn;
+        if (more) cn = loadcols(b + (kDepth + 1) * kStepWarps);
+        // the loads of the next batch are spread over the look-up groups below (a burst of 8*NR loads per warp at the
+        // top of a batch filled the load/store queue in front of the other warps' look-ups)
+        auto issue_pair = [&](int i) {
+            const int col = __shfl_sync(0xffffffffu, cnow, 2 * i + h);
+            if (more) {
+                const uint8_t* ptr = base + (int64_t)col * p.col_stride;
+#pragma unroll
+                for (int rr = 0; rr < NR; rr++) {
+                    if constexpr (kDepth == 2) Wn2[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
+                    else Wn[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
+                }
+            }
+        };
         if (p.pf && b + kPfAhead * kStepWarps < nb) {
             const uint8_t* a = pf_base + (int64_t)pcol * p.col_stride;
             if (pf_off_a < NR * kRowBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_a));
             if (pf_off_b < NR * kRowBytes && NR > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_b));
             pcol = loadcols(b + (kPfAhead + 1) * kStepWarps);
         }
-        double acc[8][T];
+        double acc[kPairs][T];
 #pragma unroll
-        for (int i = 0; i < 8; i++)
+        for (int i = 0; i < kPairs; i++)
 #pragma unroll
             for (int t = 0; t < T; t++) acc[i][t] = 0.0;
 
 #define GMRM_LOOKUP(RR, K)                                                    \
-    _Pragma("unroll") for (int i = 0; i < 8; i++)                             \
-        lookup_traits<RR * T, K, T>(acc[i], tab_addr<K>(W[i][RR], low));
+    _Pragma("unroll") for (int i = 0; i < kPairs; i++)                             \
+        lookup_traits<RR * T, K, T>(acc[i], tab_addr<K>(W[i][RR], low));      \
+    {                                                                         \
+        constexpr int PPG = (kPairs + NR * 4 - 1) / (NR * 4), G = RR * 4 + K; \
+        _Pragma("unroll") for (int i = G * PPG; i < (G + 1) * PPG; i++)       \
+            if (i < kPairs) issue_pair(i);                                    \
+    }
 #define GMRM_ROW(RR)                                                          \
     if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_LOOKUP(RR, 1) GMRM_LOOKUP(RR, 2) GMRM_LOOKUP(RR, 3) }
         GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3) GMRM_ROW(4)
 #undef GMRM_ROW
 #undef GMRM_LOOKUP
 
-        // 16-lane transposed butterfly: 8 pair accumulators -> the total of pair `own` (fixed order: reproducible)
+        // 16-lane transposed butterfly: the pair accumulators -> the total of pair `own` (fixed order: reproducible)
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            double b4[4], b2[2], b1;
+            double b1;
+            if constexpr (kPairs == 8) {
+                double b4[4], b2[2];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double keep = hi8 ? acc[4 + j][t] : acc[j][t], send = hi8 ? acc[j][t] : acc[4 + j][t];
-                b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
+                for (int j = 0; j < 4; j++) {
+                    const double keep = hi8 ? acc[4 + j][t] : acc[j][t], send = hi8 ? acc[j][t] : acc[4 + j][t];
+                    b4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const double keep = hi4 ? b4[2 + j] : b4[j], send = hi4 ? b4[j] : b4[2 + j];
-                b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            {
+                for (int j = 0; j < 2; j++) {
+                    const double keep = hi4 ? b4[2 + j] : b4[j], send = hi4 ? b4[j] : b4[2 + j];
+                    b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
                 const double keep = hi2 ? b2[1] : b2[0], send = hi2 ? b2[0] : b2[1];
                 b1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+            } else if constexpr (kPairs == 4) {
+                double b2[2];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const double keep = hi8 ? acc[2 + j][t] : acc[j][t], send = hi8 ? acc[j][t] : acc[2 + j][t];
+                    b2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                const double keep = hi4 ? b2[1] : b2[0], send = hi4 ? b2[0] : b2[1];
+                b1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+            } else {
+                const double keep = hi8 ? acc[1][t] : acc[0][t], send = hi8 ? acc[0][t] : acc[1][t];
+                b1 = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 4);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
             const int v = b * kBatch + 2 * own + h;
-            if ((l16 & 1) == 0 && v < p.V) part[v * T + t] += b1;
+            if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V) part[v * T + t] += b1;
         }
     }
 }
@@ -661,7 +735,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     PassRows& pr = *reinterpret_cast<PassRows*>(lut + 82);
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(&pr + 1);
     double* red = reinterpret_cast<double*>(bitmap + ((npass * p.rows_per_pass * 8 + 1) & ~1));
-    int* wcnt = reinterpret_cast<int*>(red + 32);
+    int* wcnt = reinterpret_cast<int*>(red + 32);                  // [4 windows][warps]
 
     if (tid == 0) {
         int tot = 0;
@@ -674,10 +748,15 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     __syncthreads();
     const int nr = pr.total;
+    const bool profme = p.prof && tid == 0 && (cta == 0 || cta == nsm / 2);
+    long long tk = profme ? clock64() : 0;
+    int nk = 8;
+#define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
-    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area);
+    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
+    GMRM_TICK()                                           // [8] prologue + update phase
     if (p.V == 0) return;
 
     double es[T];
@@ -685,9 +764,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     for (int t = 0; t < T; t++) es[t] = 0.0;
     for (int pass = 0; pass < npass; pass++) {
         const int r_lo = pr.start[pass], nrp = pr.count[pass];
-        if (pass) __syncthreads();                        // everyone is done with the previous tables
         build_tables<T, NT>(p, r_lo, nrp, es);
         __syncthreads();
+        GMRM_TICK()                                       // [9 + 3*pass] sync + build
         switch (nrp) {
         case 1: stream_rows<1, T>(p, r_lo, part); break;
         case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part); break;
@@ -696,9 +775,13 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part); break;
         default: break;
         }
+        GMRM_TICK()                                       // [10 + 3*pass] this warp's streaming
         if (p.pf && pass + 1 < npass && pr.count[pass + 1] > 0) prefetch_pass_head(p, pr.start[pass + 1], pr.count[pass + 1]);
+        if (pass + 1 < npass) __syncthreads();            // everyone is done with these tables
+        GMRM_TICK()                                       // [11 + 3*pass] waiting for the slowest warp
     }
     __syncthreads();
+    GMRM_TICK()
     for (int i = tid; i < p.V * T; i += NT) {
         const int v = i / T, t = i - v * T;
         p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
@@ -708,6 +791,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         const double tot = block_sum_fixed(es[t], red);
         if (tid == 0) p.spart[(int64_t)(p.t0 + t) * nsm + cta] = tot;
     }
+    GMRM_TICK()                                           // epilogue: partial / spart writes
+    if (profme) atomicAdd(&p.prof[7], 1ull);
+#undef GMRM_TICK
 }
 
 // =====================================================================================
@@ -775,31 +861,65 @@ __global__ void group_consts_kernel(int T, int G, int K, int N, const double* __
     o[2 * K] = 0.0; o[3 * K] = 0.0;
 }
 
+// Latency-ordered: the kernel is one dependent chain per warp, so independent loads are issued together --
+// round 1: column index, the marker's partial sums and the residual sums (none depends on the column);
+// round 2 (needs the column): missing-list bounds, group, mave, msig, beta;  round 3: sigmaG, sampler constants.
 __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
     const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v >= p.V) return;
     const int col = p.cols[v];
+    // ---- round 1: sum a*eps partials and sum eps, trait by trait (fixed order), while `col` is in flight
+    double my_coded = 0.0, my_sall = 0.0;
+    for (int t = 0; t < p.T; t++) {
+        const double* part = p.partial + ((int64_t)v * p.T + t) * p.nsm;
+        double x[8], y[8], s = 0.0, sa = 0.0;
+        for (int i0 = lane; i0 < p.nsm; i0 += 32 * 8) {      // 8 independent loads per round, fixed summation order
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                x[j] = i0 + 32 * j < p.nsm ? part[i0 + 32 * j] : 0.0;
+                y[j] = i0 + 32 * j < p.nsm ? p.spart[(int64_t)t * p.nsm + i0 + 32 * j] : 0.0;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) s += x[j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) sa += y[j];
+        }
+        const double coded = warp_sum_fixed(s), sall = warp_sum_fixed(sa);
+        if (lane == t) { my_coded = coded; my_sall = sall; }
+    }
     if (col < 0) {
         if (lane < p.T) { p.pub[(int64_t)v * p.T + lane].lam = 0.0; p.pub[(int64_t)v * p.T + lane].mave = 0.0; }
         return;
     }
-    double my_dpa = 0.0, my_dpb = 0.0;
-    for (int t = 0; t < p.T; t++) {
-        const DotPieces d = finish_dot(p, v, col, t, lane);
-        if (lane == t) { my_dpa = d.dpa; my_dpb = d.dpb; }
-    }
+    // ---- round 2
+    const uint32_t m0 = p.miss_off[col], m1 = p.miss_off[col + 1];
+    const int grp = p.group[col];
+    const int tl = lane < p.T ? lane : 0;
+    const int64_t mi = (int64_t)tl * p.Mloc + col;
+    const double mave = p.mave[mi], msig = p.msig[mi], beta_old = p.betas[mi];
+    const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + tl;
+    const double rep_u = p.rep_u ? p.rep_u[ri] : 0.0;
+    const int nonas = p.nonas[tl];
+    // ---- round 3
+    const double sigg = p.sigmag[tl * p.G + grp];
+    const double* gc = p.gc + ((int64_t)tl * p.G + grp) * 4 * p.K;
+    double my_smiss = 0.0;
+    if (m1 > m0)                                              // warp-uniform: sum of eps over the missing genotypes
+        for (int t = 0; t < p.T; t++) {
+            double sm = 0.0;
+            for (uint32_t i = m0 + lane; i < m1; i += 32) sm += p.eps[(int64_t)t * p.npad + p.miss_idx[i]];
+            const double smiss = warp_sum_fixed(sm);
+            if (lane == t) my_smiss = smiss;
+        }
     if (lane >= p.T) return;
     const int t = lane;
-    const int grp = p.group[col];
-    const int64_t mi = (int64_t)t * p.Mloc + col;
-    const double mave = p.mave[mi], msig = p.msig[mi];
+    const double my_dpa = my_coded;                           // a = 0 at missing (lut_a): stored as dosage 0
+    const double my_dpb = my_sall - my_smiss;                 // b = 0 at missing (lut_b)
     const double dot_raw = msig * (my_dpa - mave * my_dpb);                // bayes.cpp:766
     const uint32_t mglo = (uint32_t)(p.marker_begin + col);
     double u;
-    const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + t;
-    const double sigg = p.sigmag[t * p.G + grp];
     if (p.rep_u) {
-        u = p.rep_u[ri];
+        u = rep_u;
         if (sigg != 0.0 && !(u == u)) atomicExch(p.err, 1);               // reference drew nothing here
     } else {
         u = draw_uniform(p.seed, STREAM_SAMPLER_U, (uint32_t)p.it, mglo, (uint32_t)t);
@@ -813,7 +933,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
         }
         return draw_normal(p.seed, STREAM_SAMPLER_N, (uint32_t)p.it, mglo, (uint32_t)t);
     };
-    const MarkerDraw d = sample_marker_pre(dot_raw, p.betas[mi], sigg, p.gc + ((int64_t)t * p.G + grp) * 4 * p.K, p.K, p.nonas[t], u, zdraw);
+    const MarkerDraw d = sample_marker_pre(dot_raw, beta_old, sigg, gc, p.K, nonas, u, zdraw);
     p.betas[mi] = d.beta_new;
     if (d.comp >= 0) {
         p.comp[mi] = d.comp;                                               // bayes.cpp:462
@@ -999,7 +1119,7 @@ int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
     if (step_npass(L, rows_per_pass) > kMaxPasses) return -1;
     const int nrmax = step_npass(L, rows_per_pass) * rows_per_pass;   // bound on the rows one CTA owns
     const int64_t bytes = (int64_t)kTabBase + (int64_t)step_area_bytes(V, T, rows_per_pass, step_npass(L, rows_per_pass)) + (int64_t)kPubCap * 32 +
-                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 32 * 4;
+                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 4 * 32 * 4;
     return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 
@@ -1030,7 +1150,10 @@ static int step_launch_t(const Layout& L, const StepParams& p, cudaStream_t s) {
         if (cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
         attr = true;
     }
-    step_kernel<T><<<L.nsm, kStepThreads, smem, s>>>(p);
+    // every launch asks for the full 227 KB, update-only ones included: a different dynamic size would make the
+    // driver re-partition L1/shared memory between consecutive launches of the marker loop
+    (void)smem;
+    step_kernel<T><<<L.nsm, kStepThreads, kMaxDynSmem, s>>>(p);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 // T = traits of this launch (1..4); p.rows_per_pass * T <= kMaxSlots

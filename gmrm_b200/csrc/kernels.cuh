@@ -10,7 +10,17 @@
 
 namespace gmrm {
 
-constexpr int kBatch = 16;             // markers per warp batch (8 pairs: one marker per half-warp)
+// Step-kernel shape: (32 warps, batches of 8 markers, 64 registers) or (16 warps, batches of 16, 128 registers)
+#ifndef GMRM_STEP_WARPS
+#define GMRM_STEP_WARPS 16
+#endif
+#ifndef GMRM_STEP_BATCH
+#define GMRM_STEP_BATCH 8
+#endif
+#ifndef GMRM_STEP_DEPTH
+#define GMRM_STEP_DEPTH 1
+#endif
+constexpr int kBatch = GMRM_STEP_BATCH;   // markers per warp batch (one marker per half-warp: kBatch/2 pairs)
 constexpr int kPubCap = 128;           // published updates staged per round of the update phase
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
