@@ -151,6 +151,13 @@ def run_ours(args):
     t0 = time.time()
     e.generate_bed(seed=1, maf_lo=0.05, maf_hi=0.5, missing_rate=0.0)
     e.finalize_bed()
+    if world > 1 and args.sync_rate == 1:      # list exchange: the shards read each other's columns over NVLink
+
+        def gather(x):
+            out = [None] * world
+            dist.all_gather_object(out, x)
+            return out
+        e.exchange_buffers(gather)
     # phenotype: simulated on rank 0 from its shard, shared with the other ranks (epsilon is replicated)
     obj = [None]
     if rank == 0:

@@ -223,6 +223,23 @@ class Engine:
     def set_timing_detail(self, on: bool):
         _check(lib().gmrm_set_timing_detail(self._h, int(on)))
 
+    def export_buffers(self) -> bytes:
+        buf = (C.c_uint8 * 192)()
+        _check(lib().gmrm_comm_export_buffers(self._h, buf))
+        return bytes(buf)
+
+    def import_buffers(self, rank: int, handles: bytes):
+        buf = (C.c_uint8 * 192).from_buffer_copy(handles)
+        _check(lib().gmrm_comm_import_buffers(self._h, int(rank), buf))
+
+    def exchange_buffers(self, all_gather_object):
+        """List exchange set-up for one process per GPU: `all_gather_object(x)` must return the list of every rank's x
+        (e.g. a torch.distributed.all_gather_object wrapper).  Call after finalize_bed()."""
+        handles = all_gather_object(self.export_buffers())
+        for r, h in enumerate(handles):
+            if r != self.cfg.world_rank:
+                self.import_buffers(r, h)
+
     def comm_init(self, uid: bytes):
         buf = (C.c_uint8 * 128).from_buffer_copy(uid)
         _check(lib().gmrm_comm_init(self._h, buf))

@@ -51,6 +51,7 @@ struct Nccl {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     bool load() {
         if (h) return true;
@@ -63,8 +64,9 @@ struct Nccl {
         CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
         Broadcast = (decltype(Broadcast))dlsym(h, "ncclBroadcast");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
         GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast;
+        return GetUniqueId && CommInitRank && CommDestroy && AllReduce && Broadcast && AllGather;
     }
 } g_nccl;
 constexpr int kNcclInt32 = 2, kNcclFloat64 = 8, kNcclSum = 0;   // ncclDataType_t / ncclRedOp_t values (nccl.h)
@@ -125,6 +127,16 @@ struct gmrm_engine {
     // assembled into one CSR by gmrm_finalize_bed
     struct MissChunk { int begin = 0, count = 0; std::vector<uint32_t> cnt; DevBuf<uint32_t>* idx = nullptr; uint64_t total = 0; };
     std::vector<MissChunk> miss_chunks;
+    // exchange by published lists (world_size > 1, sync_rate == 1): every GPU applies every GPU's published updates
+    // itself, reading the other shards' columns over NVLink peer memory; the lists travel by one small all-gather
+    bool list_exchange = false;
+    const uint8_t* peer_bed[kMaxGpus] = {};
+    const uint32_t* peer_moff[kMaxGpus] = {};
+    const uint32_t* peer_midx[kMaxGpus] = {};
+    void* ipc_opened[kMaxGpus][3] = {};
+    int peers_set = 0;
+    DevBuf<int32_t> steptab_all;     // [world][Mm][Vl] columns (local to each GPU's shard) of every GPU's steps
+    DevBuf<PubEntry> pub_all;        // [world][Vl][T]; this GPU's sampler writes its own block
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
     bool force_flush = false;        // GMRM_FORCE_FLUSH=1: update-only launch after every step (timing aid)
     int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
@@ -145,6 +157,7 @@ struct gmrm_engine {
 
     ~gmrm_engine() {
         if (comm && g_nccl.CommDestroy) g_nccl.CommDestroy(comm);
+        for (auto& g : ipc_opened) for (void* q : g) if (q) cudaIpcCloseMemHandle(q);
         for (auto& c : miss_chunks) delete c.idx;
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : dot_ev) cudaEventDestroy(e);
@@ -228,7 +241,13 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T)); A(e->gc.alloc((size_t)T * G * 4 * K));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
     A(e->miss_off.alloc((size_t)e->Mloc + 1)); A(e->miss_idx.alloc(1));
-    if (c->world_size > 1) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
+    e->list_exchange = c->world_size > 1 && c->sync_rate == 1;
+    if (c->world_size > kMaxGpus) { delete e; return fail(GMRM_EINVAL, "world_size %d > %d", c->world_size, kMaxGpus); }
+    if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
+    if (e->list_exchange) {
+        A(e->steptab_all.alloc((size_t)c->world_size * e->Mm * e->Vl));
+        A(e->pub_all.alloc((size_t)c->world_size * e->Vl * T));
+    }
     if (rc != 0) { delete e; return rc; }
     // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
     for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
@@ -482,9 +501,13 @@ int gmrm_get_marker_stats(gmrm_engine* e, int32_t t, double* mave, double* msig)
 }
 
 // ------------------------------------------------------------------------------ shared launch glue
-// One marker-step (kernels.cu K1) for all traits: pending updates of the previous step (pcols/pV/pub, may be
-// none), tables, and the dot products of the V columns `cols` (V == 0: update only).
-static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const int32_t* pcols, int pV, double* partial, int* nlaunch) {
+// One marker-step (kernels.cu K1) for all traits: pending updates of the previous step (none when pend_step < 0),
+// tables, and the dot products of the V columns `cols` (V == 0: update only).  `pend_cols` (non-null) overrides
+// the pending list with a single local one of pV entries whose PubEntry block is e->pub (test hook).
+struct Pending { int step = -1; const int32_t* cols = nullptr; int pV = 0; };
+static PubEntry* own_pub(gmrm_engine* e) { return e->list_exchange ? e->pub_all.p + (size_t)e->cfg.world_rank * e->Vl * e->cfg.T : e->pub.p; }
+
+static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch) {
     const int T = e->cfg.T;
     int tc = e->step_tc, rpp = e->step_rpp;
     if (V > e->Vl || V == 0) {                                  // test hook with its own marker count / update-only launch
@@ -496,9 +519,21 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const int
         p.bed = e->bed.p; p.col_stride = e->L.col_stride; p.nrows = e->L.nrows; p.cols = cols; p.V = V;
         p.eps = e->eps.p; p.npad = e->L.npad; p.Ttot = T; p.t0 = t0; p.rows_per_pass = rpp; p.npass = step_npass(e->L, rpp);
         p.partial = partial; p.spart = e->spart.p;
-        p.pcols = pcols; p.pV = pV; p.pub = e->pub.p; p.mask4 = e->mask4.p;
-        p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
-        p.delta = e->cfg.world_size > 1 ? e->delta.p : nullptr;
+        p.mask4 = e->mask4.p;
+        if (pend.cols) {                                        // one local list
+            p.pG = 1; p.pV = pend.pV; p.pub = e->pub.p;
+            p.pcols[0] = pend.cols; p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
+        } else if (pend.step >= 0 && e->list_exchange) {        // the lists of all GPUs for step pend.step
+            p.pG = e->cfg.world_size; p.pV = e->Vl; p.pub = e->pub_all.p;
+            for (int g = 0; g < p.pG; g++) {
+                p.pcols[g] = e->steptab_all.p + ((size_t)g * e->Mm + pend.step) * e->Vl;
+                p.pbed[g] = e->peer_bed[g]; p.pmiss_off[g] = e->peer_moff[g]; p.pmiss_idx[g] = e->peer_midx[g];
+            }
+        } else if (pend.step >= 0) {                            // this GPU's own list
+            p.pG = 1; p.pV = e->Vl; p.pub = e->pub.p;
+            p.pcols[0] = e->steptab.p + (size_t)pend.step * e->Vl; p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
+        }
+        p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
         p.err = e->err.p;
         p.prof = e->prof.p;
         p.pf = e->step_pf;
@@ -516,7 +551,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
-    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.err = e->err.p; p.npublished = e->npub.p;
+    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = own_pub(e); p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }
 
@@ -547,7 +582,7 @@ int gmrm_dot_products(gmrm_engine* e, const int32_t* local_ids, int32_t n, doubl
     CU(cudaMemcpyAsync(cols.p, local_ids, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
     for (int done = 0; done < n; done += chunk) {
         const int m = std::min(chunk, n - done);
-        rc = launch_step_all(e, cols.p + done, m, nullptr, 0, partial.p, nullptr); if (rc) return rc;
+        rc = launch_step_all(e, cols.p + done, m, Pending{}, partial.p, nullptr); if (rc) return rc;
         SampleParams sp = sample_params(e, cols.p + done, m, partial.p);
         launch_finish_dots(sp, res.p + (size_t)done * T, e->stream);
         CU(cudaGetLastError());
@@ -601,7 +636,8 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     int rc = cols.alloc(1); if (rc) return rc;
     CU(cudaMemcpyAsync(cols.p, &local_id, 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaMemcpyAsync(e->pub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));   // virtual rank 0's slot
-    rc = launch_step_all(e, nullptr, 0, cols.p, 1, nullptr, nullptr); if (rc) return rc;
+    Pending one; one.cols = cols.p; one.pV = 1;
+    rc = launch_step_all(e, nullptr, 0, one, nullptr, nullptr); if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
     return check_step_error(e);
@@ -722,31 +758,51 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     launches += 4;
 
     // ---- marker loop (bayes.cpp:375-555).  The residual update of step s is fused into the step kernel of
-    // step s+1 (it needs the same rows of eps the table build reads); an update-only launch flushes it before a
-    // cross-GPU exchange and after the last step.
+    // step s+1 (it needs the same rows of eps the table build reads); an update-only launch flushes it after the
+    // last step.  Exchange (bayes.cpp:495-553):
+    //   sync_rate == 1: the GPUs all-gather their published lists (V x 16 B each) after the sampler; the next step
+    //                   kernel applies ALL lists in global virtual-rank order, reading the other shards' columns
+    //                   over NVLink peer memory -- every GPU keeps the same residuals, bit for bit, as a single
+    //                   GPU with R virtual ranks would
+    //   sync_rate  > 1: each GPU applies its own list, accumulates what it changed, and every sync_rate steps the
+    //                   residual deltas are all-reduced and merged
     CU(cudaEventRecord(e->ev[1], s));
     const bool multi = c.world_size > 1;
-    const int32_t* pcols = nullptr;          // columns whose published updates are still pending
+    if (e->list_exchange) {
+        if (e->peers_set != c.world_size - 1) return fail(GMRM_EINVAL, "world_size > 1 with sync_rate 1 needs the peers' buffers (gmrm_comm_import_buffers / gmrm_comm_set_peer_buffers)");
+        for (int g = 0; g < c.world_size; g++) {
+            int Sg, Mg;
+            block_of(c.Mt, R, g * Vl, Sg, Mg);
+            launch_steptab(e->steptab_all.p + (size_t)g * Mm * Vl, Mm, Vl, g * Vl, R, c.Mt, Sg, c.shuffle, c.seed, it, d_perm, s);
+        }
+        launches += c.world_size;
+    }
+    Pending pend;                             // step whose published updates are still to be applied
     for (int st = 0; st < Mm; st++) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
         int nl = 0;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st], s));
-        if ((rc = launch_step_all(e, cols, Vl, pcols, pcols ? Vl : 0, e->partial.p, &nl))) return rc;
+        if ((rc = launch_step_all(e, cols, Vl, pend, e->partial.p, &nl))) return rc;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 1], s));
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
         launch_sample(sp, s);
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
-        pcols = cols;
-        const bool exchange = multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
-        if (exchange || st == Mm - 1 || e->force_flush) {
-            if ((rc = launch_step_all(e, nullptr, 0, pcols, Vl, nullptr, &nl))) return rc;
-            pcols = nullptr;
+        pend.step = st;
+        const bool delta_exchange = multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
+        if (e->list_exchange) {
+            PubEntry* mine = own_pub(e);
+            NC(g_nccl.AllGather(mine, e->pub_all.p, (size_t)Vl * T * 2, kNcclFloat64, e->comm, s));
+            if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
+            launches += 1;
+        }
+        if (delta_exchange || st == Mm - 1 || e->force_flush) {
+            if ((rc = launch_step_all(e, nullptr, 0, pend, nullptr, &nl))) return rc;
+            pend.step = -1;
         }
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
         launches += nl + 1;
-        // ---- exchange (bayes.cpp:495-553): every sync_rate steps the shards all-reduce what they changed
-        if (exchange) {
+        if (delta_exchange) {
             NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
             if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, s);
@@ -798,7 +854,10 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
             e->last.update_kernel_ms += ms;
             CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 4]));
             e->last.exchange_ms += ms;
-            if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+            if (e->list_exchange) {
+                CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 2], e->dot_ev[6 * st + 5]));
+                e->last.allreduce_ms += ms;
+            } else if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
                 CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 5]));
                 e->last.allreduce_ms += ms;
             }
@@ -873,6 +932,57 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&e->comm, e->cfg.world_size, u, e->cfg.world_rank));
     return GMRM_OK;
+}
+
+// Buffers the other GPUs read in the list exchange: genotypes, missing-list offsets and indices.  Call after
+// gmrm_finalize_bed.  Across processes they travel as CUDA IPC handles (3 x 64 bytes); inside one process as plain
+// pointers (+ peer access).
+int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[192]) {
+    if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
+    if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
+    CU(cudaSetDevice(e->cfg.device));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->bed.p)); memcpy(handles, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->miss_off.p)); memcpy(handles + 64, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->miss_idx.p)); memcpy(handles + 128, &h, 64);
+    return GMRM_OK;
+}
+static int set_peer(gmrm_engine* e, int rank, void* const p[3]) {
+    if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
+    if (!e->peer_bed[rank]) e->peers_set++;
+    e->peer_bed[rank] = (const uint8_t*)p[0]; e->peer_moff[rank] = (const uint32_t*)p[1]; e->peer_midx[rank] = (const uint32_t*)p[2];
+    const int me = e->cfg.world_rank;
+    e->peer_bed[me] = e->bed.p; e->peer_moff[me] = e->miss_off.p; e->peer_midx[me] = e->miss_idx.p;
+    return GMRM_OK;
+}
+int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[192]) {
+    if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
+    if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
+    CU(cudaSetDevice(e->cfg.device));
+    if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
+    void* p[3];
+    for (int i = 0; i < 3; i++) {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * i, 64);
+        CU(cudaIpcOpenMemHandle(&p[i], h, cudaIpcMemLazyEnablePeerAccess));
+        e->ipc_opened[rank][i] = p[i];
+    }
+    return set_peer(e, rank, p);
+}
+int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[3]) {
+    if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
+    if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
+    ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p;
+    return GMRM_OK;
+}
+int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[3]) {
+    if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const cudaError_t pe = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) return fail(GMRM_ECUDA, "no peer access from device %d to %d: %s", e->cfg.device, peer_device, cudaGetErrorString(pe));
+    cudaGetLastError();
+    return set_peer(e, rank, ptrs);
 }
 
 }  // extern "C"

@@ -45,6 +45,7 @@ struct Shared {
     std::vector<host::Phen> phens;
     std::vector<int32_t> group_index;
     uint8_t nccl_id[128];
+    void* peer_ptrs[8][3] = {};
     int vranks = 0;
 };
 
@@ -77,6 +78,12 @@ void worker(int rank, Shared* sh, Barrier* bar) {
             ck(gmrm_upload_bed(e, buf.data(), S + done, n), "gmrm_upload_bed");
         }
         ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
+    }
+    if (ngpu > 1 && o.sync_rate == 1) {      // list exchange: the shards read each other's columns over NVLink
+        ck(gmrm_comm_local_buffers(e, sh->peer_ptrs[rank]), "gmrm_comm_local_buffers");
+        bar->wait();
+        for (int r = 0; r < ngpu; r++)
+            if (r != rank) ck(gmrm_comm_set_peer_buffers(e, r, r, sh->peer_ptrs[r]), "gmrm_comm_set_peer_buffers");
     }
     if (rank == 0) printf("INFO   : time to load genotype data = %.3f seconds.\n", now() - t_load);
     for (int t = 0; t < T; t++) ck(gmrm_set_phenotype(e, t, sh->phens[t].eps.data(), sh->phens[t].mask4.data(), sh->phens[t].nonas), "gmrm_set_phenotype");

@@ -275,7 +275,7 @@ __device__ __forceinline__ uint32_t ldg_stream_u32(const uint8_t* p) {
     return v;
 }
 struct PubStage { double v[4]; };   // increment by dosage: (a - mave*b) * dbeta*msig for a = 0,1,2 (b = 1); v[3] = 0
-struct PubInfo { int32_t col; uint32_t nmiss; };
+struct PubInfo { int32_t col; uint32_t nmiss_g; };   // nmiss_g = missing genotypes of the column << 4 | publishing GPU
 
 template <int IMM>
 __device__ __forceinline__ double lds_f64_imm(uint32_t addr) {
@@ -385,16 +385,21 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             // ordered compaction of the published entries, 4 windows of NT virtual ranks at a time: all their pub
             // loads are in flight together and one scan orders them (rank order is preserved)
             constexpr int kWin = 4;
-            for (int v_lo = 0; v_lo < p.pV; v_lo += kWin * NT) {
+            const int pN = p.pG * p.pV;                      // entries of all lists, in global virtual-rank order
+            for (int v_lo = 0; v_lo < pN; v_lo += kWin * NT) {
                 PubEntry pe[kWin];
-                int pc[kWin];                                // column of each entry, fetched with it (same round trip)
+                int pc[kWin], pg[kWin];                      // column (fetched with the entry: same round trip) and publishing GPU
                 uint32_t bal[kWin];
 #pragma unroll
                 for (int w = 0; w < kWin; w++) {
                     const int v = v_lo + w * NT + tid;
                     pe[w] = PubEntry{0.0, 0.0};
-                    pc[w] = 0;
-                    if (v < p.pV) { pe[w] = p.pub[(int64_t)v * p.Ttot + tt]; pc[w] = p.pcols[v]; }
+                    pc[w] = 0; pg[w] = 0;
+                    if (v < pN) {
+                        pg[w] = v / p.pV;
+                        pe[w] = p.pub[(int64_t)v * p.Ttot + tt];
+                        pc[w] = p.pcols[pg[w]][v - pg[w] * p.pV];
+                    }
                 }
                 __syncthreads();
 #pragma unroll
@@ -424,14 +429,15 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                             s.v[1] = (mdb * 1.0 + 1.0) * pe[w].lam;
                             s.v[2] = (mdb * 1.0 + 2.0) * pe[w].lam;
                             s.v[3] = 0.0;
-                            info[ord[w] - r0].col = pc[w];       // nmiss is filled in with the column bytes below
+                            info[ord[w] - r0].col = pc[w];
+                            info[ord[w] - r0].nmiss_g = (uint32_t)pg[w];   // the missing count is filled in with the column bytes below
                         }
                     }
                     __syncthreads();
                     touched = true;
                     if (q0 == 0 || nq > 2 * NT) {            // (re)stage: once per round unless the rows need several quad chunks
                         uint32_t mo0 = 0, mo1 = 0;           // missing-list bounds of entry `tid`, in flight with the bytes
-                        if (tid < n) { mo0 = p.miss_off[info[tid].col]; mo1 = p.miss_off[info[tid].col + 1]; }
+                        if (tid < n) { const uint32_t* mo = p.pmiss_off[info[tid].nmiss_g & 15u]; mo0 = mo[info[tid].col]; mo1 = mo[info[tid].col + 1]; }
                         const int npiece = n * nr * 4;       // 16-byte pieces: entry x local row x 4
                         for (int i0 = tid; i0 < npiece; i0 += 8 * NT) {
                             uint4 v[8];
@@ -440,7 +446,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                                 const int i = i0 + j * NT;
                                 if (i < npiece) {
                                     const int en = i / (nr * 4), rem = i - en * (nr * 4), lr = rem >> 2, part = rem & 3;
-                                    const uint8_t* src = p.bed + (int64_t)info[en].col * p.col_stride + (int64_t)global_row(pr, lr) * kRowBytes + part * 16;
+                                    const uint8_t* src = p.pbed[info[en].nmiss_g & 15u] + (int64_t)info[en].col * p.col_stride + (int64_t)global_row(pr, lr) * kRowBytes + part * 16;
                                     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src));
                                 }
                             }
@@ -450,7 +456,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                                 if (i < npiece) *reinterpret_cast<uint4*>(bytes + (size_t)i * 16) = v[j];   // == entry*nq + lr*64 + part*16
                             }
                         }
-                        if (tid < n) info[tid].nmiss = mo1 - mo0;
+                        if (tid < n) info[tid].nmiss_g = ((mo1 - mo0) << 4) | (info[tid].nmiss_g & 15u);
                         __syncthreads();
                     }
                     GMRM_ATICK()   // [42] stage fill + column bytes
@@ -466,13 +472,14 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                         const uint32_t gbase = stage_u32 + (uint32_t)g0 * 32u;   // 256-aligned: stage is, g0 is a multiple of 8
 #define GMRM_APPLY(J)                                                                                              \
     if (g0 + J < n) {                                                                                             \
-        const bool hasmiss = info[g0 + J].nmiss != 0; /* CTA-uniform */                                           \
+        const uint32_t nmiss = info[g0 + J].nmiss_g >> 4, pgpu = info[g0 + J].nmiss_g & 15u;                      \
+        const bool hasmiss = nmiss != 0; /* CTA-uniform */                                                        \
         if (hasmiss) {                                                                                            \
             for (int i = tid; i < nr * 8; i += NT) bitmap[i] = 0u;                                                \
             __syncthreads();                                                                                      \
-            const uint32_t mo = p.miss_off[info[g0 + J].col];                                                     \
-            for (uint32_t i = tid; i < info[g0 + J].nmiss; i += NT) {                                             \
-                const int ind = (int)p.miss_idx[mo + i], grow = ind >> 8;                                         \
+            const uint32_t mo = p.pmiss_off[pgpu][info[g0 + J].col];                                              \
+            for (uint32_t i = tid; i < nmiss; i += NT) {                                                          \
+                const int ind = (int)p.pmiss_idx[pgpu][mo + i], grow = ind >> 8;                                  \
                 for (int qp = 0; qp < pr.npass; qp++)                                                             \
                     if (grow >= pr.start[qp] && grow < pr.start[qp] + pr.count[qp]) {                             \
                         const int loc = (pr.base[qp] + grow - pr.start[qp]) * kRowInd + (ind & 255);              \
@@ -754,7 +761,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 #define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
-    if (p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
+    if (p.pG * p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     GMRM_TICK()                                           // [8] prologue + update phase
     if (p.V == 0) return;

@@ -21,6 +21,7 @@ namespace gmrm {
 #define GMRM_STEP_DEPTH 1
 #endif
 constexpr int kBatch = GMRM_STEP_BATCH;   // markers per warp batch (one marker per half-warp: kBatch/2 pairs)
+constexpr int kMaxGpus = 8;
 constexpr int kPubCap = 128;           // published updates staged per round of the update phase
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
@@ -43,13 +44,16 @@ struct StepParams {
     int32_t npass;           // step_npass(L, rows_per_pass)
     double* partial;         // [V][Ttot][nsm]   per-CTA partial sums of sum a*eps
     double* spart;           // [Ttot][nsm]      per-CTA sums of eps
-    // pending updates (previous step), applied in virtual-rank order
-    const int32_t* pcols;    // [pV]
-    int32_t pV;
-    const PubEntry* pub;     // [pV][Ttot]
+    // pending updates (previous step), applied in virtual-rank order: pG lists of pV entries, list g published by
+    // GPU g about ITS markers -- columns, genotypes and missing lists of list g are read from GPU g's buffers
+    // (peer memory over NVLink when g is not this GPU)
+    int32_t pG, pV;
+    const PubEntry* pub;                 // [pG][pV][Ttot]
+    const int32_t* pcols[kMaxGpus];      // [pV] columns local to GPU g
+    const uint8_t* pbed[kMaxGpus];
+    const uint32_t* pmiss_off[kMaxGpus];
+    const uint32_t* pmiss_idx[kMaxGpus];
     const uint8_t* mask4;    // [Ttot][col_stride] NA nibble of every quad (bit k: individual 4q+k observed)
-    const uint32_t* miss_off;
-    const uint32_t* miss_idx;
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     int32_t* err;
     int32_t pf;              // 1: L2 prefetch ahead of the streaming loads

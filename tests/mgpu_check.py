@@ -39,6 +39,13 @@ def main():
     lo, n = e.marker_begin, e.marker_count
     e.upload_bed(inp["bed"][lo:lo + n])
     e.finalize_bed()
+    if sync_rate == 1:
+
+        def gather(x):
+            out = [None] * world
+            dist.all_gather_object(out, x)
+            return out
+        e.exchange_buffers(gather)
     for t in range(T):
         e.set_phenotype(t, inp["eps0"][t], inp["mask4"][t], int(inp["nonas"][t]))
     e.set_groups(inp["group_index"], inp["cva"])
@@ -57,8 +64,10 @@ def main():
     dist.all_gather_object(gathered, (lo, n, hist, eps))
     ok = True
     if rank == 0:
+        # sync_rate 1: list exchange, every GPU holds the residuals of ONE chain with R virtual ranks (the reference under
+        # mpirun -n R); sync_rate > 1: one residual replica per GPU, deltas all-reduced every sync_rate steps
         res = O.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=N, R=R,
-                      nrep=world, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
+                      nrep=1 if sync_rate == 1 else world, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
         for (lo_g, n_g, hist_g, eps_g) in gathered:
             for i in range(iters):
                 assert np.array_equal(hist_g[i]["comp"], res["comp"][i][:, lo_g:lo_g + n_g]), f"comp differs it {i + 1}"
