@@ -135,8 +135,8 @@ struct gmrm_engine {
     const uint32_t* peer_midx[kMaxGpus] = {};
     void* ipc_opened[kMaxGpus][3] = {};
     int peers_set = 0;
-    DevBuf<int32_t> steptab_all;     // [world][Mm][Vl] columns (local to each GPU's shard) of every GPU's steps
-    DevBuf<PubEntry> pub_all;        // [world][Vl][T]; this GPU's sampler writes its own block
+    DevBuf<double> plist;            // [world or 1][T][publist_doubles(Vl)] compacted published lists; the sampler writes this GPU's block
+    DevBuf<unsigned int> ticket;
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
     bool force_flush = false;        // GMRM_FORCE_FLUSH=1: update-only launch after every step (timing aid)
     int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
@@ -244,15 +244,14 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->list_exchange = c->world_size > 1 && c->sync_rate == 1;
     if (c->world_size > kMaxGpus) { delete e; return fail(GMRM_EINVAL, "world_size %d > %d", c->world_size, kMaxGpus); }
     if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
-    if (e->list_exchange) {
-        A(e->steptab_all.alloc((size_t)c->world_size * e->Mm * e->Vl));
-        A(e->pub_all.alloc((size_t)c->world_size * e->Vl * T));
-    }
+    A(e->plist.alloc((size_t)(e->list_exchange ? c->world_size : 1) * T * publist_doubles(e->Vl)));
+    A(e->ticket.alloc(1));
     if (rc != 0) { delete e; return rc; }
     // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
     for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
                     &e->mu_old, &e->partial, &e->delta, &e->delta_tot})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->plist.zero(e->stream) != 0 || e->ticket.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
@@ -504,8 +503,8 @@ int gmrm_get_marker_stats(gmrm_engine* e, int32_t t, double* mave, double* msig)
 // One marker-step (kernels.cu K1) for all traits: pending updates of the previous step (none when pend_step < 0),
 // tables, and the dot products of the V columns `cols` (V == 0: update only).  `pend_cols` (non-null) overrides
 // the pending list with a single local one of pV entries whose PubEntry block is e->pub (test hook).
-struct Pending { int step = -1; const int32_t* cols = nullptr; int pV = 0; };
-static PubEntry* own_pub(gmrm_engine* e) { return e->list_exchange ? e->pub_all.p + (size_t)e->cfg.world_rank * e->Vl * e->cfg.T : e->pub.p; }
+struct Pending { bool any = false; bool own_only = false; };
+static double* own_list(gmrm_engine* e) { return e->plist.p + (e->list_exchange ? (size_t)e->cfg.world_rank * e->cfg.T * publist_doubles(e->Vl) : 0); }
 
 static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch) {
     const int T = e->cfg.T;
@@ -520,18 +519,13 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         p.eps = e->eps.p; p.npad = e->L.npad; p.Ttot = T; p.t0 = t0; p.rows_per_pass = rpp; p.npass = step_npass(e->L, rpp);
         p.partial = partial; p.spart = e->spart.p;
         p.mask4 = e->mask4.p;
-        if (pend.cols) {                                        // one local list
-            p.pG = 1; p.pV = pend.pV; p.pub = e->pub.p;
-            p.pcols[0] = pend.cols; p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
-        } else if (pend.step >= 0 && e->list_exchange) {        // the lists of all GPUs for step pend.step
-            p.pG = e->cfg.world_size; p.pV = e->Vl; p.pub = e->pub_all.p;
-            for (int g = 0; g < p.pG; g++) {
-                p.pcols[g] = e->steptab_all.p + ((size_t)g * e->Mm + pend.step) * e->Vl;
-                p.pbed[g] = e->peer_bed[g]; p.pmiss_off[g] = e->peer_moff[g]; p.pmiss_idx[g] = e->peer_midx[g];
-            }
-        } else if (pend.step >= 0) {                            // this GPU's own list
-            p.pG = 1; p.pV = e->Vl; p.pub = e->pub.p;
-            p.pcols[0] = e->steptab.p + (size_t)pend.step * e->Vl; p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
+        p.pV = e->Vl;
+        if (pend.any && e->list_exchange && !pend.own_only) {   // the lists of all GPUs (after the all-gather)
+            p.pG = e->cfg.world_size; p.plist = e->plist.p;
+            for (int g = 0; g < p.pG; g++) { p.pbed[g] = e->peer_bed[g]; p.pmiss_off[g] = e->peer_moff[g]; p.pmiss_idx[g] = e->peer_midx[g]; }
+        } else if (pend.any) {                                  // this GPU's own list
+            p.pG = 1; p.plist = own_list(e);
+            p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
         }
         p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
         p.err = e->err.p;
@@ -551,7 +545,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
-    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = own_pub(e); p.err = e->err.p; p.npublished = e->npub.p;
+    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e); p.ticket = e->ticket.p; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }
 
@@ -629,15 +623,15 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     double av, sg;
     CU(cudaMemcpy(&av, e->mave.p + (size_t)trait * e->Mloc + local_id, 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(&sg, e->msig.p + (size_t)trait * e->Mloc + local_id, 8, cudaMemcpyDeviceToHost));
-    std::vector<PubEntry> pub(T, PubEntry{0.0, 0.0});
-    pub[trait].lam = dbeta * sg;                                   // phenotype.cpp:328
-    pub[trait].mave = av;
-    DevBuf<int32_t> cols;
-    int rc = cols.alloc(1); if (rc) return rc;
-    CU(cudaMemcpyAsync(cols.p, &local_id, 4, cudaMemcpyHostToDevice, e->stream));
-    CU(cudaMemcpyAsync(e->pub.p, pub.data(), sizeof(PubEntry) * T, cudaMemcpyHostToDevice, e->stream));   // virtual rank 0's slot
-    Pending one; one.cols = cols.p; one.pV = 1;
-    rc = launch_step_all(e, nullptr, 0, one, nullptr, nullptr); if (rc) return rc;
+    // a one-item published list for `trait`, empty lists for the others (Phenotype::update_epsilon's dbeta[3], phenotype.cpp:328)
+    const size_t ld = publist_doubles(e->Vl);
+    std::vector<double> lists((size_t)T * ld, 0.0);
+    *reinterpret_cast<int32_t*>(&lists[(size_t)trait * ld]) = 1;
+    PubItem it{dbeta * sg, av, local_id, 0};
+    memcpy(&lists[(size_t)trait * ld + 2], &it, sizeof it);
+    CU(cudaMemcpyAsync(own_list(e), lists.data(), lists.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    Pending one; one.any = true; one.own_only = true;
+    int rc = launch_step_all(e, nullptr, 0, one, nullptr, nullptr); if (rc) return rc;
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
     return check_step_error(e);
@@ -770,14 +764,8 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     const bool multi = c.world_size > 1;
     if (e->list_exchange) {
         if (e->peers_set != c.world_size - 1) return fail(GMRM_EINVAL, "world_size > 1 with sync_rate 1 needs the peers' buffers (gmrm_comm_import_buffers / gmrm_comm_set_peer_buffers)");
-        for (int g = 0; g < c.world_size; g++) {
-            int Sg, Mg;
-            block_of(c.Mt, R, g * Vl, Sg, Mg);
-            launch_steptab(e->steptab_all.p + (size_t)g * Mm * Vl, Mm, Vl, g * Vl, R, c.Mt, Sg, c.shuffle, c.seed, it, d_perm, s);
-        }
-        launches += c.world_size;
     }
-    Pending pend;                             // step whose published updates are still to be applied
+    Pending pend;                             // published updates of the previous step still to be applied?
     for (int st = 0; st < Mm; st++) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
         int nl = 0;
@@ -788,17 +776,16 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
         launch_sample(sp, s);
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
-        pend.step = st;
+        pend.any = true;
         const bool delta_exchange = multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
         if (e->list_exchange) {
-            PubEntry* mine = own_pub(e);
-            NC(g_nccl.AllGather(mine, e->pub_all.p, (size_t)Vl * T * 2, kNcclFloat64, e->comm, s));
+            NC(g_nccl.AllGather(own_list(e), e->plist.p, (size_t)T * publist_doubles(Vl), kNcclFloat64, e->comm, s));
             if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launches += 1;
         }
         if (delta_exchange || st == Mm - 1 || e->force_flush) {
             if ((rc = launch_step_all(e, nullptr, 0, pend, nullptr, &nl))) return rc;
-            pend.step = -1;
+            pend.any = false;
         }
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
         launches += nl + 1;

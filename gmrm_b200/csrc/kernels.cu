@@ -382,56 +382,36 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             }
             GMRM_ATICK()   // [40] lut + eps/mask loads
             bool touched = false;
-            // ordered compaction of the published entries, 4 windows of NT virtual ranks at a time: all their pub
-            // loads are in flight together and one scan orders them (rank order is preserved)
-            constexpr int kWin = 4;
-            const int pN = p.pG * p.pV;                      // entries of all lists, in global virtual-rank order
-            for (int v_lo = 0; v_lo < pN; v_lo += kWin * NT) {
-                PubEntry pe[kWin];
-                int pc[kWin], pg[kWin];                      // column (fetched with the entry: same round trip) and publishing GPU
-                uint32_t bal[kWin];
+            // the lists arrive compacted and ordered (sampler kernel); list g of GPU g, GPUs in rank order = global
+            // virtual-rank order
+            int pre[kMaxGpus + 1];
+            pre[0] = 0;
 #pragma unroll
-                for (int w = 0; w < kWin; w++) {
-                    const int v = v_lo + w * NT + tid;
-                    pe[w] = PubEntry{0.0, 0.0};
-                    pc[w] = 0; pg[w] = 0;
-                    if (v < pN) {
-                        pg[w] = v / p.pV;
-                        pe[w] = p.pub[(int64_t)v * p.Ttot + tt];
-                        pc[w] = p.pcols[pg[w]][v - pg[w] * p.pV];
-                    }
-                }
-                __syncthreads();
-#pragma unroll
-                for (int w = 0; w < kWin; w++) {
-                    bal[w] = __ballot_sync(0xffffffffu, pe[w].lam != 0.0);
-                    if (lane == 0) wcnt[w * NWALL + warp] = __popc(bal[w]);
-                }
-                __syncthreads();
-                int ord[kWin], total = 0;
-#pragma unroll
-                for (int w = 0; w < kWin; w++) {
-                    int before = 0, all = 0;
-                    for (int x = 0; x < NWALL; x++) { const int c = wcnt[w * NWALL + x]; if (x < warp) before += c; all += c; }
-                    ord[w] = total + before + __popc(bal[w] & ((1u << lane) - 1u));
-                    total += all;
-                }
-                GMRM_ATICK()   // [41] pub loads + scan
+            for (int g = 0; g < kMaxGpus; g++) {
+                int c = 0;
+                if (g < p.pG) c = *reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV));
+                pre[g + 1] = pre[g] + c;
+            }
+            const int total = pre[kMaxGpus];
+            GMRM_ATICK()   // [41] list headers
+            {
                 for (int r0 = 0; r0 < total; r0 += cap) {
                     const int n = min(cap, total - r0);
                     __syncthreads();
+                    if (tid < n) {
+                        const int x = r0 + tid;
+                        int g = 0;
 #pragma unroll
-                    for (int w = 0; w < kWin; w++) {
-                        if (pe[w].lam != 0.0 && ord[w] >= r0 && ord[w] < r0 + n) {
-                            PubStage& s = stage[ord[w] - r0];
-                            const double mdb = -pe[w].mave;            // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
-                            s.v[0] = (mdb * 1.0 + 0.0) * pe[w].lam;
-                            s.v[1] = (mdb * 1.0 + 1.0) * pe[w].lam;
-                            s.v[2] = (mdb * 1.0 + 2.0) * pe[w].lam;
-                            s.v[3] = 0.0;
-                            info[ord[w] - r0].col = pc[w];
-                            info[ord[w] - r0].nmiss_g = (uint32_t)pg[w];   // the missing count is filled in with the column bytes below
-                        }
+                        for (int q = 1; q < kMaxGpus; q++) g += (x >= pre[q]) ? 1 : 0;
+                        const PubItem it = reinterpret_cast<const PubItem*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + 2)[x - pre[g]];
+                        PubStage& s = stage[tid];
+                        const double mdb = -it.mave;                   // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
+                        s.v[0] = (mdb * 1.0 + 0.0) * it.lam;
+                        s.v[1] = (mdb * 1.0 + 1.0) * it.lam;
+                        s.v[2] = (mdb * 1.0 + 2.0) * it.lam;
+                        s.v[3] = 0.0;
+                        info[tid].col = it.col;
+                        info[tid].nmiss_g = (uint32_t)g;               // the missing count is filled in with the column bytes below
                     }
                     __syncthreads();
                     touched = true;
@@ -871,9 +851,7 @@ __global__ void group_consts_kernel(int T, int G, int K, int N, const double* __
 // Latency-ordered: the kernel is one dependent chain per warp, so independent loads are issued together --
 // round 1: column index, the marker's partial sums and the residual sums (none depends on the column);
 // round 2 (needs the column): missing-list bounds, group, mave, msig, beta;  round 3: sigmaG, sampler constants.
-__global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
-    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (v >= p.V) return;
+__device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lane) {
     const int col = p.cols[v];
     // ---- round 1: sum a*eps partials and sum eps, trait by trait (fixed order), while `col` is in flight
     double my_coded = 0.0, my_sall = 0.0;
@@ -951,6 +929,72 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
     e.mave = mave;
     p.pub[(int64_t)v * p.T + t] = e;
     if (e.lam != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), 1ull);
+}
+
+
+// One warp per virtual rank; the last CTA to finish compacts the step's published entries, in virtual-rank order,
+// into this GPU's list (what the next step kernel -- on every GPU, after the all-gather -- applies).
+__global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
+    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (v < p.V) sample_one(p, v, lane);
+    __shared__ bool last;
+    __threadfence();                                         // this thread's pub entry is visible device-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;   // ... before the CTA takes its ticket
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    // ordered compaction, 16 x 128 entries at a time: coalesced loads all in flight, one ballot per warp and chunk,
+    // one 64-element scan
+    const int tid = threadIdx.x, warp = tid >> 5;
+    __shared__ int cnts[64], offs[64];
+    __shared__ int s_total;
+    for (int t = 0; t < p.T; t++) {
+        double* list = p.plist + (size_t)t * publist_doubles(p.V);
+        PubItem* items = reinterpret_cast<PubItem*>(list + 2);
+        int base = 0;
+        for (int x0 = 0; x0 < p.V; x0 += 16 * 128) {
+            double lam[16];
+            uint32_t bal[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int x = x0 + i * 128 + tid;
+                lam[i] = x < p.V ? __ldcg(&p.pub[(int64_t)x * p.T + t].lam) : 0.0;
+            }
+            __syncthreads();                                 // cnts / offs of the previous round are consumed
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                bal[i] = __ballot_sync(0xffffffffu, lam[i] != 0.0);
+                if (lane == 0) cnts[i * 4 + warp] = __popc(bal[i]);
+            }
+            __syncthreads();
+            if (warp == 0) {                                 // exclusive scan of the 64 (chunk, warp) counts
+                const int c0 = cnts[2 * lane], c1 = cnts[2 * lane + 1];
+                int incl = c0 + c1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                offs[2 * lane] = incl - c0 - c1;
+                offs[2 * lane + 1] = incl - c1;
+                if (lane == 31) s_total = incl;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (lam[i] != 0.0) {
+                    const int x = x0 + i * 128 + tid;
+                    PubItem it;
+                    it.lam = lam[i]; it.mave = __ldcg(&p.pub[(int64_t)x * p.T + t].mave); it.col = p.cols[x]; it.v = x;
+                    items[base + offs[i * 4 + warp] + __popc(bal[i] & ((1u << lane) - 1u))] = it;
+                }
+            }
+            base += s_total;
+        }
+        if (tid == 0) *reinterpret_cast<int32_t*>(list) = base;
+    }
+    if (tid == 0) *p.ticket = 0u;
 }
 
 // test hook behind gmrm_dot_products: out[v*T+t] = Bayes::dot_product

@@ -28,6 +28,10 @@ struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3
     double lam;     // dbeta * msig   (0 == nothing to apply)
     double mave;
 };
+// The step's published updates of one GPU and trait, compacted in virtual-rank order by the sampler kernel:
+// a 16-byte header (int32 count) followed by up to V items.  This is what the GPUs all-gather.
+struct PubItem { double lam, mave; int32_t col, v; };     // col: column local to the publishing GPU
+__host__ __device__ constexpr size_t publist_doubles(int V) { return 2 + 3 * (size_t)V; }
 
 // One marker-step on one GPU: (a) apply the updates published by the previous step to this CTA's rows of
 // the residuals, (b) build the look-up tables of those rows, (c) stream the step's V columns through them.
@@ -47,9 +51,8 @@ struct StepParams {
     // pending updates (previous step), applied in virtual-rank order: pG lists of pV entries, list g published by
     // GPU g about ITS markers -- columns, genotypes and missing lists of list g are read from GPU g's buffers
     // (peer memory over NVLink when g is not this GPU)
-    int32_t pG, pV;
-    const PubEntry* pub;                 // [pG][pV][Ttot]
-    const int32_t* pcols[kMaxGpus];      // [pV] columns local to GPU g
+    int32_t pG, pV;                      // lists, capacity of a list (0 lists: nothing pending)
+    const double* plist;                 // [pG][Ttot][publist_doubles(pV)]
     const uint8_t* pbed[kMaxGpus];
     const uint32_t* pmiss_off[kMaxGpus];
     const uint32_t* pmiss_idx[kMaxGpus];
@@ -85,7 +88,9 @@ struct SampleParams {
     const double* gc;        // [T][G][4K] per-iteration sampler constants (group_consts_kernel)
     const int32_t* nonas;    // [T]
     int32_t* cass;           // [T][G*K]
-    PubEntry* pub;           // [V][T]
+    PubEntry* pub;           // [V][T] scratch: every marker's entry (lam == 0: nothing published)
+    double* plist;           // [T][publist_doubles(V)] this GPU's compacted list (written by the last CTA to finish)
+    unsigned int* ticket;    // CTA counter for that, zero between launches
     const double* rep_u;     // replay: [Mm][R][T] or nullptr
     const double* rep_z;
     int32_t* err;            // device error flag
