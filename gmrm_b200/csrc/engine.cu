@@ -133,7 +133,13 @@ struct gmrm_engine {
     const uint8_t* peer_bed[kMaxGpus] = {};
     const uint32_t* peer_moff[kMaxGpus] = {};
     const uint32_t* peer_midx[kMaxGpus] = {};
-    void* ipc_opened[kMaxGpus][3] = {};
+    double* peer_plist[kMaxGpus] = {};               // peers' (and own) list buffers [2][world][T][ld]
+    unsigned long long* peer_xflags[kMaxGpus] = {};  // peers' (and own) flag arrays [world]
+    void* ipc_opened[kMaxGpus][5] = {};
+    bool list_p2p = true;            // lists are pushed into the peers' buffers by the sampler kernel (GMRM_EXCHANGE=nccl: all-gather)
+    unsigned long long xseq = 0;     // exchange sequence number: one per sampled step, identical on all GPUs
+    unsigned long long pend_seq = 0; // sequence number of the step whose lists are pending
+    DevBuf<unsigned long long> xflags;
     int peers_set = 0;
     DevBuf<double> plist;            // [world or 1][T][publist_doubles(Vl)] compacted published lists; the sampler writes this GPU's block
     DevBuf<unsigned int> ticket;
@@ -244,14 +250,15 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->list_exchange = c->world_size > 1 && c->sync_rate == 1;
     if (c->world_size > kMaxGpus) { delete e; return fail(GMRM_EINVAL, "world_size %d > %d", c->world_size, kMaxGpus); }
     if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
-    A(e->plist.alloc((size_t)(e->list_exchange ? c->world_size : 1) * T * publist_doubles(e->Vl)));
-    A(e->ticket.alloc(1));
+    if (const char* v = getenv("GMRM_EXCHANGE")) e->list_p2p = strcmp(v, "nccl") != 0;
+    A(e->plist.alloc((size_t)(e->list_exchange ? 2 * c->world_size : 1) * T * publist_doubles(e->Vl)));   // 2: parity of the exchange sequence
+    A(e->ticket.alloc(1)); A(e->xflags.alloc(kMaxGpus));
     if (rc != 0) { delete e; return rc; }
     // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
     for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
                     &e->mu_old, &e->partial, &e->delta, &e->delta_tot})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
-    if (e->plist.zero(e->stream) != 0 || e->ticket.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->plist.zero(e->stream) != 0 || e->ticket.zero(e->stream) != 0 || e->xflags.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
@@ -504,7 +511,10 @@ int gmrm_get_marker_stats(gmrm_engine* e, int32_t t, double* mave, double* msig)
 // tables, and the dot products of the V columns `cols` (V == 0: update only).  `pend_cols` (non-null) overrides
 // the pending list with a single local one of pV entries whose PubEntry block is e->pub (test hook).
 struct Pending { bool any = false; bool own_only = false; };
-static double* own_list(gmrm_engine* e) { return e->plist.p + (e->list_exchange ? (size_t)e->cfg.world_rank * e->cfg.T * publist_doubles(e->Vl) : 0); }
+// list buffer layout: [parity of the exchange sequence][GPU][trait][publist_doubles(Vl)] (one block without exchange)
+static size_t list_block(const gmrm_engine* e) { return (size_t)e->cfg.T * publist_doubles(e->Vl); }
+static double* lists_of(gmrm_engine* e, unsigned long long seq) { return e->plist.p + (e->list_exchange ? (size_t)(seq & 1) * e->cfg.world_size * list_block(e) : 0); }
+static double* own_list(gmrm_engine* e, unsigned long long seq) { return lists_of(e, seq) + (e->list_exchange ? (size_t)e->cfg.world_rank * list_block(e) : 0); }
 
 static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch) {
     const int T = e->cfg.T;
@@ -521,10 +531,11 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         p.mask4 = e->mask4.p;
         p.pV = e->Vl;
         if (pend.any && e->list_exchange && !pend.own_only) {   // the lists of all GPUs (after the all-gather)
-            p.pG = e->cfg.world_size; p.plist = e->plist.p;
+            p.pG = e->cfg.world_size; p.plist = lists_of(e, e->pend_seq);
             for (int g = 0; g < p.pG; g++) { p.pbed[g] = e->peer_bed[g]; p.pmiss_off[g] = e->peer_moff[g]; p.pmiss_idx[g] = e->peer_midx[g]; }
+            if (e->list_p2p) { p.xflags = e->xflags.p; p.wait_seq = e->pend_seq; }
         } else if (pend.any) {                                  // this GPU's own list
-            p.pG = 1; p.plist = own_list(e);
+            p.pG = 1; p.plist = own_list(e, e->pend_seq);
             p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
         }
         p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
@@ -545,7 +556,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
-    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e); p.ticket = e->ticket.p; p.err = e->err.p; p.npublished = e->npub.p;
+    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e, e->xseq); p.ticket = e->ticket.p; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }
 
@@ -629,7 +640,8 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     *reinterpret_cast<int32_t*>(&lists[(size_t)trait * ld]) = 1;
     PubItem it{dbeta * sg, av, local_id, 0};
     memcpy(&lists[(size_t)trait * ld + 2], &it, sizeof it);
-    CU(cudaMemcpyAsync(own_list(e), lists.data(), lists.size() * 8, cudaMemcpyHostToDevice, e->stream));
+    e->pend_seq = e->xseq;
+    CU(cudaMemcpyAsync(own_list(e, e->pend_seq), lists.data(), lists.size() * 8, cudaMemcpyHostToDevice, e->stream));
     Pending one; one.any = true; one.own_only = true;
     int rc = launch_step_all(e, nullptr, 0, one, nullptr, nullptr); if (rc) return rc;
     CU(cudaGetLastError());
@@ -772,14 +784,23 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st], s));
         if ((rc = launch_step_all(e, cols, Vl, pend, e->partial.p, &nl))) return rc;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 1], s));
+        e->xseq++;                                           // this step's lists: sequence number xseq, buffer parity xseq & 1
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
+        if (e->list_exchange && e->list_p2p) {               // the sampler pushes the list into every peer's buffer and raises our flag there
+            sp.world = c.world_size; sp.rank = c.world_rank; sp.seq = e->xseq;
+            for (int g = 0; g < c.world_size; g++) {
+                sp.peer_list[g] = e->peer_plist[g] + ((size_t)(e->xseq & 1) * c.world_size + c.world_rank) * list_block(e);
+                sp.peer_flag[g] = e->peer_xflags[g] + c.world_rank;
+            }
+        }
         launch_sample(sp, s);
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
         pend.any = true;
+        e->pend_seq = e->xseq;
         const bool delta_exchange = multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
-        if (e->list_exchange) {
-            NC(g_nccl.AllGather(own_list(e), e->plist.p, (size_t)T * publist_doubles(Vl), kNcclFloat64, e->comm, s));
+        if (e->list_exchange && !e->list_p2p) {
+            NC(g_nccl.AllGather(own_list(e, e->xseq), lists_of(e, e->xseq), (size_t)T * publist_doubles(Vl), kNcclFloat64, e->comm, s));
             if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launches += 1;
         }
@@ -841,10 +862,10 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
             e->last.update_kernel_ms += ms;
             CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 4]));
             e->last.exchange_ms += ms;
-            if (e->list_exchange) {
+            if (e->list_exchange && !e->list_p2p) {
                 CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 2], e->dot_ev[6 * st + 5]));
                 e->last.allreduce_ms += ms;
-            } else if (multi && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+            } else if (multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
                 CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 5]));
                 e->last.allreduce_ms += ms;
             }
@@ -924,7 +945,7 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
 // Buffers the other GPUs read in the list exchange: genotypes, missing-list offsets and indices.  Call after
 // gmrm_finalize_bed.  Across processes they travel as CUDA IPC handles (3 x 64 bytes); inside one process as plain
 // pointers (+ peer access).
-int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[192]) {
+int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[320]) {
     if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     CU(cudaSetDevice(e->cfg.device));
@@ -933,23 +954,27 @@ int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[192]) {
     CU(cudaIpcGetMemHandle(&h, e->bed.p)); memcpy(handles, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->miss_off.p)); memcpy(handles + 64, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->miss_idx.p)); memcpy(handles + 128, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->plist.p)); memcpy(handles + 192, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->xflags.p)); memcpy(handles + 256, &h, 64);
     return GMRM_OK;
 }
-static int set_peer(gmrm_engine* e, int rank, void* const p[3]) {
+static int set_peer(gmrm_engine* e, int rank, void* const p[5]) {
     if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
     if (!e->peer_bed[rank]) e->peers_set++;
     e->peer_bed[rank] = (const uint8_t*)p[0]; e->peer_moff[rank] = (const uint32_t*)p[1]; e->peer_midx[rank] = (const uint32_t*)p[2];
+    e->peer_plist[rank] = (double*)p[3]; e->peer_xflags[rank] = (unsigned long long*)p[4];
     const int me = e->cfg.world_rank;
     e->peer_bed[me] = e->bed.p; e->peer_moff[me] = e->miss_off.p; e->peer_midx[me] = e->miss_idx.p;
+    e->peer_plist[me] = e->plist.p; e->peer_xflags[me] = e->xflags.p;
     return GMRM_OK;
 }
-int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[192]) {
+int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[320]) {
     if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     CU(cudaSetDevice(e->cfg.device));
     if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
-    void* p[3];
-    for (int i = 0; i < 3; i++) {
+    void* p[5];
+    for (int i = 0; i < 5; i++) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * i, 64);
         CU(cudaIpcOpenMemHandle(&p[i], h, cudaIpcMemLazyEnablePeerAccess));
@@ -957,13 +982,13 @@ int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles
     }
     return set_peer(e, rank, p);
 }
-int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[3]) {
+int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[5]) {
     if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
-    ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p;
+    ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p; ptrs[3] = e->plist.p; ptrs[4] = e->xflags.p;
     return GMRM_OK;
 }
-int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[3]) {
+int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[5]) {
     if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
     const cudaError_t pe = cudaDeviceEnablePeerAccess(peer_device, 0);

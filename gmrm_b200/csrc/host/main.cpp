@@ -45,7 +45,7 @@ struct Shared {
     std::vector<host::Phen> phens;
     std::vector<int32_t> group_index;
     uint8_t nccl_id[128];
-    void* peer_ptrs[8][3] = {};
+    void* peer_ptrs[8][5] = {};
     int vranks = 0;
 };
 

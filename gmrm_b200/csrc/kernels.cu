@@ -389,7 +389,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
 #pragma unroll
             for (int g = 0; g < kMaxGpus; g++) {
                 int c = 0;
-                if (g < p.pG) c = *reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV));
+                if (g < p.pG) c = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV)));
                 pre[g + 1] = pre[g] + c;
             }
             const int total = pre[kMaxGpus];
@@ -403,7 +403,11 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                         int g = 0;
 #pragma unroll
                         for (int q = 1; q < kMaxGpus; q++) g += (x >= pre[q]) ? 1 : 0;
-                        const PubItem it = reinterpret_cast<const PubItem*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + 2)[x - pre[g]];
+                        const double* ip = p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + 2 + 3 * (size_t)(x - pre[g]);
+                        PubItem it;                          // .cg loads: peers rewrite this buffer between launches
+                        it.lam = __ldcg(ip); it.mave = __ldcg(ip + 1);
+                        const int2 cv = __ldcg(reinterpret_cast<const int2*>(ip + 2));
+                        it.col = cv.x; it.v = cv.y;
                         PubStage& s = stage[tid];
                         const double mdb = -it.mave;                   // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
                         s.v[0] = (mdb * 1.0 + 0.0) * it.lam;
@@ -741,6 +745,17 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 #define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
+    if (p.xflags != nullptr) {                            // peer-memory exchange: every GPU's list of the previous step has landed
+        if (tid < p.pG) {
+            const volatile unsigned long long* f = p.xflags + tid;
+            for (uint32_t spins = 0; *f < p.wait_seq; ++spins) {
+                __nanosleep(100);
+                if (spins > (1u << 24)) __trap();          // a lost peer must surface as an error, not as a hung GPU
+            }
+        }
+        __threadfence();
+        __syncthreads();
+    }
     if (p.pG * p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     GMRM_TICK()                                           // [8] prologue + update phase
@@ -993,6 +1008,20 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
             base += s_total;
         }
         if (tid == 0) *reinterpret_cast<int32_t*>(list) = base;
+        if (p.world > 1 && p.peer_list[0] != nullptr) {          // push header + items into every peer's copy (NVLink stores)
+            __syncthreads();
+            const int nd = 2 + 3 * base;
+            for (int g = 0; g < p.world; g++) {
+                if (g == p.rank) continue;
+                double* dst = p.peer_list[g] + (size_t)t * publist_doubles(p.V);
+                for (int i = tid; i < nd; i += 128) dst[i] = list[i];
+            }
+        }
+    }
+    if (p.world > 1 && p.peer_list[0] != nullptr) {
+        __threadfence_system();                              // the lists are visible to the peers before the flags
+        __syncthreads();
+        if (tid < p.world) *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
     }
     if (tid == 0) *p.ticket = 0u;
 }

@@ -53,6 +53,8 @@ struct StepParams {
     // (peer memory over NVLink when g is not this GPU)
     int32_t pG, pV;                      // lists, capacity of a list (0 lists: nothing pending)
     const double* plist;                 // [pG][Ttot][publist_doubles(pV)]
+    const unsigned long long* xflags;    // [pG] or nullptr: wait until every list's flag has reached wait_seq
+    unsigned long long wait_seq;
     const uint8_t* pbed[kMaxGpus];
     const uint32_t* pmiss_off[kMaxGpus];
     const uint32_t* pmiss_idx[kMaxGpus];
@@ -91,6 +93,12 @@ struct SampleParams {
     PubEntry* pub;           // [V][T] scratch: every marker's entry (lam == 0: nothing published)
     double* plist;           // [T][publist_doubles(V)] this GPU's compacted list (written by the last CTA to finish)
     unsigned int* ticket;    // CTA counter for that, zero between launches
+    // peer-memory exchange (world > 1): the last CTA also stores the list into every peer's buffer over NVLink and
+    // then raises this GPU's flag there to `seq`
+    int32_t world, rank;
+    double* peer_list[kMaxGpus];                 // where GPU g wants THIS GPU's list (nullptr: no exchange)
+    unsigned long long* peer_flag[kMaxGpus];     // this GPU's flag in GPU g's flag array
+    unsigned long long seq;
     const double* rep_u;     // replay: [Mm][R][T] or nullptr
     const double* rep_z;
     int32_t* err;            // device error flag

@@ -160,13 +160,15 @@ int gmrm_set_timing_detail(gmrm_engine* e, int32_t on);
 int gmrm_comm_unique_id(uint8_t id[128]);
 int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]);
 /* Exchange at sync_rate 1 (replaces Allgather(bool) + Allgatherv(dbetas) + Allgatherv(bed column), bayes.cpp:500-545):
- * the GPUs all-gather their published (dbeta*msig, mave) lists and every GPU applies every update itself, reading the
- * other shards' columns over NVLink peer memory.  After gmrm_finalize_bed each engine exports its buffers and
- * imports every peer's -- as CUDA IPC handles across processes (3 x 64 bytes), or as pointers inside one process. */
-int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[192]);
-int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[192]);
-int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[3]);
-int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[3]);
+ * the sampler kernel of every GPU pushes its compacted list of published (dbeta*msig, mave, column) items into the
+ * peers' buffers over NVLink and raises a flag there; every GPU then applies every update itself, reading the other
+ * shards' columns from peer memory.  After gmrm_finalize_bed each engine exports its buffers (genotypes, missing
+ * lists, list buffer, flags) and imports every peer's -- as CUDA IPC handles across processes (5 x 64 bytes), or as
+ * pointers inside one process.  GMRM_EXCHANGE=nccl falls back to an NCCL all-gather of the lists. */
+int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[320]);
+int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[320]);
+int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[5]);
+int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[5]);
 
 #ifdef __cplusplus
 }
