@@ -220,8 +220,9 @@ class Engine:
         _check(lib().gmrm_get_timing(self._h, C.byref(tm)))
         return {k: getattr(tm, k) for k, _ in Timing._fields_}
 
-    def set_timing_detail(self, on: bool):
-        _check(lib().gmrm_set_timing_detail(self._h, int(on)))
+    def set_timing_detail(self, level):
+        """0: iteration totals; 1: + step-kernel time (2 events per step); 2: every phase (6 events per step)."""
+        _check(lib().gmrm_set_timing_detail(self._h, int(level)))
 
     def export_buffers(self) -> bytes:
         buf = (C.c_uint8 * 320)()

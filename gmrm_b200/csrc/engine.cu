@@ -158,7 +158,7 @@ struct gmrm_engine {
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> dot_ev;
-    bool timing_detail = false;
+    int timing_detail = 0;           // 0: iteration totals only; 1: + the step kernel (2 events per step); 2: every phase (6 events per step)
     gmrm_timing last{};
 
     ~gmrm_engine() {
@@ -795,28 +795,28 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
             }
         }
         launch_sample(sp, s);
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
+        if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
         pend.any = true;
         e->pend_seq = e->xseq;
         const bool delta_exchange = multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
         if (e->list_exchange && !e->list_p2p) {
             NC(g_nccl.AllGather(own_list(e, e->xseq), lists_of(e, e->xseq), (size_t)T * publist_doubles(Vl), kNcclFloat64, e->comm, s));
-            if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
+            if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launches += 1;
         }
         if (delta_exchange || st == Mm - 1 || e->force_flush) {
             if ((rc = launch_step_all(e, nullptr, 0, pend, nullptr, &nl))) return rc;
             pend.any = false;
         }
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
+        if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 3], s));
         launches += nl + 1;
         if (delta_exchange) {
             NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
-            if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
+            if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, s);
             launches += 2;
         }
-        if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 4], s));
+        if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 4], s));
     }
     CU(cudaEventRecord(e->ev[2], s));
 
@@ -856,6 +856,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st], e->dot_ev[6 * st + 1]));
             e->last.dot_kernel_ms += ms;
+            if (e->timing_detail < 2) continue;
             CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 1], e->dot_ev[6 * st + 2]));
             e->last.sample_kernel_ms += ms;
             CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 2], e->dot_ev[6 * st + 3]));
@@ -919,7 +920,7 @@ int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out) {
 }
 int gmrm_set_timing_detail(gmrm_engine* e, int32_t on) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
-    e->timing_detail = on != 0;
+    e->timing_detail = on < 0 ? 0 : (on > 2 ? 2 : on);
     return GMRM_OK;
 }
 

@@ -154,7 +154,7 @@ int gmrm_get_betas(gmrm_engine* e, int32_t trait, double* betas);          /* sh
 int gmrm_get_components(gmrm_engine* e, int32_t trait, int32_t* comp);     /* shard-local, marker_count */
 int gmrm_get_epsilon(gmrm_engine* e, int32_t trait, double* eps);          /* N doubles */
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out);
-int gmrm_set_timing_detail(gmrm_engine* e, int32_t on);
+int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step) */
 
 /* --- multi-GPU (one process per GPU): rank 0 makes the id, the launcher broadcasts it. */
 int gmrm_comm_unique_id(uint8_t id[128]);
