@@ -953,7 +953,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
     const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (v < p.V) sample_one(p, v, lane);
     __shared__ bool last;
-    __threadfence();                                         // this thread's pub entry is visible device-wide ...
+    if (lane < p.T) __threadfence();                         // the lanes that wrote a pub entry make it visible device-wide ...
     __syncthreads();
     if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;   // ... before the CTA takes its ticket
     __syncthreads();
