@@ -221,6 +221,31 @@ def test_replay_live_reference(api, oracle, tmp_path, N, M, T, G, R, nsm):
     check_traj(hist, res, 1e-8)
 
 
+def test_replay_c2_full_size_first_10_iterations(api, oracle, tmp_path):
+    """BASELINE.json config C2 at full size (N=20,000, M=50,000, 1 trait, 1 group): the reference binary runs 10
+    iterations with 64 ranks on this host, its logged variates are replayed through the GPU path with 64 virtual
+    ranks, and the beta / sigma / pi trajectories must agree to 1e-6 relative (the north-star bound; observed ~1e-11)."""
+    if not oracle.have_reference():
+        pytest.skip("oracle/_ref/gmrm_ref not present")
+    N, M, R, iters = 20000, 50000, 64, 10
+    inp = make_case(oracle, tmp_path, N=N, M=M, T=1, G=1, missing_rate=0.001, seed=21)
+    p = inp["paths"]
+    log = str(tmp_path / "log")
+    oracle.run_reference(str(tmp_path), p["bed"], p["dim"], p["phen"], p["gri"], p["grm"], str(tmp_path / "out"),
+                         iterations=iters, seed=171014, nranks=R, log_dir=log, timeout=2400)
+    res = oracle.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=N, R=R,
+                       iterations=iters, rng_mode=0, replay_dir=log)
+    hist, _ = run_replay(api, inp, res, R, iters)
+    check_traj(hist, res, 1e-6)
+    # and against the reference's own output files
+    stem = os.path.splitext(os.path.basename(p["phen"][0]))[0]
+    _, bet = oracle.read_bet(str(tmp_path / "out" / (stem + ".bet")))
+    _, cpn = oracle.read_cpn(str(tmp_path / "out" / (stem + ".cpn")))
+    for i in range(iters):
+        assert np.array_equal(hist[i]["comp"][0], cpn[i])
+        np.testing.assert_allclose(hist[i]["betas"][0], bet[i], rtol=1e-6, atol=1e-12)
+
+
 # ------------------------------------------------------------------ production (Philox) streams
 @pytest.mark.parametrize("N,M,T,G,R,nsm", [(2000, 500, 1, 1, 1, 1), (4100, 900, 2, 2, 32, 2), (20000, 3000, 1, 1, 128, 0)])
 def test_production_streams_match_oracle(api, oracle, tmp_path, N, M, T, G, R, nsm):
