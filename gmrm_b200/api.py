@@ -80,6 +80,27 @@ def _bp(a):
     return a.ctypes.data_as(_BP)
 
 
+def host_array(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array in pinned host memory (gmrm_host_alloc): upload_bed from it runs at DMA speed.  The memory lives
+    as long as the array (and its views) do."""
+    L = lib()
+    L.gmrm_host_alloc.restype = C.c_void_p
+    L.gmrm_host_alloc.argtypes = [C.c_size_t]
+    L.gmrm_host_free.restype = None
+    L.gmrm_host_free.argtypes = [C.c_void_p]
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.gmrm_host_alloc(n)
+    if not p:
+        raise GmrmError(f"gmrm_host_alloc({n}) failed: {L.gmrm_last_error().decode()}")
+
+    class _Owner:
+        def __del__(self, p=p, L=L):
+            L.gmrm_host_free(p)
+    buf = (C.c_uint8 * n).from_address(p)
+    buf._owner = _Owner()
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     _check(lib().gmrm_comm_unique_id(buf))

@@ -118,7 +118,9 @@ struct gmrm_engine {
     std::vector<double> h_cva;
     std::vector<int32_t> h_nonas;
 
-    DevBuf<uint8_t> bed, mask4, stage;
+    DevBuf<uint8_t> bed, mask4, stage, stage2;     // stage/stage2: double-buffered PLINK staging of gmrm_upload_bed
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old;
     DevBuf<double> delta, delta_tot, gc;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
@@ -166,6 +168,9 @@ struct gmrm_engine {
         for (auto& g : ipc_opened) for (void* q : g) if (q) cudaIpcCloseMemHandle(q);
         for (auto& c : miss_chunks) delete c.idx;
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& x : ev_h2d) if (x) cudaEventDestroy(x);
+        for (auto& x : ev_free) if (x) cudaEventDestroy(x);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto& e : dot_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -304,17 +309,18 @@ static int ensure_stage(gmrm_engine* e, size_t bytes) {
 }
 
 static int chunk_markers(const gmrm_engine* e) {
-    const size_t budget = 256u << 20;
+    size_t budget = 256u << 20;
+    if (const char* v = getenv("GMRM_STAGE_MB")) budget = (size_t)std::max(1, atoi(v)) << 20;   // staging chunk size (tests use a small one)
     size_t n = budget / (size_t)e->L.mbytes;
     return (int)std::max<size_t>(1, std::min<size_t>(n, 65535));   // grid.y limit
 }
 
 // PLINK bytes of markers [lb, lb+n) (shard-local) sit in e->stage: transcode them into the HBM layout and
 // collect their missing-genotype lists.
-static int ingest_staged(gmrm_engine* e, int lb, int n) {
+static int ingest_staged(gmrm_engine* e, const uint8_t* staged, int lb, int n) {
     if (e->miss_cnt.n < (size_t)n + 1) { int rc = e->miss_cnt.alloc((size_t)n + 1); if (rc) return rc; }
     CU(cudaMemsetAsync(e->miss_cnt.p, 0, ((size_t)n + 1) * 4, e->stream));
-    launch_transcode(e->stage.p, n, e->L, e->bed.p + (size_t)lb * e->L.col_stride, e->miss_cnt.p, e->stream);
+    launch_transcode(staged, n, e->L, e->bed.p + (size_t)lb * e->L.col_stride, e->miss_cnt.p, e->stream);
     CU(cudaGetLastError());
     gmrm_engine::MissChunk ch;
     ch.begin = lb; ch.count = n; ch.cnt.resize(n);
@@ -342,7 +348,7 @@ static int ingest_staged(gmrm_engine* e, int lb, int n) {
         int rc = ch.idx->alloc(tot);
         if (rc) { delete ch.idx; return rc; }
         CU(cudaMemcpyAsync(e->miss_cnt.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
-        launch_fill_missing(e->stage.p, n, e->L, e->miss_cnt.p, ch.idx->p, e->stream);
+        launch_fill_missing(staged, n, e->L, e->miss_cnt.p, ch.idx->p, e->stream);
         CU(cudaGetLastError());
         CU(cudaStreamSynchronize(e->stream));
     }
@@ -356,15 +362,37 @@ int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, in
         return fail(GMRM_EINVAL, "markers [%d, %d) outside this shard [%d, %d)", marker_begin, marker_begin + marker_count,
                     e->marker_begin, e->marker_begin + e->Mloc);
     CU(cudaSetDevice(e->cfg.device));
+    // Two device staging buffers: the H2D copy of chunk k+1 (own stream) overlaps the transcode and the missing-list
+    // pass of chunk k.  With a pinned host buffer (gmrm_host_alloc) the copies are true DMA at PCIe speed; a pageable
+    // one is staged by the driver and the calls simply serialise.
     const int chunk = chunk_markers(e);
-    int rc = ensure_stage(e, (size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes);
+    const size_t stage_bytes = (((size_t)std::min(chunk, std::max(marker_count, 1)) * e->L.mbytes) + 15) & ~(size_t)15;
+    int rc = ensure_stage(e, stage_bytes);
     if (rc) return rc;
-    e->bed_final = false;
-    for (int done = 0; done < marker_count; done += chunk) {
-        const int n = std::min(chunk, marker_count - done);
-        CU(cudaMemcpyAsync(e->stage.p, bed + (size_t)done * e->L.mbytes, (size_t)n * e->L.mbytes, cudaMemcpyHostToDevice, e->stream));
-        if ((rc = ingest_staged(e, marker_begin - e->marker_begin + done, n))) return rc;   // syncs: the staging buffer is reused
+    if (marker_count > chunk && e->stage2.n < stage_bytes && (rc = e->stage2.alloc(stage_bytes))) return rc;
+    if (!e->copy_stream) {
+        CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) { CU(cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&e->ev_free[i], cudaEventDisableTiming)); }
     }
+    e->bed_final = false;
+    uint8_t* stg[2] = {e->stage.p, e->stage2.p};
+    const int nchunks = (marker_count + chunk - 1) / chunk;
+    auto issue_h2d = [&](int k) -> int {
+        const int done = k * chunk, n = std::min(chunk, marker_count - done);
+        if (k >= 2) CU(cudaStreamWaitEvent(e->copy_stream, e->ev_free[k & 1], 0));          // the buffer's previous chunk has been ingested
+        CU(cudaMemcpyAsync(stg[k & 1], bed + (size_t)done * e->L.mbytes, (size_t)n * e->L.mbytes, cudaMemcpyHostToDevice, e->copy_stream));
+        CU(cudaEventRecord(e->ev_h2d[k & 1], e->copy_stream));
+        return 0;
+    };
+    if (nchunks > 0 && (rc = issue_h2d(0))) return rc;
+    for (int k = 0; k < nchunks; k++) {
+        const int done = k * chunk, n = std::min(chunk, marker_count - done);
+        if (k + 1 < nchunks && (rc = issue_h2d(k + 1))) return rc;
+        CU(cudaStreamWaitEvent(e->stream, e->ev_h2d[k & 1], 0));
+        if ((rc = ingest_staged(e, stg[k & 1], marker_begin - e->marker_begin + done, n))) return rc;   // ends with a stream sync
+        CU(cudaEventRecord(e->ev_free[k & 1], e->stream));
+    }
+    CU(cudaStreamSynchronize(e->copy_stream));
     return GMRM_OK;
 }
 
@@ -378,7 +406,7 @@ int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_h
     for (int done = 0; done < e->Mloc; done += chunk) {
         const int n = std::min(chunk, e->Mloc - done);
         launch_generate_plink(e->stage.p, n, e->marker_begin + done, e->L, seed, maf_lo, maf_hi, missing_rate, e->stream);
-        if ((rc = ingest_staged(e, done, n))) return rc;
+        if ((rc = ingest_staged(e, e->stage.p, done, n))) return rc;
     }
     return GMRM_OK;
 }
@@ -399,7 +427,7 @@ int gmrm_finalize_bed(gmrm_engine* e) {
     for (auto& c : e->miss_chunks)
         if (c.total) CU(cudaMemcpyAsync(e->miss_idx.p + off[c.begin], c.idx->p, c.total * 4, cudaMemcpyDeviceToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    e->stage.free();
+    e->stage.free(); e->stage2.free();
     e->bed_final = true;
     e->stats_done = false;
     return GMRM_OK;
@@ -941,6 +969,16 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&e->comm, e->cfg.world_size, u, e->cfg.world_rank));
     return GMRM_OK;
+}
+
+// Pinned host memory for gmrm_upload_bed sources (true asynchronous DMA) and output buffers.
+void* gmrm_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); fail(GMRM_ENOMEM, "cudaHostAlloc of %zu bytes failed", bytes); return nullptr; }
+    return p;
+}
+void gmrm_host_free(void* p) {
+    if (p) cudaFreeHost(p);
 }
 
 // Buffers the other GPUs read in the list exchange: genotypes, missing-list offsets and indices.  Call after

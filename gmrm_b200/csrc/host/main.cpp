@@ -71,12 +71,15 @@ void worker(int rank, Shared* sh, Barrier* bar) {
     {
         host::BedReader bed(o.bed_file, N);
         const int chunk = std::max(1, (int)((256u << 20) / (size_t)bed.mbytes()));
-        std::vector<uint8_t> buf((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
+        // pinned read buffer: the upload is then plain DMA (gmrm_host_alloc, include/gmrm_b200.h)
+        uint8_t* buf = (uint8_t*)gmrm_host_alloc((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
+        if (!buf) ck(-4, "gmrm_host_alloc");
         for (int done = 0; done < M; done += chunk) {
             const int n = std::min(chunk, M - done);
-            bed.read(S + done, n, buf.data());
-            ck(gmrm_upload_bed(e, buf.data(), S + done, n), "gmrm_upload_bed");
+            bed.read(S + done, n, buf);
+            ck(gmrm_upload_bed(e, buf, S + done, n), "gmrm_upload_bed");
         }
+        gmrm_host_free(buf);
         ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
     }
     if (ngpu > 1 && o.sync_rate == 1) {      // list exchange: the shards read each other's columns over NVLink

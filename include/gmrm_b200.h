@@ -111,6 +111,10 @@ int gmrm_shard_info(const gmrm_engine* e, int32_t* marker_begin, int32_t* marker
  * index; the range must lie inside this engine's shard.  May be called repeatedly with chunks.
  * The bytes are copied to the device and transcoded there into the tile-planar layout. */
 int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, int32_t marker_count);
+/* Pinned host memory: a gmrm_upload_bed source allocated here is copied by DMA, chunk k+1 overlapping the transcode
+ * of chunk k (.bed ingestion at 114 GB).  Any other host pointer works too, more slowly. */
+void* gmrm_host_alloc(size_t bytes);
+void gmrm_host_free(void* p);
 /* Synthetic genotypes generated ON the device (MAF ~ U(maf_lo, maf_hi) per marker,
  * Binomial(2, p) dosages, optional missing), through the same transcode as gmrm_upload_bed. */
 int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_hi, double missing_rate);
