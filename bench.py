@@ -241,13 +241,21 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     d2h = 0
+    staged = False
     for _ in range(args.steps):
         it += 1
         e.run_iteration(it)
+        if staged:                                   # outputs of the previous iteration: their copy ran under this one
+            for t in range(T):
+                bb, cc = e.fetch_outputs(t)
+                d2h += bb.nbytes + cc.nbytes
         st = e.state()
         d2h += sum(v.nbytes for v in st.values())
-        for t in range(T):
-            d2h += e.betas(t).nbytes + e.components(t).nbytes
+        e.stage_outputs()
+        staged = True
+    for t in range(T):
+        bb, cc = e.fetch_outputs(t)
+        d2h += bb.nbytes + cc.nbytes
     barrier()
     e2e_s = maxreduce((time.perf_counter() - t1) / args.steps)
     st = e.state()
@@ -285,7 +293,8 @@ def run_ours(args):
                                                  f"per step ({1e3 * dev2_ms / steps_per_it:.1f} us per step in that pass)"}},
             "e2e": {"value": M * T / e2e_s, "unit": "marker-updates/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": d2h // args.steps,
-                    "note": "per-iteration call through the C ABI (gmrm_run_iteration) + read-back of betas/components/state to host "
+                    "note": "per-iteration call through the C ABI (gmrm_run_iteration) + read-back of betas/components (staged: device "
+                            "snapshot, pinned D2H on a second stream, fetched one iteration later) and state to host "
                             "buffers (what the reference writes to .bet/.cpn/.csv); an iteration has no host inputs: genotypes and "
                             "phenotypes are uploaded once per run (config.upload_bed_gbs is that path's measured rate)"},
             "gpu_launches": int(launches),

@@ -231,6 +231,14 @@ class Engine:
         _check(lib().gmrm_get_components(self._h, t, _ip(out)))
         return out
 
+    def stage_outputs(self):
+        _check(lib().gmrm_stage_outputs(self._h))
+
+    def fetch_outputs(self, t: int):
+        b = np.empty(self.marker_count); c = np.empty(self.marker_count, dtype=np.int32)
+        _check(lib().gmrm_fetch_outputs(self._h, t, _dp(b), _ip(c)))
+        return b, c
+
     def epsilon(self, t: int) -> np.ndarray:
         out = np.empty(self.N)
         _check(lib().gmrm_get_epsilon(self._h, t, _dp(out)))

@@ -120,6 +120,12 @@ struct gmrm_engine {
 
     DevBuf<uint8_t> bed, mask4, stage, stage2;     // stage/stage2: double-buffered PLINK staging of gmrm_upload_bed
     cudaStream_t copy_stream = nullptr;
+    // output staging: betas/components of an iteration are snapshotted on the device and copied to
+    // pinned host memory on the copy stream while the next iteration runs
+    DevBuf<double> out_betas; DevBuf<int32_t> out_comp;
+    double* h_out_betas = nullptr; int32_t* h_out_comp = nullptr;
+    cudaEvent_t ev_staged = nullptr, ev_out = nullptr;
+    bool out_pending = false;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old;
     DevBuf<double> delta, delta_tot, gc;
@@ -171,6 +177,10 @@ struct gmrm_engine {
         for (auto& x : ev_h2d) if (x) cudaEventDestroy(x);
         for (auto& x : ev_free) if (x) cudaEventDestroy(x);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_staged) cudaEventDestroy(ev_staged);
+        if (ev_out) cudaEventDestroy(ev_out);
+        if (h_out_betas) cudaFreeHost(h_out_betas);
+        if (h_out_comp) cudaFreeHost(h_out_comp);
         for (auto& e : dot_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -939,6 +949,43 @@ int gmrm_get_epsilon(gmrm_engine* e, int32_t t, double* eps) {
     if (!e || !eps || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
     CU(cudaSetDevice(e->cfg.device));
     CU(cudaMemcpy(eps, e->eps.p + (size_t)t * e->L.npad, (size_t)e->cfg.N * 8, cudaMemcpyDeviceToHost));
+    return GMRM_OK;
+}
+// Asynchronous read-back of an iteration's betas / components (what .bet / .cpn record, bayes.cpp:666-667):
+// gmrm_stage_outputs snapshots them on the device and starts the device-to-host copy on a second stream;
+// gmrm_fetch_outputs waits for that copy and hands the values out.  Calling run_iteration in between overlaps the
+// copy with the next iteration.
+int gmrm_stage_outputs(gmrm_engine* e) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    const size_t n = (size_t)e->cfg.T * e->Mloc;
+    if (!e->ev_staged) {
+        int rc = e->out_betas.alloc(n); if (rc) return rc;
+        rc = e->out_comp.alloc(n); if (rc) return rc;
+        CU(cudaHostAlloc((void**)&e->h_out_betas, n * 8, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&e->h_out_comp, n * 4, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&e->ev_staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+        if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    }
+    if (e->out_pending) CU(cudaEventSynchronize(e->ev_out));          // the previous snapshot's copy still owns the buffers
+    CU(cudaMemcpyAsync(e->out_betas.p, e->betas.p, n * 8, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->out_comp.p, e->comp.p, n * 4, cudaMemcpyDeviceToDevice, e->stream));
+    CU(cudaEventRecord(e->ev_staged, e->stream));
+    CU(cudaStreamWaitEvent(e->copy_stream, e->ev_staged, 0));
+    CU(cudaMemcpyAsync(e->h_out_betas, e->out_betas.p, n * 8, cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(cudaMemcpyAsync(e->h_out_comp, e->out_comp.p, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    CU(cudaEventRecord(e->ev_out, e->copy_stream));
+    e->out_pending = true;
+    return GMRM_OK;
+}
+int gmrm_fetch_outputs(gmrm_engine* e, int32_t t, double* betas, int32_t* comp) {
+    if (!e || t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "bad argument");
+    if (!e->out_pending) return fail(GMRM_EINVAL, "no staged outputs: call gmrm_stage_outputs first");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventSynchronize(e->ev_out));
+    if (betas) memcpy(betas, e->h_out_betas + (size_t)t * e->Mloc, (size_t)e->Mloc * 8);
+    if (comp) memcpy(comp, e->h_out_comp + (size_t)t * e->Mloc, (size_t)e->Mloc * 4);
     return GMRM_OK;
 }
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out) {

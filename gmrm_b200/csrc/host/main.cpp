@@ -108,9 +108,30 @@ void worker(int rank, Shared* sh, Barrier* bar) {
     std::vector<int32_t> m0((size_t)T * G), cass((size_t)T * G * K), comp(M);
     std::vector<std::vector<double>> bmean(T, std::vector<double>(o.burn_in < o.iterations ? M : 0, 0.0));
     gmrm_state st{sigmag.data(), sigmae.data(), pi.data(), mu.data(), m0.data(), cass.data()};
+    // betas / components leave the GPU through the staged path (gmrm_stage_outputs): their copy to pinned host memory
+    // runs under the next iteration, and the files of iteration i are written after iteration i+1 has been enqueued
+    struct PendingOut { unsigned it = 0; bool save = false, mean = false; std::vector<double> sigmag, pi; std::vector<double> sigmae; std::vector<int32_t> m0; } po;
+    auto write_pending = [&]() {
+        if (!po.it) return;
+        for (int t = 0; t < T; t++) {
+            ck(gmrm_fetch_outputs(e, t, betas.data(), comp.data()), "gmrm_fetch_outputs");
+            if (po.mean) for (int j = 0; j < M; j++) bmean[t][j] += betas[j];
+            if (!po.save) continue;
+            const unsigned nthinned = po.it / o.thin - 1;                                          // bayes.cpp:660
+            if (rank == 0) {
+                int m0_sum = 0;
+                for (int g = 0; g < G; g++) m0_sum += po.m0[(size_t)t * G + g];
+                outs[t]->write_csv(po.it, nthinned, &po.sigmag[(size_t)t * G], G, po.sigmae[t], m0_sum, &po.pi[(size_t)t * G * K], K);
+            }
+            outs[t]->write_bet((unsigned)Mt, po.it, nthinned, S, M, betas.data(), rank == 0);
+            outs[t]->write_cpn((unsigned)Mt, po.it, nthinned, S, M, comp.data(), rank == 0);
+        }
+        po.it = 0;
+    };
     for (unsigned it = 1; it <= o.iterations; it++) {
         const double ts = now();
         ck(gmrm_run_iteration(e, (int32_t)it, nullptr), "gmrm_run_iteration");
+        write_pending();                                     // iteration it-1: its copy has had a whole iteration
         ck(gmrm_get_state(e, &st), "gmrm_get_state");
         gmrm_timing tm{};
         gmrm_get_timing(e, &tm);
@@ -122,22 +143,13 @@ void worker(int rank, Shared* sh, Barrier* bar) {
             }
         if (rank == 0) printf("RESULT : It %d  total proc time = %7.3f sec, with sync time = %7.3f\n", it, now() - ts, tm.exchange_ms * 1e-3);   // bayes.cpp:655
         const bool save = it % o.thin == 0, mean = it > o.burn_in && !bmean[0].empty();
-        if (save || mean)
-            for (int t = 0; t < T; t++) {
-                ck(gmrm_get_betas(e, t, betas.data()), "gmrm_get_betas");
-                if (mean) for (int j = 0; j < M; j++) bmean[t][j] += betas[j];
-                if (!save) continue;
-                const unsigned nthinned = it / o.thin - 1;                                             // bayes.cpp:660
-                ck(gmrm_get_components(e, t, comp.data()), "gmrm_get_components");
-                if (rank == 0) {
-                    int m0_sum = 0;
-                    for (int g = 0; g < G; g++) m0_sum += m0[(size_t)t * G + g];
-                    outs[t]->write_csv(it, nthinned, &sigmag[(size_t)t * G], G, sigmae[t], m0_sum, &pi[(size_t)t * G * K], K);
-                }
-                outs[t]->write_bet((unsigned)Mt, it, nthinned, S, M, betas.data(), rank == 0);
-                outs[t]->write_cpn((unsigned)Mt, it, nthinned, S, M, comp.data(), rank == 0);
-            }
+        if (save || mean) {
+            ck(gmrm_stage_outputs(e), "gmrm_stage_outputs");
+            po.it = it; po.save = save; po.mean = mean;
+            po.sigmag = sigmag; po.sigmae = sigmae; po.pi = pi; po.m0 = m0;
+        }
     }
+    write_pending();
     // ---- superset: posterior means of beta over the iterations after --burn-in, <stem>.mbet (Mt doubles)
     if (o.burn_in > 0 && o.burn_in < o.iterations)
         for (int t = 0; t < T; t++) {

@@ -157,6 +157,11 @@ int gmrm_get_state(gmrm_engine* e, gmrm_state* out);
 int gmrm_get_betas(gmrm_engine* e, int32_t trait, double* betas);          /* shard-local, marker_count */
 int gmrm_get_components(gmrm_engine* e, int32_t trait, int32_t* comp);     /* shard-local, marker_count */
 int gmrm_get_epsilon(gmrm_engine* e, int32_t trait, double* eps);          /* N doubles */
+/* Asynchronous variant of get_betas / get_components (output staging for thin-rate-1 runs):
+ * stage = device snapshot + device-to-host copy on a second stream into pinned memory; fetch = wait + hand out.
+ * A gmrm_run_iteration between the two overlaps the copy with the next iteration. */
+int gmrm_stage_outputs(gmrm_engine* e);
+int gmrm_fetch_outputs(gmrm_engine* e, int32_t trait, double* betas, int32_t* comp);
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out);
 int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step) */
 

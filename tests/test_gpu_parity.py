@@ -289,6 +289,27 @@ def test_production_streams_match_oracle(api, oracle, tmp_path, N, M, T, G, R, n
     check_traj(hist, res, 1e-8)
 
 
+def test_staged_outputs_equal_direct_reads(api, oracle, tmp_path):
+    """gmrm_stage_outputs / gmrm_fetch_outputs (asynchronous read-back overlapped with the next iteration) hand out
+    exactly what gmrm_get_betas / gmrm_get_components returned for the staged iteration."""
+    inp = make_case(oracle, tmp_path, N=3001, M=640, T=2, G=2, na_rate=0.01, missing_rate=0.005, seed=5)
+    e = engine_for(api, inp, vranks=16, seed=11)
+    e.init_chain(None)
+    prev = None
+    for i in range(4):
+        e.run_iteration(i + 1)
+        if prev is not None:                              # staged after iteration i, fetched after iteration i+1 ran
+            for t in range(2):
+                b, c = e.fetch_outputs(t)
+                assert np.array_equal(b, prev[t][0]) and np.array_equal(c, prev[t][1])
+        prev = [(e.betas(t), e.components(t)) for t in range(2)]
+        e.stage_outputs()
+    for t in range(2):
+        b, c = e.fetch_outputs(t)
+        assert np.array_equal(b, prev[t][0]) and np.array_equal(c, prev[t][1])
+    e.close()
+
+
 def test_posterior_recovers_simulated_effects(api, oracle, tmp_path):
     """Long-ish chain on simulated data (data_sim.R recipe): posterior means of the GPU chain and of the
     oracle chain (different seeds) agree within Monte Carlo error, and h2 lands near the simulated 0.5."""
