@@ -416,6 +416,9 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                         s.v[3] = 0.0;
                         info[tid].col = it.col;
                         info[tid].nmiss_g = (uint32_t)g;               // the missing count is filled in with the column bytes below
+                    } else if (tid < ((n + 7) & ~7)) {                 // pad the last group of 8 with no-op entries
+                        stage[tid].v[0] = stage[tid].v[1] = stage[tid].v[2] = stage[tid].v[3] = 0.0;
+                        info[tid].col = 0; info[tid].nmiss_g = 0u;
                     }
                     __syncthreads();
                     touched = true;
@@ -454,6 +457,28 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                                 if (g0 + j < n && have[qq]) by[j][qq] = bytes[(size_t)(g0 + j) * nq + q0 + qq * NT + tid];
                             }
                         const uint32_t gbase = stage_u32 + (uint32_t)g0 * 32u;   // 256-aligned: stage is, g0 is a multiple of 8
+                        // fast path (no entry of the group has missing genotypes): one branch-free block for the 8
+                        // entries -- padded entries are all-zero, unobserved / absent quads hit the zero slot -- so that
+                        // the look-ups of later entries are in flight while earlier ones are added
+                        uint32_t anymiss = 0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) anymiss |= info[g0 + j].nmiss_g >> 4;
+                        if (!anymiss) {
+#define GMRM_APPLY_FAST(J)                                                                                          \
+    _Pragma("unroll") for (int qq = 0; qq < 2; qq++) {                                                            \
+        uint32_t off;                                                                                             \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(lut_u32 + by[J][qq] * 4u));                      \
+        off |= nmask[qq];                                                                                         \
+        e[qq][0] += lds_f64_imm<J * 32>(byte_into<0>(off, gbase));   /* * na (phenotype.cpp:388) */               \
+        e[qq][1] += lds_f64_imm<J * 32>(byte_into<1>(off, gbase));                                                \
+        e[qq][2] += lds_f64_imm<J * 32>(byte_into<2>(off, gbase));                                                \
+        e[qq][3] += lds_f64_imm<J * 32>(byte_into<3>(off, gbase));                                                \
+    }
+                            GMRM_APPLY_FAST(0) GMRM_APPLY_FAST(1) GMRM_APPLY_FAST(2) GMRM_APPLY_FAST(3)
+                            GMRM_APPLY_FAST(4) GMRM_APPLY_FAST(5) GMRM_APPLY_FAST(6) GMRM_APPLY_FAST(7)
+#undef GMRM_APPLY_FAST
+                            continue;
+                        }
 #define GMRM_APPLY(J)                                                                                              \
     if (g0 + J < n) {                                                                                             \
         const uint32_t nmiss = info[g0 + J].nmiss_g >> 4, pgpu = info[g0 + J].nmiss_g & 15u;                      \
