@@ -19,7 +19,7 @@ struct Options {
     unsigned seed = 0, iterations = 1, truncm = 0, thin = 1;
     std::vector<double> S;
     // supersets (defaults reproduce the reference: one exchange per marker-step)
-    int vranks = 0;          // --vranks: total virtual ranks; 0 = 1024 per GPU
+    int vranks = 0;          // --vranks: total virtual ranks; 0 = 2048 per GPU
     int gpus = 1;            // --gpus: GPUs of this node sharing the chain (one host thread each)
     int sync_rate = 1;       // --sync-rate
     unsigned burn_in = 0;    // --burn-in: iterations left out of the posterior-mean summary (.mbet)

@@ -184,7 +184,7 @@ int main(int argc, char** argv) {
     printf("INFO   : Reading groups from %s.\n", o.group_index_file.c_str());
     sh.group_index = host::read_group_index_file(o.group_index_file, o.ngroups, sh.dims.Mt);
     // virtual ranks: the run is the reference under `mpirun -n vranks`
-    int vr = o.vranks > 0 ? o.vranks : 1024 * o.gpus;
+    int vr = o.vranks > 0 ? o.vranks : 2048 * o.gpus;   // default: 2,048 markers in flight per GPU (the benchmarked setting)
     if (vr > sh.dims.Mt) vr = sh.dims.Mt;
     vr -= vr % o.gpus;
     if (vr < o.gpus) {
