@@ -24,6 +24,8 @@ struct Options {
     int sync_rate = 1;       // --sync-rate
     unsigned burn_in = 0;    // --burn-in: iterations left out of the posterior-mean summary (.mbet)
     bool check_inputs = false;   // --check-inputs: parse everything, print a summary, no GPU work
+    std::string dump_inputs;     // --dump-inputs <dir>: with --check-inputs, write the parsed phenotypes / groups / mixtures as raw binaries (tests)
+    bool selftest_outputs = false;   // --selftest-outputs: with --check-inputs, write a fixed 2-iteration .csv/.bet/.cpn history from 2 "ranks" (tests)
     // derived from the .grm file
     int ngroups = 0, nmixtures = 0;
     std::vector<double> cva;     // [G][K]

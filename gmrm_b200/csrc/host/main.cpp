@@ -195,6 +195,36 @@ int main(int argc, char** argv) {
     printf("INFO   : %d GPU(s), %d virtual ranks (markers in flight per step), sync rate %d\n", o.gpus, vr, o.sync_rate);
     if (o.check_inputs) {
         for (const auto& p : sh.phens) printf("INFO   : %s: %d observed, %d NA\n", p.path.c_str(), p.nonas, p.nas);
+        if (!o.dump_inputs.empty()) {                    // raw dumps for the CPU parity tests of the readers
+            auto dump = [&](const std::string& name, const void* p, size_t n) {
+                FILE* f = fopen((o.dump_inputs + "/" + name).c_str(), "wb");
+                if (f) { fwrite(p, 1, n, f); fclose(f); }
+            };
+            for (size_t t = 0; t < sh.phens.size(); t++) {
+                dump("eps" + std::to_string(t) + ".f64", sh.phens[t].eps.data(), sh.phens[t].eps.size() * 8);
+                dump("mask" + std::to_string(t) + ".u8", sh.phens[t].mask4.data(), sh.phens[t].mask4.size());
+            }
+            dump("groups.i32", sh.group_index.data(), sh.group_index.size() * 4);
+            dump("cva.f64", o.cva.data(), o.cva.size() * 8);
+        }
+        if (o.selftest_outputs) {                        // the writers, exercised exactly as the iteration loop does from 2 ranks
+            const int G = o.ngroups, K = o.nmixtures, Mt = sh.dims.Mt, M0 = Mt / 2;
+            host::OutFiles r0(o.out_dir, "selftest", true), r1(o.out_dir, "selftest", false);
+            for (unsigned it = 1; it <= 4; it++) {
+                if (it % 2) continue;                    // thin rate 2: iterations 2 and 4
+                const unsigned nthinned = it / 2 - 1;
+                std::vector<double> sg(G), pi((size_t)G * K), b(Mt);
+                std::vector<int32_t> c(Mt);
+                for (int g = 0; g < G; g++) sg[g] = 0.1 * (g + 1) + 0.001 * it;
+                for (int i = 0; i < G * K; i++) pi[i] = (i + 1.0) / (G * K * 10.0) + 1e-4 * it;
+                for (int j = 0; j < Mt; j++) { b[j] = 1e-3 * j - 0.5 * it; c[j] = (j + it) % K; }
+                r0.write_csv(it, nthinned, sg.data(), G, 0.5 + 0.01 * it, 1234 + (int)it, pi.data(), K);
+                r0.write_bet((unsigned)Mt, it, nthinned, 0, M0, b.data(), true);
+                r1.write_bet((unsigned)Mt, it, nthinned, M0, Mt - M0, b.data() + M0, false);
+                r0.write_cpn((unsigned)Mt, it, nthinned, 0, M0, c.data(), true);
+                r1.write_cpn((unsigned)Mt, it, nthinned, M0, Mt - M0, c.data() + M0, false);
+            }
+        }
         printf("INFO   : inputs parsed; --check-inputs given, no GPU work\n");
         return 0;
     }

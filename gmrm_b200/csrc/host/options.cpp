@@ -134,6 +134,8 @@ Options parse_options(int argc, char** argv, int rank) {
         else if (!strcmp(a, "--sync-rate")) { o.sync_rate = (int)positive("--sync-rate", value_of(argc, argv, i), 1, "strictly positive"); ss << "--sync-rate " << o.sync_rate << "\n"; }
         else if (!strcmp(a, "--burn-in")) { o.burn_in = positive("--burn-in", value_of(argc, argv, i), 0, "positive"); ss << "--burn-in " << o.burn_in << "\n"; }
         else if (!strcmp(a, "--check-inputs")) { o.check_inputs = true; ss << "--check-inputs 1\n"; }
+        else if (!strcmp(a, "--dump-inputs")) { o.dump_inputs = value_of(argc, argv, i); ss << "--dump-inputs " << o.dump_inputs << "\n"; }
+        else if (!strcmp(a, "--selftest-outputs")) { o.selftest_outputs = true; ss << "--selftest-outputs 1\n"; }
         else if (!strcmp(a, "--gpus")) { o.gpus = (int)positive("--gpus", value_of(argc, argv, i), 1, "strictly positive"); ss << "--gpus " << o.gpus << "\n"; }
         else fatal(std::string("FATAL: option \"") + a + "\" unknown");
     }

@@ -43,6 +43,52 @@ def test_cli_echoes_options_and_counts_nas(data, oracle):
         assert f"{ph}: {int(inp['nonas'][t])} observed, {1003 - int(inp['nonas'][t])} NA" in r.stdout
 
 
+def test_cli_readers_match_oracle(data, oracle, tmp_path):
+    """.phen / .gri / .grm readers of the executable against the oracle's restatement of Phenotype::read_file
+    (phenotype.cpp:587-673), read_group_index_file (bayes.cpp:830-853) and read_group_mixture_file (options.cpp:222-286):
+    centred-scaled phenotypes to 1e-15, NA masks / groups / mixtures bit-exact."""
+    r = run(base_args(data, str(tmp_path / "o")) + ["--check-inputs", "--dump-inputs", str(tmp_path)])
+    assert r.returncode == 0, r.stdout + r.stderr
+    p = data["paths"]
+    inp = oracle.load_inputs(p["bed"], p["dim"], p["phen"], p["gri"], p["grm"])
+    for t in range(2):
+        eps = np.fromfile(tmp_path / f"eps{t}.f64")
+        mask = np.fromfile(tmp_path / f"mask{t}.u8", dtype=np.uint8)
+        assert np.array_equal(mask, inp["mask4"][t])
+        np.testing.assert_allclose(eps[: inp["N"]], inp["eps0"][t][: inp["N"]], rtol=0, atol=1e-15)
+        assert (eps[inp["N"]:] == 0).all()
+    assert np.array_equal(np.fromfile(tmp_path / "groups.i32", dtype=np.int32), inp["group_index"])
+    assert np.array_equal(np.fromfile(tmp_path / "cva.f64").reshape(inp["cva"].shape), inp["cva"])
+
+
+def test_cli_writers_produce_the_reference_layouts(data, oracle, tmp_path):
+    """.csv / .bet / .cpn writers (xfiles.cpp:17-45, xfiles.hpp:24-37) driven as the iteration loop drives them from two
+    ranks with thin rate 2; read back with the parsers that tests/test_oracle_golden.py pins on the reference's own files."""
+    out = tmp_path / "o"
+    r = run(base_args(data, str(out)) + ["--check-inputs", "--selftest-outputs"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    Mt, G, K = 300, 2, 4
+    its, bet = oracle.read_bet(str(out / "selftest.bet"))
+    its_c, cpn = oracle.read_cpn(str(out / "selftest.cpn"))
+    assert list(its) == [2, 4] and list(its_c) == [2, 4]
+    assert os.path.getsize(out / "selftest.bet") == 4 + 2 * (4 + 8 * Mt) and os.path.getsize(out / "selftest.cpn") == 4 + 2 * (4 + 4 * Mt)
+    j = np.arange(Mt)
+    for n, it in enumerate((2, 4)):
+        np.testing.assert_array_equal(bet[n], 1e-3 * j - 0.5 * it)
+        np.testing.assert_array_equal(cpn[n], (j + it) % K)
+    lines = open(out / "selftest.csv").read().splitlines()
+    assert len(lines) == 2 and len(set(len(x) for x in lines)) == 1                        # constant line length (xfiles.cpp:45)
+    for n, it in enumerate((2, 4)):
+        sg = [0.1 * (g + 1) + 0.001 * it for g in range(G)]
+        want = "%5d, %4d" % (it, G) + "".join(", %20.15f" % v for v in sg)
+        sige = 0.5 + 0.01 * it
+        want += ", %20.15f, %20.15f, %7d, %4d, %2d" % (sige, sum(sg) / (sige + sum(sg)), 1234 + it, G, K)
+        want += "".join(", %20.15f" % ((i + 1.0) / (G * K * 10.0) + 1e-4 * it) for i in range(G * K))
+        assert lines[n] == want
+    rows = oracle.read_csv(str(out / "selftest.csv"))
+    assert [r_["it"] for r_ in rows] == [2, 4] and rows[1]["m0_sum"] == 1238
+
+
 @pytest.mark.parametrize("args,msg", [(["--bogus", "1"], 'option "--bogus" unknown'),                       # options.cpp:152-155
                                       (["--iterations"], "missing argument for last option"),               # options.cpp:169-172
                                       (["--iterations", "0"], "strictly positive"),
