@@ -781,7 +781,9 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
             const volatile unsigned long long* f = p.xflags + tid;
             for (uint32_t spins = 0; *f < p.wait_seq; ++spins) {
                 __nanosleep(100);
-                if (spins > (1u << 24)) __trap();          // a lost peer must surface as an error, not as a hung GPU
+                // a lost peer must surface as an error, not as a hung GPU; the bound (>= 27 s) has to cover honest skew
+                // between the processes (first-launch module loading, a rank writing output files)
+                if (spins > (1u << 28)) __trap();
             }
         }
         __threadfence();
