@@ -1018,6 +1018,31 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
     return GMRM_OK;
 }
 
+// Test hook, no device needed: the step kernel's launch plan for (N, nsm, V, T) -- traits per launch, rows per pass,
+// passes, dynamic shared memory -- and, if `ranges` is given, the rows [start, start+count) every CTA owns in every pass
+// (ranges[(pass * nsm + cta) * 2 + {0,1}], room for 64 * nsm * 2 ints).
+int gmrm_debug_step_plan(int32_t N, int32_t nsm, int32_t V, int32_t T, int32_t* traits_per_launch, int32_t* rows_per_pass,
+                         int32_t* npass, int32_t* smem_bytes, int32_t* nrows, int32_t* ranges) {
+    if (N < 1 || nsm < 1 || V < 0 || T < 1) return fail(GMRM_EINVAL, "bad argument");
+    const Layout L = make_layout(N, nsm);
+    int tc = 0, rpp = 0;
+    step_plan(L, V, T, &tc, &rpp);
+    if (tc < 1 || rpp < 1) return fail(GMRM_EINVAL, "does not fit");
+    const int np = step_npass(L, rpp);
+    if (traits_per_launch) *traits_per_launch = tc;
+    if (rows_per_pass) *rows_per_pass = rpp;
+    if (npass) *npass = np;
+    if (smem_bytes) *smem_bytes = step_smem_bytes(L, V, tc, rpp);
+    if (nrows) *nrows = L.nrows;
+    if (ranges)
+        for (int c = 0; c < nsm; c++) {
+            int start[64], count[64];
+            host_pass_rows(L.nrows, np, nsm, c, start, count);
+            for (int q = 0; q < np; q++) { ranges[((size_t)q * nsm + c) * 2] = start[q]; ranges[((size_t)q * nsm + c) * 2 + 1] = count[q]; }
+        }
+    return GMRM_OK;
+}
+
 // Pinned host memory for gmrm_upload_bed sources (true asynchronous DMA) and output buffers.
 void* gmrm_host_alloc(size_t bytes) {
     void* p = nullptr;

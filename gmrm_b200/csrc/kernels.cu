@@ -249,9 +249,9 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // K1: one marker-step of one GPU -- apply the previous step's published updates, build the look-up
 // tables of this CTA's rows, stream the step's V columns through them (layout.h).
 //
-// One CTA per SM, 16 warps.  CTA c owns rows [row_begin(c), row_begin(c+1)) of every column and of the
-// residuals.  The rows are taken in passes of <= rows_per_pass rows (as many (row, trait) table slots as
-// shared memory holds):
+// One CTA per SM, 16 warps.  CTA c owns a short contiguous range of rows of every column and of the residuals in
+// each pass (all_pass_rows below), at most rows_per_pass rows (as many (row, trait) table slots as shared memory
+// holds).  Per CTA:
 //   update: every thread owns up to 2 quads of the CTA's rows per round; for each published marker of the
 //           previous step (rank order) it adds  v[dosage]  to its 4 residuals -- one PRMT + LDS.64 + DADD per
 //           individual, NA / missing individuals are routed to a zero entry
@@ -319,13 +319,19 @@ __device__ __forceinline__ void lookup_traits(double (&acc)[T], uint32_t a) {
 // ranges; `pr` lists them, local rows are numbered range after range.
 constexpr int kMaxPasses = 64;
 struct PassRows { int start[kMaxPasses], count[kMaxPasses], base[kMaxPasses]; int npass, total; };
-__device__ __forceinline__ void pass_rows(int nrows, int npass, int nsm, int cta, int q, int& start, int& count) {
-    const int lo = (int)((int64_t)nrows * q / npass), hi = (int)((int64_t)nrows * (q + 1) / npass), n = hi - lo;
-    // the CTAs that get the extra row of an uneven split differ from pass to pass (rotation), so that a CTA's total
-    // stays within one row of the average
-    const int c = (cta + q * (nsm / npass)) % nsm;
-    const int a = (int)((int64_t)n * c / nsm), b = (int)((int64_t)n * (c + 1) / nsm);
-    start = lo + a; count = b - a;
+// Pass q covers rows [nrows q/npass, nrows (q+1)/npass): n = every * nsm + extra rows, the first `extra` positions of the
+// split get one more.  Position 0 of a pass is the CTA after the last one served an extra row by the passes before it
+// (round robin), so a CTA's total over the step stays within one row of the average.
+__host__ __device__ __forceinline__ void all_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count) {
+    int lo = 0, first = 0;
+    for (int q = 0; q < npass; q++) {
+        const int hi = (int)((int64_t)nrows * (q + 1) / npass), n = hi - lo, every = n / nsm, extra = n % nsm;
+        const int c = (cta - first + nsm) % nsm;
+        start[q] = lo + c * every + (c < extra ? c : extra);
+        count[q] = every + (c < extra ? 1 : 0);
+        first = (first + extra) % nsm;
+        lo = hi;
+    }
 }
 __device__ __forceinline__ int global_row(const PassRows& pr, int local_row) {
     int q = 0;
@@ -348,8 +354,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
     long long tk = profme ? clock64() : 0;
     int nk = 40;
 #define GMRM_ATICK() if (profme && nk < 60) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
-    constexpr int NWALL = NT / 32;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int nr = pr.total, nq = nr * kRowBytes;       // quads of my rows
     // base-3 byte -> byte offsets (8 * dosage) of its four individuals into a PubStage
     for (int e = tid; e < kTabEntries; e += NT) {
@@ -613,7 +618,8 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         return (bb < nb && v < p.V) ? p.cols[v] : 0;
     };
     // register prefetch: Wn holds the next batch, Wn2 (GMRM_STEP_DEPTH == 2) the one after
-    uint32_t Wn[kPairs][NR], Wn2[kDepth == 2 ? kPairs : 1][NR];
+    uint32_t Wn[kPairs][NR];
+    [[maybe_unused]] uint32_t Wn2[kDepth == 2 ? kPairs : 1][NR];
     auto issue = [&](int c, uint32_t (&dst)[kPairs][NR]) {
 #pragma unroll
         for (int i = 0; i < kPairs; i++) {
@@ -635,7 +641,7 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
     constexpr int kLG = 32 / kBatch;
     const int pf_g = lane / kBatch;
     const int pf_off_a = (kLG == 4 && pf_g == 3) ? NR * kRowBytes - 1 : pf_g * 128, pf_off_b = kLG == 4 ? 1 << 20 : (pf_g ? NR * kRowBytes - 1 : 256);
-    const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
+    [[maybe_unused]] const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
     // pair whose total this lane ends up with
     const int own = kPairs == 8 ? ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1)
                   : kPairs == 4 ? ((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1) : ((l16 >> 3) & 1);
@@ -761,8 +767,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 
     if (tid == 0) {
         int tot = 0;
+        all_pass_rows(p.nrows, npass, nsm, cta, pr.start, pr.count);
         for (int q = 0; q < npass; q++) {
-            pass_rows(p.nrows, npass, nsm, cta, q, pr.start[q], pr.count[q]);
             pr.base[q] = tot;
             tot += pr.count[q];
         }
@@ -1216,6 +1222,8 @@ void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout&
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);
 }
+
+void host_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count) { all_pass_rows(nrows, npass, nsm, cta, start, count); }
 
 constexpr int kMaxDynSmem = 232448;   // 227 KB: the most one CTA can opt into on sm_100
 

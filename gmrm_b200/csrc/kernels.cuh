@@ -121,6 +121,7 @@ void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout&
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
 // dynamic shared memory the step kernel needs, or -1 if (V, T, rows_per_pass, rows per CTA) do not fit
 int step_npass(const Layout& L, int rows_per_pass);
+void host_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count);   // the kernel's row ownership [npass], for tests
 int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass);
 // traits per launch and rows per pass for a step of V markers (0 rows = does not fit)
 void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass);

@@ -165,6 +165,10 @@ int gmrm_fetch_outputs(gmrm_engine* e, int32_t trait, double* betas, int32_t* co
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out);
 int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step) */
 
+/* --- test hook without a device: launch plan of the step kernel and the rows each CTA owns in each pass */
+int gmrm_debug_step_plan(int32_t N, int32_t nsm, int32_t V, int32_t T, int32_t* traits_per_launch, int32_t* rows_per_pass,
+                         int32_t* npass, int32_t* smem_bytes, int32_t* nrows, int32_t* ranges);
+
 /* --- multi-GPU (one process per GPU): rank 0 makes the id, the launcher broadcasts it. */
 int gmrm_comm_unique_id(uint8_t id[128]);
 int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]);
