@@ -101,6 +101,22 @@ def host_array(shape, dtype=np.uint8) -> np.ndarray:
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
+def step_plan(N, nsm, V, T, want_ranges=True):
+    """gmrm_debug_step_plan (no device needed): the step kernel's launch plan for N individuals on nsm CTAs, V markers
+    per step and T traits, plus the rows [start, start+count) of every (pass, CTA).  None if the shape is refused."""
+    f = lib().gmrm_debug_step_plan
+    f.restype = C.c_int
+    f.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 5 + [C.c_void_p]
+    tc, rpp, npass, smem, nrows = (C.c_int32() for _ in range(5))
+    ranges = np.full(64 * max(nsm, 1) * 2, -1, dtype=np.int32)
+    rc = f(N, nsm, V, T, C.byref(tc), C.byref(rpp), C.byref(npass), C.byref(smem), C.byref(nrows),
+           ranges.ctypes.data if want_ranges else None)
+    if rc != 0:
+        return None
+    return dict(traits_per_launch=tc.value, rows_per_pass=rpp.value, npass=npass.value, smem_bytes=smem.value,
+                nrows=nrows.value, ranges=ranges[: npass.value * nsm * 2].reshape(npass.value, nsm, 2))
+
+
 def comm_unique_id() -> bytes:
     buf = (C.c_uint8 * 128)()
     _check(lib().gmrm_comm_unique_id(buf))

@@ -4,8 +4,6 @@ The dot product of Bayes::dot_product (src/bayes.cpp:709-770) is taken by CTAs t
 individuals in every pass; a row owned twice or not at all would be a silently wrong sum, so the ownership
 map is checked over many (N, CTA count) shapes: every row exactly once, at most rows_per_pass per CTA and
 pass, balanced to within one row over the whole step, and the plan inside the 227 KB shared-memory limit."""
-import ctypes as C
-
 import numpy as np
 import pytest
 
@@ -14,19 +12,12 @@ from gmrm_b200 import api
 MAX_DYN_SMEM = 232448
 
 
-def plan(N, nsm, V, T, want_ranges=True):
-    lib = api.lib()
-    f = lib.gmrm_debug_step_plan
-    f.restype = C.c_int
-    f.argtypes = [C.c_int32] * 4 + [C.POINTER(C.c_int32)] * 5 + [C.c_void_p]
-    tc, rpp, npass, smem, nrows = (C.c_int32() for _ in range(5))
-    ranges = np.full(64 * nsm * 2, -1, dtype=np.int32)
-    rc = f(N, nsm, V, T, C.byref(tc), C.byref(rpp), C.byref(npass), C.byref(smem), C.byref(nrows),
-           ranges.ctypes.data if want_ranges else None)
-    if rc != 0:
+def plan(N, nsm, V, T):
+    p = api.step_plan(N, nsm, V, T)
+    if p is None:
         return None
-    return dict(tc=tc.value, rpp=rpp.value, npass=npass.value, smem=smem.value, nrows=nrows.value,
-                ranges=ranges[: npass.value * nsm * 2].reshape(npass.value, nsm, 2))
+    return dict(tc=p["traits_per_launch"], rpp=p["rows_per_pass"], npass=p["npass"], smem=p["smem_bytes"],
+                nrows=p["nrows"], ranges=p["ranges"])
 
 
 def check_ownership(p, nsm):
