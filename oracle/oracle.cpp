@@ -616,4 +616,80 @@ int oracle_gibbs(const OracleCfg* cfg, const uint8_t* bed, const double* eps0, c
     return g.run();
 }
 
+// Bayes::predict, src/bayes.cpp:14-284, for one trait and R ranks emulated in one thread.
+//   bed [Mt][ceil(N/4)], y = the trait's residuals as read (Phenotype::get_centered_and_scaled_y returns epsilon_,
+//   phenotype.hpp:229-234), mave/msig [Mt] from compute_markers_statistics, beta_hist [niter][Mt] the .bet history,
+//   keep [Mt] != 0 where the marker's id is present in the reference .bim (bayes.cpp:95-100, 176-180).
+// Outputs: g [4*im4] total genetic values (the Allreduce of line 136), and per marker (NaN where skipped)
+//   beta, tdist, se, pval [Mt] (199-208), sigma [R] the residual variance every rank uses (149-152).
+// Quirk kept: a rank subtracts from y only the OTHER ranks' genetic values (146-147), so results depend on R.
+int oracle_predict(int N, int Mt, int R, const uint8_t* bed, const uint8_t* mask4, int nonas, const double* y,
+                   const double* mave, const double* msig, const double* beta_hist, int niter, const uint8_t* keep,
+                   double* g_out, double* beta_out, double* tdist_out, double* se_out, double* pval_out, double* sigma_out) {
+    g_err.clear();
+    if (N < 1 || Mt < 1 || R < 1 || niter < 1) { g_err = "oracle_predict: bad sizes"; return -1; }
+    build_luts();
+    const int mbytes = (N + 3) / 4, im4 = mbytes;
+    std::vector<double> beta_sum(Mt, 0.0);                                  // 59-78: mean of the recorded betas
+    for (int i = 0; i < niter; i++)
+        for (int j = 0; j < Mt; j++) beta_sum[j] += beta_hist[(size_t)i * Mt + j];
+    for (int j = 0; j < Mt; j++) beta_sum[j] /= double(niter);
+
+    std::vector<std::vector<double>> g_k(R, std::vector<double>((size_t)im4 * 4, 0.0));
+    std::vector<double> g((size_t)im4 * 4, 0.0);
+    for (int r = 0; r < R; r++) {                                           // 87-124
+        int S, M, Mm;
+        oracle_block_of_markers(Mt, R, r, &S, &M, &Mm);
+        for (int mrki = 0; mrki < M; mrki++) {
+            const int mglo = S + mrki;
+            if (keep && !keep[mglo]) continue;
+            const uint8_t* bedm = bed + (size_t)mglo * mbytes;
+            for (int j = 0; j < im4; j++)
+                for (int k = 0; k < 4; k++) {
+                    const double val = (LUT_A[bedm[j] * 4 + k] - mave[mglo]) * LUT_B[bedm[j] * 4 + k] * LUT_NA[mask4[j] * 4 + k] * msig[mglo];
+                    g_k[r][j * 4 + k] += val * beta_sum[mglo];
+                }
+        }
+        for (size_t i = 0; i < g.size(); i++) g[i] += g_k[r][i];            // 136
+    }
+    if (g_out) for (size_t i = 0; i < g.size(); i++) g_out[i] = g[i];
+    for (int j = 0; j < Mt; j++) {
+        if (beta_out) beta_out[j] = kNaN;
+        if (tdist_out) tdist_out[j] = kNaN;
+        if (se_out) se_out[j] = kNaN;
+        if (pval_out) pval_out[j] = kNaN;
+    }
+    std::vector<double> y_k((size_t)im4 * 4);
+    for (int r = 0; r < R; r++) {
+        int S, M, Mm;
+        oracle_block_of_markers(Mt, R, r, &S, &M, &Mm);
+        for (size_t i = 0; i < y_k.size(); i++) y_k[i] = ((int)i < N ? y[i] : 0.0) - (g[i] - g_k[r][i]);   // 141-147
+        double sigma = 0.0;                                                 // 149-152
+        for (int i = 0; i < N; i++) sigma += y_k[i] * y_k[i];
+        sigma /= nonas;
+        if (sigma_out) sigma_out[r] = sigma;
+        for (int mrki = 0; mrki < M; mrki++) {                              // 170-214
+            const int mglo = S + mrki;
+            if (keep && !keep[mglo]) continue;
+            const uint8_t* bedm = bed + (size_t)mglo * mbytes;
+            double xtx = 0.0, xty = 0.0;
+            for (int j = 0; j < im4; j++)
+                for (int k = 0; k < 4; k++) {
+                    const double val = LUT_A[bedm[j] * 4 + k] * LUT_B[bedm[j] * 4 + k] * LUT_NA[mask4[j] * 4 + k];
+                    xtx += val * val;
+                    xty += val * y_k[j * 4 + k];
+                }
+            const double beta = xty / xtx;
+            const double tdist = xty / std::sqrt(sigma * xtx);
+            const double se = beta / tdist;
+            const double pval = 1.0 - std::erf(std::sqrt(tdist * tdist * 0.5));   // boost::math::gamma_p(0.5, x) = erf(sqrt(x))
+            if (beta_out) beta_out[mglo] = beta;
+            if (tdist_out) tdist_out[mglo] = tdist;
+            if (se_out) se_out[mglo] = se;
+            if (pval_out) pval_out[mglo] = pval;
+        }
+    }
+    return 0;
+}
+
 }  // extern "C"

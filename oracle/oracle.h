@@ -79,6 +79,14 @@ void oracle_block_of_markers(int Mt, int nranks, int rank, int* S, int* M, int* 
 int oracle_gibbs(const OracleCfg* cfg, const uint8_t* bed, const double* eps0, const uint8_t* mask4,
                  const int* nonas, const int* group_index, const double* cva, OracleOut* out);
 
+/* Bayes::predict, src/bayes.cpp:14-284, one trait, R ranks emulated (the results depend on R: a rank removes only the
+ * other ranks' genetic values from y, lines 146-147).  beta_hist [niter][Mt] is the .bet history; keep [Mt] (or NULL)
+ * marks markers whose id is in the reference .bim.  g [4*ceil(N/4)]; beta/tdist/se/pval [Mt], NaN where skipped;
+ * sigma [R]. */
+int oracle_predict(int N, int Mt, int R, const uint8_t* bed, const uint8_t* mask4, int nonas, const double* y,
+                   const double* mave, const double* msig, const double* beta_hist, int niter, const uint8_t* keep,
+                   double* g, double* beta, double* tdist, double* se, double* pval, double* sigma);
+
 const char* oracle_last_error(void);
 
 #ifdef __cplusplus

@@ -146,6 +146,29 @@ def gibbs(bed, eps0, mask4, nonas, group_index, cva, *, N, R=1, nrep=None, itera
     return res
 
 
+def predict(bed, mask4, nonas, y, mave, msig, beta_hist, *, N, R=1, keep=None):
+    """Bayes::predict (bayes.cpp:14-284) for one trait under R ranks.  Returns g, beta, tdist, se, pval, sigma."""
+    bed = np.ascontiguousarray(bed, dtype=np.uint8)
+    Mt = bed.shape[0]
+    im4 = (N + 3) // 4
+    beta_hist = np.ascontiguousarray(beta_hist, dtype=np.float64).reshape(-1, Mt)
+    y = np.ascontiguousarray(y, dtype=np.float64)
+    mave = np.ascontiguousarray(mave, dtype=np.float64); msig = np.ascontiguousarray(msig, dtype=np.float64)
+    mask4 = np.ascontiguousarray(mask4, dtype=np.uint8)
+    k8 = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+    g = np.empty(4 * im4); beta = np.empty(Mt); tdist = np.empty(Mt); se = np.empty(Mt); pval = np.empty(Mt)
+    sigma = np.empty(R)
+    f = lib().oracle_predict
+    f.restype = C.c_int
+    f.argtypes = [C.c_int] * 3 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 7
+    rc = f(N, Mt, R, bed.ctypes.data, mask4.ctypes.data, int(nonas), y.ctypes.data, mave.ctypes.data, msig.ctypes.data,
+           beta_hist.ctypes.data, beta_hist.shape[0], None if k8 is None else k8.ctypes.data,
+           g.ctypes.data, beta.ctypes.data, tdist.ctypes.data, se.ctypes.data, pval.ctypes.data, sigma.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_predict failed ({rc}): {lib().oracle_last_error().decode()}")
+    return {"g": g, "beta": beta, "tdist": tdist, "se": se, "pval": pval, "sigma": sigma}
+
+
 # ---------------------------------------------------------------- reference binary + its files
 
 def have_reference() -> bool:
@@ -196,6 +219,18 @@ def read_cpn(path):
         its.append(int(raw[o:o + 4].view(np.uint32)[0]))
         vals.append(raw[o + 4:o + rec].view(np.int32).copy())
     return np.array(its), np.stack(vals) if vals else np.zeros((0, Mt), dtype=np.int32)
+
+
+def read_mlma(path):
+    """bayes.cpp:230-236: "%20s %8d %8d %20.15f %20.15f %20.15f %20.15f\n" = 123 bytes per kept marker:
+    id, index in the .bim, index in the reference .bim, beta, t, se, p."""
+    rows = []
+    with open(path) as f:
+        for line in f:
+            v = line.split()
+            if len(v) == 7:
+                rows.append((v[0], int(v[1]), int(v[2]), float(v[3]), float(v[4]), float(v[5]), float(v[6])))
+    return rows
 
 
 def read_csv(path):

@@ -4,6 +4,8 @@
   g1/          N=203 (N%4 != 0), M=400, 2 traits with NAs, missing genotypes, 2 groups x 4 mixtures,
                5 iterations, seed 171014: inputs, the reference's variate logs for 1 and 3 ranks
                (oracle/ref_shim) and the reference's own .bet/.cpn/.csv outputs.
+               plus the reference's --predict outputs (.mlma) computed from those .bet histories with 1 and 3
+               ranks, against syn.bim / ref.bim (ref.bim: permuted ids, two of them absent).
   lut_ref.bin  dotp_lut_a, dotp_lut_b (1024 doubles each) and na_lut (64) exactly as shipped in the
                reference's src/dotp_lut.hpp and src/na_lut.hpp.
 """
@@ -29,7 +31,23 @@ def main():
         out = os.path.join(g1, f"out{R}")
         O.run_reference(g1, p["bed"], p["dim"], p["phen"], p["gri"], p["grm"], out, iterations=5, seed=171014,
                         nranks=R, log_dir=os.path.join(g1, f"log{R}"))
+    add_predict(g1, p)
     print("golden fixtures written under", HERE)
+
+
+def add_predict(g1, p, M=400):
+    """Bayes::predict (bayes.cpp:14-284) on the histories written above."""
+    bim, ref = os.path.join(g1, "syn.bim"), os.path.join(g1, "ref.bim")
+    with open(bim, "w") as f:
+        for i in range(M):
+            f.write(f"1 rs{i} 0 {1000 + i} A G\n")
+    with open(ref, "w") as f:                      # 3 is coprime with 400: a permutation; rs21 and rs222 are dropped
+        for i in range(M):
+            j = (i * 3) % M
+            f.write(f"1 {'rs' + str(j) if j not in (21, 222) else 'absent' + str(j)} 0 {1000 + i} A G\n")
+    for R in (1, 3):
+        O.run_reference(g1, p["bed"], p["dim"], p["phen"], p["gri"], p["grm"], os.path.join(g1, f"out{R}"), iterations=5,
+                        seed=171014, nranks=R, extra=("--predict", "--bim-file", bim, "--ref-bim-file", ref))
 
 
 if __name__ == "__main__":
