@@ -197,6 +197,24 @@ class Engine:
         _check(lib().gmrm_dot_products(self._h, _ip(ids), ids.size, _dp(out)))
         return out
 
+    def predict(self, t: int, y: np.ndarray, beta_mean: np.ndarray, keep: np.ndarray | None = None) -> dict:
+        """Bayes::predict (bayes.cpp:14-284) for trait t on this shard: genetic values g [N] and, per shard-local marker,
+        beta / tdist / se / pval (NaN where keep == 0).  The engine's vranks are the reference's ranks."""
+        y = np.ascontiguousarray(y[: self.N], dtype=np.float64)
+        bm = np.ascontiguousarray(beta_mean, dtype=np.float64)
+        assert y.size == self.N and bm.size == self.marker_count
+        k8 = None if keep is None else np.ascontiguousarray(keep, dtype=np.uint8)
+        assert k8 is None or k8.size == self.marker_count
+        g = np.empty(self.N)
+        out = {n: np.empty(self.marker_count) for n in ("beta", "tdist", "se", "pval")}
+        f = lib().gmrm_predict
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_int32] + [C.c_void_p] * 8
+        _check(f(self._h, t, y.ctypes.data, bm.ctypes.data, None if k8 is None else k8.ctypes.data, g.ctypes.data,
+                 *(out[n].ctypes.data for n in ("beta", "tdist", "se", "pval"))))
+        out["g"] = g
+        return out
+
     def decode_marker(self, local_id: int):
         a = np.empty(self.N); b = np.empty(self.N)
         _check(lib().gmrm_decode_marker(self._h, local_id, _dp(a), _dp(b)))

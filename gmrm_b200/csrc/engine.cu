@@ -687,6 +687,103 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     return check_step_error(e);
 }
 
+// ------------------------------------------------------------------------------ association pass
+// Bayes::predict (src/bayes.cpp:14-284) for one trait on this GPU's shard.  The reference's ranks are the engine's
+// virtual ranks: block r of markers (set_block_of_markers) sees y_k = y - (g - g_r), g_r its own genetic values.
+int gmrm_predict(gmrm_engine* e, int32_t t, const double* y, const double* beta_mean, const uint8_t* keep, double* g_out,
+                 double* beta, double* tdist, double* se, double* pval) {
+    if (!e || !y || !beta_mean) return fail(GMRM_EINVAL, "null argument");
+    if (t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "trait %d out of range", t);
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    if (e->cfg.world_size > 1 && !e->comm) return fail(GMRM_EINVAL, "world_size > 1 needs gmrm_comm_init");
+    CU(cudaSetDevice(e->cfg.device));
+    const Layout& L = e->L;
+    const int Mloc = e->Mloc, Vl = e->Vl, R = e->cfg.vranks, nsm = L.nsm;
+    cudaStream_t s = e->stream;
+    const uint8_t* mask_t = e->mask4.p + (size_t)t * L.col_stride;
+    const double* mave_t = e->mave.p + (size_t)t * Mloc;
+    const double* msig_t = e->msig.p + (size_t)t * Mloc;
+    int rc;
+
+    // the phenotype, 0 at NA individuals and in the padding (phenotype.cpp:647-667)
+    std::vector<uint8_t> hmask((size_t)L.col_stride);
+    CU(cudaMemcpy(hmask.data(), mask_t, hmask.size(), cudaMemcpyDeviceToHost));
+    std::vector<double> hy((size_t)L.npad, 0.0);
+    for (int i = 0; i < L.N; i++)
+        if ((hmask[i >> 2] >> (i & 3)) & 1) hy[i] = y[i];
+
+    int maxlen = 0;
+    for (int v = 0; v < Vl; v++) { int S, M; block_of(e->cfg.Mt, R, e->r0 + v, S, M); maxlen = std::max(maxlen, M); }
+    const int vchunk = std::max(1, std::min(maxlen, 1024));            // markers per step-kernel launch
+    int tc = 0, rpp = 0;
+    step_plan(L, vchunk, 1, &tc, &rpp);
+    if (tc < 1 || rpp < 1) return fail(GMRM_EINVAL, "%d markers per launch do not fit the step kernel's shared memory", vchunk);
+
+    DevBuf<double> d_y, d_beta, d_xtx, d_scr, part, g, gk, yk, partial, spart, sumsq, outs;
+    DevBuf<uint8_t> d_keep;
+    DevBuf<int32_t> cols;
+    if ((rc = d_y.alloc((size_t)L.npad)) || (rc = d_beta.alloc(std::max(Mloc, 1))) || (rc = d_xtx.alloc(std::max(Mloc, 1))) ||
+        (rc = d_scr.alloc((size_t)2 * std::max(Mloc, 1))) || (rc = part.alloc((size_t)gvalue_chunks(maxlen) * L.npad)) ||
+        (rc = g.alloc((size_t)L.npad)) || (rc = gk.alloc((size_t)L.npad)) || (rc = yk.alloc((size_t)L.npad)) ||
+        (rc = partial.alloc((size_t)vchunk * nsm)) || (rc = spart.alloc((size_t)nsm)) || (rc = sumsq.alloc(1)) ||
+        (rc = outs.alloc((size_t)4 * std::max(Mloc, 1))) || (rc = cols.alloc(std::max(Mloc, 1))))
+        return rc;
+    if (keep && (rc = d_keep.alloc(std::max(Mloc, 1)))) return rc;
+    CU(cudaMemcpyAsync(d_y.p, hy.data(), hy.size() * 8, cudaMemcpyHostToDevice, s));
+    if (Mloc > 0) {
+        CU(cudaMemcpyAsync(d_beta.p, beta_mean, (size_t)Mloc * 8, cudaMemcpyHostToDevice, s));
+        if (keep) CU(cudaMemcpyAsync(d_keep.p, keep, (size_t)Mloc, cudaMemcpyHostToDevice, s));
+    }
+    const uint8_t* keep_d = keep ? d_keep.p : nullptr;
+    launch_iota(cols.p, Mloc, s);
+    // sum (a b na)^2 per marker from the dosage counts under the trait's NA mask (bayes.cpp:190-195)
+    launch_stats(e->bed.p, Mloc, L, mask_t, e->miss_off.p, e->miss_idx.p, e->nonas.p + t, 1, d_scr.p, d_scr.p + std::max(Mloc, 1), s, d_xtx.p);
+    CU(cudaGetLastError());
+
+    // pass 1: g = sum over all blocks of their genetic values (bayes.cpp:87-136)
+    if ((rc = g.zero(s))) return rc;
+    for (int v = 0; v < Vl; v++) {
+        int S, M; block_of(e->cfg.Mt, R, e->r0 + v, S, M);
+        const int b0 = S - e->marker_begin;
+        launch_gvalues(e->bed.p, L, e->miss_off.p, e->miss_idx.p, b0, b0 + M, mave_t, msig_t, d_beta.p, keep_d, mask_t, part.p, gk.p, g.p, s);
+        CU(cudaGetLastError());
+    }
+    if (e->cfg.world_size > 1) NC(g_nccl.AllReduce(g.p, g.p, (size_t)L.npad, kNcclFloat64, kNcclSum, e->comm, s));
+    if (g_out) CU(cudaMemcpyAsync(g_out, g.p, (size_t)L.N * 8, cudaMemcpyDeviceToHost, s));
+
+    // pass 2, block by block: y_k, its variance, and the markers' statistics (bayes.cpp:138-214)
+    for (int v = 0; v < Vl; v++) {
+        int S, M; block_of(e->cfg.Mt, R, e->r0 + v, S, M);
+        if (M == 0) continue;
+        const int b0 = S - e->marker_begin;
+        launch_gvalues(e->bed.p, L, e->miss_off.p, e->miss_idx.p, b0, b0 + M, mave_t, msig_t, d_beta.p, keep_d, mask_t, part.p, gk.p, nullptr, s);
+        launch_predict_residual(d_y.p, g.p, gk.p, L, yk.p, s);
+        launch_eps_sumsq(yk.p, L.npad, L.N, 1, sumsq.p, s);
+        CU(cudaGetLastError());
+        for (int done = 0; done < M; done += vchunk) {
+            const int V = std::min(vchunk, M - done);
+            StepParams p{};
+            p.bed = e->bed.p; p.col_stride = L.col_stride; p.nrows = L.nrows; p.cols = cols.p + b0 + done; p.V = V;
+            p.eps = yk.p; p.npad = L.npad; p.Ttot = 1; p.t0 = 0; p.rows_per_pass = rpp; p.npass = step_npass(L, rpp);
+            p.partial = partial.p; p.spart = spart.p; p.mask4 = mask_t; p.pV = Vl;
+            p.err = e->err.p; p.prof = e->prof.p; p.pf = e->step_pf;
+            const int lrc = launch_step(L, 1, p, s);
+            if (lrc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", lrc, cudaGetErrorString(cudaGetLastError()));
+            launch_predict_finish(cols.p + b0 + done, V, nsm, partial.p, d_xtx.p, sumsq.p, e->h_nonas[t], keep_d,
+                                  outs.p, outs.p + Mloc, outs.p + 2 * (size_t)Mloc, outs.p + 3 * (size_t)Mloc, s);
+            CU(cudaGetLastError());
+        }
+    }
+    if (Mloc > 0) {
+        if (beta) CU(cudaMemcpyAsync(beta, outs.p, (size_t)Mloc * 8, cudaMemcpyDeviceToHost, s));
+        if (tdist) CU(cudaMemcpyAsync(tdist, outs.p + Mloc, (size_t)Mloc * 8, cudaMemcpyDeviceToHost, s));
+        if (se) CU(cudaMemcpyAsync(se, outs.p + 2 * (size_t)Mloc, (size_t)Mloc * 8, cudaMemcpyDeviceToHost, s));
+        if (pval) CU(cudaMemcpyAsync(pval, outs.p + 3 * (size_t)Mloc, (size_t)Mloc * 8, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    return check_step_error(e);
+}
+
 // ------------------------------------------------------------------------------------- the chain
 int gmrm_init_chain(gmrm_engine* e, const double* sigmag_init) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
@@ -750,7 +847,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     int rc;
 
     // ---- replay variates for this iteration
-    const double *d_u = nullptr, *d_z = nullptr, *d_small = nullptr;
+    const double *d_u = nullptr, *d_z = nullptr;
     const int32_t* d_perm = nullptr;
     const double *d_mu = nullptr, *d_sigg = nullptr, *d_piu = nullptr, *d_sige = nullptr;
     if (rp) {
@@ -776,7 +873,6 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         if (rp->sige_unit) { memcpy(hp, rp->sige_unit, T * 8); d_sige = e->rep_small.p + T + (size_t)T * G + (size_t)T * G * K; }
         CU(cudaMemcpyAsync(e->rep_small.p, small.data(), nsmall * 8, cudaMemcpyHostToDevice, s));
         CU(cudaStreamSynchronize(s));   // host staging vectors go out of scope
-        (void)d_small;
     }
 
     if (e->timing_detail && e->dot_ev.size() < (size_t)6 * Mm) {

@@ -154,7 +154,8 @@ __global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int 
 __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
                                                     const uint8_t* __restrict__ mask4, const uint32_t* __restrict__ miss_off,
                                                     const uint32_t* __restrict__ miss_idx, const int32_t* __restrict__ nonas,
-                                                    int T, double* __restrict__ mave, double* __restrict__ msig) {
+                                                    int T, double* __restrict__ mave, double* __restrict__ msig,
+                                                    double* __restrict__ xtx) {
     const int j = blockIdx.x;
     if (j >= nmark) return;
     __shared__ uint8_t fld[kTabEntries];     // base-3 byte -> 2-bit dosage fields
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ 
             const double sumsqr = c0 * (0.0 - av) * (0.0 - av) + c1 * (1.0 - av) * (1.0 - av) + c2 * (2.0 - av) * (2.0 - av);  // 544-545
             mave[(int64_t)t * nmark + j] = av;
             msig[(int64_t)t * nmark + j] = 1.0 / sqrt(sumsqr / ((double)nonas[t] - 1.0));   // 548
+            if (xtx) xtx[(int64_t)t * nmark + j] = c1 + 4.0 * c2;        // sum (a b na)^2 of Bayes::predict, bayes.cpp:190-195
         }
     }
 }
@@ -1207,9 +1209,9 @@ void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, con
     generate_plink_kernel<<<grid, 256, 0, s>>>(dst, nmark, first_global_marker, L, seed, maf_lo, maf_hi, missing_rate);
 }
 void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
-                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s) {
+                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s, double* xtx) {
     if (nmark <= 0) return;
-    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, mask4, miss_off, miss_idx, nonas, T, mave, msig);
+    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, mask4, miss_off, miss_idx, nonas, T, mave, msig, xtx);
 }
 void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s) {
     dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)T);

@@ -115,7 +115,7 @@ void launch_decode_namask(const uint8_t* mask4, const Layout& L, double* na, cud
 void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, const Layout& L, uint32_t seed,
                            double maf_lo, double maf_hi, double missing_rate, cudaStream_t s);
 void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
-                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s);
+                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s, double* xtx = nullptr);
 void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s);
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
@@ -155,5 +155,17 @@ struct MuDrawParams {
 };
 void launch_mu_draw(const MuDrawParams& p, cudaStream_t s);
 void launch_init_sigmae(const double* esq, const int32_t* nonas, int T, double* sigmae, cudaStream_t s);
+
+// association pass, Bayes::predict (predict.cu)
+int gvalue_chunks(int nmark);   // partial buffers launch_gvalues needs for a block of nmark markers: [chunks][npad] doubles
+// g[i] = na_i * sum_{m in [m_begin, m_end)} ((a_im - mave_m) msig_m) beta_m  (columns local to the shard; keep[m] == 0: skipped);
+// add (or nullptr) accumulates g as well
+void launch_gvalues(const uint8_t* bed, const Layout& L, const uint32_t* miss_off, const uint32_t* miss_idx, int m_begin, int m_end,
+                    const double* mave, const double* msig, const double* beta, const uint8_t* keep, const uint8_t* mask4,
+                    double* part, double* g, double* add, cudaStream_t s);
+void launch_predict_residual(const double* y, const double* g, const double* g_k, const Layout& L, double* y_k, cudaStream_t s);
+void launch_predict_finish(const int32_t* cols, int V, int nsm, const double* partial, const double* xtx, const double* sumsq,
+                           int32_t nonas, const uint8_t* keep, double* beta, double* tdist, double* se, double* pval, cudaStream_t s);
+void launch_iota(int32_t* x, int n, cudaStream_t s);
 
 }  // namespace gmrm

@@ -165,6 +165,18 @@ int gmrm_fetch_outputs(gmrm_engine* e, int32_t trait, double* betas, int32_t* co
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out);
 int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step) */
 
+/* --- association pass: Bayes::predict, src/bayes.cpp:14-284, for one trait on this GPU's shard.
+ * The reference's MPI ranks are the engine's virtual ranks (cfg.vranks): block r of markers is tested against
+ * y_k = y - (g - g_r), i.e. only the OTHER blocks' genetic values are removed from the phenotype (bayes.cpp:141-147),
+ * so vranks = 1 reproduces `mpirun -n 1`.  Needs gmrm_compute_marker_stats; does not touch the chain's state.
+ *   y          N doubles: the centred-scaled phenotype (what gmrm_set_phenotype took; NA entries are ignored)
+ *   beta_mean  marker_count doubles: mean of the .bet history for this shard's markers (bayes.cpp:59-78)
+ *   keep       marker_count bytes or NULL: 0 = the marker's id is absent from the reference .bim -> skipped (95-100)
+ *   g          N doubles or NULL: genetic values summed over all blocks and GPUs (bayes.cpp:136)
+ *   beta, tdist, se, pval   marker_count doubles each or NULL (bayes.cpp:199-208); NaN for skipped markers */
+int gmrm_predict(gmrm_engine* e, int32_t trait, const double* y, const double* beta_mean, const uint8_t* keep, double* g,
+                 double* beta, double* tdist, double* se, double* pval);
+
 /* --- test hook without a device: launch plan of the step kernel and the rows each CTA owns in each pass */
 int gmrm_debug_step_plan(int32_t N, int32_t nsm, int32_t V, int32_t T, int32_t* traits_per_launch, int32_t* rows_per_pass,
                          int32_t* npass, int32_t* smem_bytes, int32_t* nrows, int32_t* ranges);
