@@ -5,6 +5,7 @@
 // and src/xfiles.{hpp,cpp}; no code is shared with them.
 #pragma once
 #include <cstdint>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -25,6 +26,7 @@ struct Options {
     unsigned burn_in = 0;    // --burn-in: iterations left out of the posterior-mean summary (.mbet)
     bool check_inputs = false;   // --check-inputs: parse everything, print a summary, no GPU work
     std::string dump_inputs;     // --dump-inputs <dir>: with --check-inputs, write the parsed phenotypes / groups / mixtures as raw binaries (tests)
+    bool selftest_predict = false;   // --selftest-predict: with --check-inputs and --predict, read the .bim pair and the .bet histories and print what was found (tests)
     bool selftest_outputs = false;   // --selftest-outputs: with --check-inputs, write a fixed 2-iteration .csv/.bet/.cpn history from 2 "ranks" (tests)
     // derived from the .grm file
     int ngroups = 0, nmixtures = 0;
@@ -72,5 +74,15 @@ public:
 private:
     int csv_ = -1, bet_ = -1, cpn_ = -1;
 };
+
+// ---- association pass, the reference's --predict mode (predict.cpp)
+struct BimCross {
+    std::vector<std::string> ids;            // ids of --bim-file in row order = global marker order
+    std::map<std::string, int> ref_index;    // id -> row in --ref-bim-file
+};
+BimCross cross_bim_files(const std::string& bim, const std::string& ref_bim, bool verbose);     // bayes.cpp:286-316
+std::vector<double> read_bet_mean(const std::string& path, size_t expect_mt, unsigned* niter);  // bayes.cpp:38-78
+constexpr int kMlmaLine = 123;                                                                  // LLEN - 1, bayes.cpp:218
+std::string mlma_line(const std::string& id, int mglo, int rmglo, double beta, double tdist, double se, double pval);
 
 }  // namespace host

@@ -1,6 +1,10 @@
-// gmrm_b200_cli -- drop-in for the Gibbs mode of the reference executable (src/main.cpp:8-24, Bayes::process
-// src/bayes.cpp:318-677): same flags, inputs, outputs and stdout lines; the marker loop runs on B200s through the
-// C ABI (include/gmrm_b200.h).  One host thread per GPU plays the role of one MPI rank of the reference.
+// gmrm_b200_cli -- drop-in for the reference executable (src/main.cpp:8-24): the Gibbs mode (Bayes::process,
+// src/bayes.cpp:318-677) and the association pass (--predict, Bayes::predict, src/bayes.cpp:14-284) with the same
+// flags, inputs, outputs and stdout lines; the marker sums run on B200s through the C ABI (include/gmrm_b200.h).
+// One host thread per GPU drives its shard of the markers.
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
@@ -47,7 +51,94 @@ struct Shared {
     uint8_t nccl_id[128];
     void* peer_ptrs[8][5] = {};
     int vranks = 0;
+    // --predict
+    host::BimCross bim;
+    std::vector<uint8_t> keep;                 // [Mt] 1 = the marker's id is in the reference .bim
+    std::vector<std::vector<double>> bet_mean; // [T][Mt]
 };
+
+// this GPU's block of the .bed into the engine (Bayes::load_genotype, bayes.cpp:867-900), in chunks
+void load_block(gmrm_engine* e, const host::Options& o, int N, int S, int M) {
+    host::BedReader bed(o.bed_file, N);
+    const int chunk = std::max(1, (int)((256u << 20) / (size_t)bed.mbytes()));
+    // pinned read buffer: the upload is then plain DMA (gmrm_host_alloc, include/gmrm_b200.h)
+    uint8_t* buf = (uint8_t*)gmrm_host_alloc((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
+    if (!buf) ck(-4, "gmrm_host_alloc");
+    for (int done = 0; done < M; done += chunk) {
+        const int n = std::min(chunk, M - done);
+        bed.read(S + done, n, buf);
+        ck(gmrm_upload_bed(e, buf, S + done, n), "gmrm_upload_bed");
+    }
+    gmrm_host_free(buf);
+    ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
+}
+
+// --predict (Bayes::predict, bayes.cpp:14-284): per trait, genetic values from the mean of the .bet history, then the
+// per-marker association statistics, written to <stem>.mlma in global marker order.
+void predict_worker(int rank, Shared* sh, Barrier* bar) {
+    const host::Options& o = sh->opt;
+    const int ngpu = o.gpus, T = (int)sh->phens.size(), N = sh->dims.N, Mt = sh->dims.Mt;
+    const double t_start = now();
+    gmrm_config cfg{};
+    cfg.device = rank; cfg.N = N; cfg.Mt = Mt; cfg.T = T; cfg.G = 1; cfg.K = 2;      // groups and mixtures play no part here
+    cfg.world_size = ngpu; cfg.world_rank = rank; cfg.vranks = sh->vranks; cfg.sync_rate = 1; cfg.shuffle = 0; cfg.seed = o.seed;
+    gmrm_engine* e = nullptr;
+    ck(gmrm_create(&cfg, &e), "gmrm_create");
+    if (ngpu > 1) {
+        if (rank == 0) ck(gmrm_comm_unique_id(sh->nccl_id), "gmrm_comm_unique_id");
+        bar->wait();
+        ck(gmrm_comm_init(e, sh->nccl_id), "gmrm_comm_init");
+    }
+    int32_t S = 0, M = 0;
+    ck(gmrm_shard_info(e, &S, &M, nullptr, nullptr, nullptr), "gmrm_shard_info");
+    const double t_load = now();
+    load_block(e, o, N, S, M);
+    if (rank == 0) printf("INFO   : time to load genotype data = %.3f seconds.\n", now() - t_load);
+    for (int t = 0; t < T; t++) ck(gmrm_set_phenotype(e, t, sh->phens[t].eps.data(), sh->phens[t].mask4.data(), sh->phens[t].nonas), "gmrm_set_phenotype");
+    const double t_stats = now();
+    ck(gmrm_compute_marker_stats(e), "gmrm_compute_marker_stats");
+    if (rank == 0) printf("INFO   : Time to compute the markers' statistics: %.2f seconds.\n", now() - t_stats);
+
+    int kept_before = 0;                                 // lines the shards before this one write (bayes.cpp:240-248)
+    for (int j = 0; j < S; j++) kept_before += sh->keep[j];
+    std::vector<double> beta(std::max(M, 1)), tdist(std::max(M, 1)), se(std::max(M, 1)), pval(std::max(M, 1));
+    for (int t = 0; t < T; t++) {
+        const std::string path = (o.out_dir.empty() ? std::string() : o.out_dir + "/") + sh->phens[t].stem + ".mlma";
+        if (rank == 0) {                                 // delete_output_prediction_files + exclusive create (phenotype.cpp:146-170)
+            unlink(path.c_str());
+            const int fd = open(path.c_str(), O_CREAT | O_WRONLY | O_EXCL, 0644);
+            if (fd < 0) { printf("FATAL  : could not open output file %s\n", path.c_str()); exit(EXIT_FAILURE); }
+            close(fd);
+        }
+        bar->wait();
+        ck(gmrm_predict(e, t, sh->phens[t].eps.data(), sh->bet_mean[t].data() + S, sh->keep.data() + S, nullptr, beta.data(), tdist.data(),
+                        se.data(), pval.data()), "gmrm_predict");
+        std::string text;
+        text.reserve((size_t)M * host::kMlmaLine);
+        for (int j = 0; j < M; j++) {
+            const std::string& id = sh->bim.ids[S + j];
+            if (!sh->keep[S + j]) {
+                printf("WARNING: marker id %s excluded -- no match\n", id.c_str());            // bayes.cpp:227
+                continue;
+            }
+            const std::string line = host::mlma_line(id, S + j, sh->bim.ref_index.at(id), beta[j], tdist[j], se[j], pval[j]);
+            if (line.empty()) { printf("FATAL  : the .mlma line of marker %s does not fit the fixed width of %d bytes\n", id.c_str(), host::kMlmaLine); exit(EXIT_FAILURE); }
+            text += line;
+        }
+        const int fd = open(path.c_str(), O_WRONLY);
+        if (fd < 0) { printf("FATAL  : could not open output file %s\n", path.c_str()); exit(EXIT_FAILURE); }
+        size_t done = 0;
+        while (done < text.size()) {
+            const ssize_t w = pwrite(fd, text.data() + done, text.size() - done, (off_t)kept_before * host::kMlmaLine + (off_t)done);
+            if (w <= 0) { printf("FATAL  : write to %s failed\n", path.c_str()); exit(EXIT_FAILURE); }
+            done += (size_t)w;
+        }
+        close(fd);
+        bar->wait();
+    }
+    if (rank == 0) printf("INFO   : Time to compute the predictions: %.2f seconds.\n", now() - t_start);
+    gmrm_destroy(e);
+}
 
 void worker(int rank, Shared* sh, Barrier* bar) {
     const host::Options& o = sh->opt;
@@ -68,20 +159,7 @@ void worker(int rank, Shared* sh, Barrier* bar) {
 
     // ---- genotypes (Bayes::load_genotype, bayes.cpp:867-900): this rank's block, in chunks
     const double t_load = now();
-    {
-        host::BedReader bed(o.bed_file, N);
-        const int chunk = std::max(1, (int)((256u << 20) / (size_t)bed.mbytes()));
-        // pinned read buffer: the upload is then plain DMA (gmrm_host_alloc, include/gmrm_b200.h)
-        uint8_t* buf = (uint8_t*)gmrm_host_alloc((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
-        if (!buf) ck(-4, "gmrm_host_alloc");
-        for (int done = 0; done < M; done += chunk) {
-            const int n = std::min(chunk, M - done);
-            bed.read(S + done, n, buf);
-            ck(gmrm_upload_bed(e, buf, S + done, n), "gmrm_upload_bed");
-        }
-        gmrm_host_free(buf);
-        ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
-    }
+    load_block(e, o, N, S, M);
     if (ngpu > 1 && o.sync_rate == 1) {      // list exchange: the shards read each other's columns over NVLink
         ck(gmrm_comm_local_buffers(e, sh->peer_ptrs[rank]), "gmrm_comm_local_buffers");
         bar->wait();
@@ -177,6 +255,57 @@ int main(int argc, char** argv) {
            o.ngroups, o.nmixtures);
     for (const auto& f : o.phen_files) sh.phens.push_back(host::read_phen_file(f, sh.dims.N, o.verbosity));
     std::cout.flush();
+    if (o.predict) {
+        // the reference's ranks are the virtual ranks (include/gmrm_b200.h, gmrm_predict): default one per GPU
+        int vr = o.vranks > 0 ? o.vranks : o.gpus;
+        if (vr > sh.dims.Mt) vr = sh.dims.Mt;
+        vr -= vr % o.gpus;
+        if (vr < o.gpus) {
+            printf("FATAL  : %d markers cannot be shared by %d GPUs\n", sh.dims.Mt, o.gpus);
+            return EXIT_FAILURE;
+        }
+        sh.vranks = vr;
+        sh.bim = host::cross_bim_files(o.bim_file, o.ref_bim_file, true);
+        if ((int)sh.bim.ids.size() < sh.dims.Mt) {
+            printf("FATAL  : %s lists %d ids for %d markers\n", o.bim_file.c_str(), (int)sh.bim.ids.size(), sh.dims.Mt);
+            return EXIT_FAILURE;
+        }
+        sh.keep.resize(sh.dims.Mt);
+        for (int j = 0; j < sh.dims.Mt; j++) sh.keep[j] = sh.bim.ref_index.count(sh.bim.ids[j]) ? 1 : 0;
+        for (size_t t = 0; t < sh.phens.size(); t++) {
+            unsigned niter = 0;
+            const std::string bet = (o.out_dir.empty() ? std::string() : o.out_dir + "/") + sh.phens[t].stem + ".bet";
+            sh.bet_mean.push_back(host::read_bet_mean(bet, sh.bim.ref_index.size(), &niter));
+            printf("INFO   : Number of recorded iterations in .bet file %d: %u\n", (int)t, niter);                   // bayes.cpp:52-53
+            if ((int)sh.bet_mean.back().size() < sh.dims.Mt) {
+                printf("FATAL  : %s holds %d markers, the run has %d\n", bet.c_str(), (int)sh.bet_mean.back().size(), sh.dims.Mt);
+                return EXIT_FAILURE;
+            }
+        }
+        printf("INFO   : %d GPU(s), %d marker block(s) (ranks of the reference)\n", o.gpus, vr);
+        if (o.check_inputs) {
+            if (o.selftest_predict) {                    // what the readers found, and one formatted line (tests)
+                int kept = 0;
+                for (auto k : sh.keep) kept += k;
+                printf("SELFTEST: kept %d of %d markers\n", kept, sh.dims.Mt);
+                for (size_t t = 0; t < sh.bet_mean.size(); t++) {
+                    double s1 = 0.0;
+                    for (int j = 0; j < sh.dims.Mt; j++) s1 += sh.bet_mean[t][j] * (j + 1);
+                    printf("SELFTEST: trait %d weighted beta mean %.17g\n", (int)t, s1);
+                }
+                const int j = sh.dims.Mt - 1;
+                if (sh.keep[j]) printf("SELFTEST: %s", host::mlma_line(sh.bim.ids[j], j, sh.bim.ref_index.at(sh.bim.ids[j]), 0.25, -1.5, 0.125, 0.0625).c_str());
+            }
+            printf("INFO   : inputs parsed; --check-inputs given, no GPU work\n");
+            return 0;
+        }
+        fflush(stdout);
+        Barrier pbar(o.gpus);
+        std::vector<std::thread> pth;
+        for (int r = 0; r < o.gpus; r++) pth.emplace_back(predict_worker, r, &sh, &pbar);
+        for (auto& t : pth) t.join();
+        return 0;
+    }
     if (o.group_index_file.empty()) {
         printf("FATAL  : --group-index-file and --group-mixture-file are required\n");
         return EXIT_FAILURE;

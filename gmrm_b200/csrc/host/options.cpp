@@ -135,6 +135,7 @@ Options parse_options(int argc, char** argv, int rank) {
         else if (!strcmp(a, "--burn-in")) { o.burn_in = positive("--burn-in", value_of(argc, argv, i), 0, "positive"); ss << "--burn-in " << o.burn_in << "\n"; }
         else if (!strcmp(a, "--check-inputs")) { o.check_inputs = true; ss << "--check-inputs 1\n"; }
         else if (!strcmp(a, "--dump-inputs")) { o.dump_inputs = value_of(argc, argv, i); ss << "--dump-inputs " << o.dump_inputs << "\n"; }
+        else if (!strcmp(a, "--selftest-predict")) { o.selftest_predict = true; ss << "--selftest-predict 1\n"; }
         else if (!strcmp(a, "--selftest-outputs")) { o.selftest_outputs = true; ss << "--selftest-outputs 1\n"; }
         else if (!strcmp(a, "--gpus")) { o.gpus = (int)positive("--gpus", value_of(argc, argv, i), 1, "strictly positive"); ss << "--gpus " << o.gpus << "\n"; }
         else fatal(std::string("FATAL: option \"") + a + "\" unknown");
@@ -148,8 +149,12 @@ Options parse_options(int argc, char** argv, int rank) {
     if (o.phen_files.empty()) fatal("FATAL  : no phen file(s) provided! Please use the --phen-files option.");
     if (!o.predict && (o.group_index_file.empty() != o.group_mixture_file.empty()))
         fatal("FATAL  : you need to activate BOTH --group-index-file and --group-mixture-file");
-    if (o.predict) fatal("FATAL  : --predict (association testing on stored .bet files) is outside the scope of gmrm_b200; use the reference for that mode.");
+    if (o.predict) {                                                              // options.cpp:205-214
+        if (o.bim_file.empty()) fatal("FATAL  : you need to pass a bim file with --bim-file when activating --predict");
+        if (o.ref_bim_file.empty()) fatal("FATAL  : you need to pass a reference bim file with --ref-bim-file when activating --predict");
+    }
     if (o.mimic_hydra && o.phen_files.size() > 1) fatal("FATAL  : with --mimic-hydra, only a single phenotype can be processed.");
+    if (o.predict) return o;                                                      // options.hpp:11-12: the mixture file is not read with --predict
     read_group_mixture_file(o, rank);
     return o;
 }

@@ -144,3 +144,92 @@ def test_cli_outputs_match_oracle(data, oracle, vranks, thin):
             np.testing.assert_allclose(csv[n]["sigmae"], res["sigmae"][it - 1][t], rtol=1e-8)
         mb = np.fromfile(os.path.join(out, stem + ".mbet"))
         np.testing.assert_allclose(mb, np.mean([res["betas"][i][t] for i in range(2, iters)], axis=0), rtol=1e-8, atol=1e-13)
+
+
+# ------------------------------------------------------------------ --predict (Bayes::predict, bayes.cpp:14-284)
+def write_predict_inputs(d, out, M, niter=3, seed=5):
+    """A .bim pair (reference reversed, every 50th id replaced) and a .bet history per trait, as the Gibbs mode writes it."""
+    os.makedirs(out, exist_ok=True)
+    bim, ref = os.path.join(d["tmp"], "p.bim"), os.path.join(d["tmp"], "pref.bim")
+    with open(bim, "w") as f:
+        f.writelines(f"1 rs{i} 0 {i} A G\n" for i in range(M))
+    with open(ref, "w") as f:
+        f.writelines(f"1 {'rs' if i % 50 else 'gone'}{i} 0 {i} A G\n" for i in reversed(range(M)))
+    rng = np.random.default_rng(seed)
+    hists = []
+    for ph in d["paths"]["phen"]:
+        stem = os.path.splitext(os.path.basename(ph))[0]
+        h = rng.normal(0, 0.02, size=(niter, M)) * (rng.random((niter, M)) < 0.3)
+        with open(os.path.join(out, stem + ".bet"), "wb") as f:                    # xfiles.hpp:24-37
+            f.write(np.uint32(M).tobytes())
+            for i in range(niter):
+                f.write(np.uint32(i + 1).tobytes())
+                f.write(h[i].tobytes())
+        hists.append(h)
+    keep = np.array([i % 50 != 0 for i in range(M)], dtype=np.uint8)
+    return bim, ref, hists, keep
+
+
+def predict_args(d, out, bim, ref):
+    p = d["paths"]
+    return ["--bed-file", p["bed"], "--dim-file", p["dim"], "--phen-files", ",".join(p["phen"]), "--out-dir", out,
+            "--predict", "--bim-file", bim, "--ref-bim-file", ref]
+
+
+def test_cli_predict_needs_both_bim_files(data):
+    p = data["paths"]
+    base = ["--bed-file", p["bed"], "--dim-file", p["dim"], "--phen-files", p["phen"][0], "--predict"]
+    r = run(base)
+    assert r.returncode == 1 and "you need to pass a bim file with --bim-file" in r.stdout                 # options.cpp:206-208
+    r = run(base + ["--bim-file", "x.bim"])
+    assert r.returncode == 1 and "you need to pass a reference bim file with --ref-bim-file" in r.stdout   # options.cpp:210-212
+
+
+def test_cli_predict_readers(data, tmp_path):
+    """.bim cross-reference (bayes.cpp:286-316), .bet mean (38-78) and the .mlma line format (230-236) on the CPU."""
+    out = str(tmp_path / "o")
+    bim, ref, hists, keep = write_predict_inputs(data, out, 300)
+    r = run(predict_args(data, out, bim, ref) + ["--check-inputs", "--selftest-predict"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "INFO   : found 300 ids in bim file" in r.stdout and "INFO   : found 300 ids in reference bim file" in r.stdout
+    assert "Number of recorded iterations in .bet file 1: 3" in r.stdout                                    # bayes.cpp:52-53
+    assert f"SELFTEST: kept {int(keep.sum())} of 300 markers" in r.stdout
+    w = np.arange(1, 301)
+    for t in range(2):
+        line = [l for l in r.stdout.splitlines() if l.startswith(f"SELFTEST: trait {t} weighted beta mean")][0]
+        assert abs(float(line.split()[-1]) - float((hists[t].mean(axis=0) * w).sum())) < 1e-12
+    want = "%20s %8d %8d %20.15f %20.15f %20.15f %20.15f" % ("rs299", 299, 0, 0.25, -1.5, 0.125, 0.0625)
+    assert "SELFTEST: " + want in r.stdout and len(want) == 122
+
+
+def test_cli_predict_rejects_a_history_of_another_size(data, tmp_path):
+    out = str(tmp_path / "o")
+    bim, ref, _, _ = write_predict_inputs(data, out, 300)
+    with open(ref, "a") as f:
+        f.write("1 extra 0 1 A G\n")                       # 301 reference ids, 300 markers in the .bet
+    r = run(predict_args(data, out, bim, ref) + ["--check-inputs"])
+    assert r.returncode == 1 and "Mismatch between expected and Mtot read from .bet file" in r.stdout       # bayes.cpp:45-48
+
+
+@pytest.mark.gpu
+@pytest.mark.xfail(reason="predict.cu: first run on hardware pending", strict=False)
+@pytest.mark.parametrize("vranks", [1, 3])
+def test_cli_predict_matches_oracle(data, oracle, vranks):
+    out = os.path.join(data["tmp"], f"pred_{vranks}")
+    bim, ref, hists, keep = write_predict_inputs(data, out, 300)
+    r = run(predict_args(data, out, bim, ref) + ["--vranks", str(vranks)])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("excluded -- no match") == 2 * int((keep == 0).sum())                             # bayes.cpp:227, per trait
+    p = data["paths"]
+    inp = oracle.load_inputs(p["bed"], p["dim"], p["phen"], p["gri"], p["grm"])
+    for t in range(2):
+        stem = os.path.splitext(os.path.basename(p["phen"][t]))[0]
+        rows = oracle.read_mlma(os.path.join(out, stem + ".mlma"))
+        assert os.path.getsize(os.path.join(out, stem + ".mlma")) == 123 * int(keep.sum())
+        mave, msig = oracle.marker_stats(inp["bed"], inp["N"], inp["mask4"][t], int(inp["nonas"][t]))
+        want = oracle.predict(inp["bed"], inp["mask4"][t], int(inp["nonas"][t]), inp["eps0"][t], mave, msig, hists[t], N=inp["N"],
+                              R=vranks, keep=keep)
+        idx = np.array([r_[1] for r_ in rows])
+        assert np.array_equal(idx, np.flatnonzero(keep)) and [r_[2] for r_ in rows] == [299 - i for i in idx]
+        for c, name in ((3, "beta"), (4, "tdist"), (5, "se"), (6, "pval")):
+            np.testing.assert_allclose([r_[c] for r_ in rows], want[name][idx], rtol=1e-9, atol=2e-15, err_msg=name)
