@@ -10,6 +10,7 @@
  *   Bayes::dot_product              src/bayes.cpp:709-770      -> gmrm_dot_products (test hook)
  *   the iteration body of Bayes::process  src/bayes.cpp:340-656 -> gmrm_init_chain + gmrm_run_iteration
  *   outputs read at bayes.cpp:659-669     -> gmrm_get_betas / gmrm_get_components / gmrm_get_state
+ *   the sums of Bayes::predict            src/bayes.cpp:87-214  -> gmrm_predict
  * INTEGRATION.md shows the reference-side stub.
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
