@@ -17,6 +17,14 @@
 #include <cmath>
 #include <cstdint>
 
+#ifndef GMRM_UNROLL
+#if defined(__CUDA_ARCH__)
+#define GMRM_UNROLL _Pragma("unroll")
+#else
+#define GMRM_UNROLL            // host pass: the pragma is unknown to g++
+#endif
+#endif
+
 #if defined(__CUDACC__)
 #define GMRM_HD __host__ __device__ __forceinline__
 #else
@@ -49,7 +57,7 @@ GMRM_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
 // Philox4x32-10 (Salmon et al., SC'11), constants as published.
 GMRM_HD U4 philox4x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
+GMRM_UNROLL
     for (int r = 0; r < 10; r++) {
         uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
         uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
@@ -116,7 +124,7 @@ GMRM_HD uint32_t perm_at(uint32_t s, uint32_t n, uint32_t seed, uint32_t it, uin
     uint32_t x = s;
     do {
         uint32_t L = x >> half, R = x & mask;
-#pragma unroll
+GMRM_UNROLL
         for (uint32_t round = 0; round < 4; round++) {
             const uint32_t F = philox4x32(seed, STREAM_PERM, it, rank, R, round).x & mask;
             const uint32_t t = L ^ F;

@@ -36,6 +36,13 @@
 #else
 #define GMRM_HD inline
 #endif
+#ifndef GMRM_UNROLL
+#if defined(__CUDA_ARCH__)
+#define GMRM_UNROLL _Pragma("unroll")
+#else
+#define GMRM_UNROLL            // host pass: the pragma is unknown to g++
+#endif
+#endif
 
 namespace gmrm {
 
@@ -74,7 +81,7 @@ inline Layout make_layout(int32_t N, int nsm) {
 // PLINK byte (4 codes) -> base-3 quad byte + 4-bit mask of missing genotypes, and back.
 GMRM_HD uint8_t plink_to_tri(uint8_t x, uint32_t* missmask) {
     uint32_t e = 0, mm = 0, w = 1;
-#pragma unroll
+GMRM_UNROLL
     for (int k = 0; k < 4; k++) {
         const uint32_t c = (x >> (2 * k)) & 3u;
         const uint32_t d = c == 0 ? 2u : (c == 2 ? 1u : 0u);   // 00 -> 2, 10 -> 1, 11 -> 0, 01 (missing) -> 0 + flag
@@ -93,7 +100,7 @@ GMRM_HD uint32_t tri_to_fields(uint32_t e) {
 // dosage fields + missing mask -> PLINK byte
 GMRM_HD uint8_t fields_to_plink(uint32_t f, uint32_t missmask) {
     uint32_t x = 0;
-#pragma unroll
+GMRM_UNROLL
     for (int k = 0; k < 4; k++) {
         const uint32_t d = (f >> (2 * k)) & 3u;
         uint32_t c = d == 2 ? 0u : (d == 1 ? 2u : 3u);
