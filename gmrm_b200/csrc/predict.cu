@@ -10,6 +10,8 @@ namespace gmrm {
 
 namespace {
 
+// [kernels-begin]  (tests/emu/ compiles the text between these markers for the host, CTA by CTA with one thread per
+// CUDA thread, to check the kernels' indexing without a GPU; nothing in the product depends on that)
 constexpr int kGvThreads = 128;     // one thread per 32-bit word (16 individuals) of a column
 constexpr int kGvStage = 32;        // markers whose coefficients are staged in shared memory per round
 constexpr int kGvLoads = 8;         // column words in flight per thread
@@ -153,28 +155,39 @@ __global__ void iota_kernel(int32_t* __restrict__ x, int n) {
     if (i < n) x[i] = i;
 }
 
-}  // namespace
-
-int gvalue_chunks(int nmark) {
-    // enough (word-block, chunk) CTAs to fill the GPU for short blocks too, few enough partial buffers to stay small
+// enough (word-block, chunk) CTAs to fill the GPU for short blocks too, few enough partial buffers to stay small
+inline int gvalue_chunks_of(int nmark) {
     if (nmark <= 0) return 1;
     const int c = (nmark + kGvStage - 1) / kGvStage;
     return c < 64 ? c : 64;
 }
+// launch geometry of the three genetic-value kernels for a block of nmark markers
+struct GvPlan { int nchunk, chunk_len, nwords, word_blocks; };
+inline GvPlan gvalue_plan(const Layout& L, int nmark) {
+    GvPlan p;
+    p.nchunk = gvalue_chunks_of(nmark);
+    p.chunk_len = nmark > 0 ? (nmark + p.nchunk - 1) / p.nchunk : 1;
+    p.nwords = (int)(L.col_stride / 4);
+    p.word_blocks = (p.nwords + kGvThreads - 1) / kGvThreads;
+    return p;
+}
+// [kernels-end]
+
+}  // namespace
+
+int gvalue_chunks(int nmark) { return gvalue_chunks_of(nmark); }
 
 void launch_gvalues(const uint8_t* bed, const Layout& L, const uint32_t* miss_off, const uint32_t* miss_idx, int m_begin, int m_end,
                     const double* mave, const double* msig, const double* beta, const uint8_t* keep, const uint8_t* mask4,
                     double* part, double* g, double* add, cudaStream_t s) {
     const int nmark = m_end - m_begin;
-    const int nchunk = gvalue_chunks(nmark);
-    const int chunk_len = nmark > 0 ? (nmark + nchunk - 1) / nchunk : 1;
-    const int nwords = (int)(L.col_stride / 4);
+    const GvPlan pl = gvalue_plan(L, nmark);
     if (nmark > 0) {
-        dim3 grid((unsigned)((nwords + kGvThreads - 1) / kGvThreads), (unsigned)nchunk);
-        gvalue_partial_kernel<<<grid, kGvThreads, 0, s>>>(bed, L.col_stride, nwords, m_begin, m_end, chunk_len, mave, msig, beta, keep, part, L.npad);
-        gvalue_missing_kernel<<<nchunk, 256, 0, s>>>(miss_off, miss_idx, m_begin, m_end, chunk_len, mave, msig, beta, keep, part, L.npad);
+        dim3 grid((unsigned)pl.word_blocks, (unsigned)pl.nchunk);
+        gvalue_partial_kernel<<<grid, kGvThreads, 0, s>>>(bed, L.col_stride, pl.nwords, m_begin, m_end, pl.chunk_len, mave, msig, beta, keep, part, L.npad);
+        gvalue_missing_kernel<<<pl.nchunk, 256, 0, s>>>(miss_off, miss_idx, m_begin, m_end, pl.chunk_len, mave, msig, beta, keep, part, L.npad);
     }
-    gvalue_reduce_kernel<<<(unsigned)((L.npad + 255) / 256), 256, 0, s>>>(part, nmark > 0 ? nchunk : 0, L.npad, L.N, mask4, g, add);
+    gvalue_reduce_kernel<<<(unsigned)((L.npad + 255) / 256), 256, 0, s>>>(part, nmark > 0 ? pl.nchunk : 0, L.npad, L.N, mask4, g, add);
 }
 
 void launch_predict_residual(const double* y, const double* g, const double* g_k, const Layout& L, double* y_k, cudaStream_t s) {
