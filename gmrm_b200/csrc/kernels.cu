@@ -1,4 +1,6 @@
 // sm_100a kernels of the Gibbs marker loop (see kernels.cuh, layout.h).
+#include <atomic>
+
 #include "kernels.cuh"
 
 #include <cstdio>
@@ -1264,15 +1266,25 @@ void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* ro
     }
 }
 
+// cudaFuncSetAttribute acts on the current device only, and the CLI drives several GPUs from one process (one host
+// thread each): the opt-in to more than 48 KB of dynamic shared memory is tracked per device.
+constexpr int kMaxDevices = 64;
+template <typename Kernel>
+static bool ensure_dyn_smem(Kernel kernel, std::atomic<int>* have, int bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return false;
+    if (have[dev].load(std::memory_order_acquire) >= bytes) return true;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    have[dev].store(bytes, std::memory_order_release);
+    return true;
+}
+
 template <int T>
 static int step_launch_t(const Layout& L, const StepParams& p, cudaStream_t s) {
     const int smem = step_smem_bytes(L, p.V, T, p.rows_per_pass);
     if (smem < 0) return -3;
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem) != cudaSuccess) return -1;
-        attr = true;
-    }
+    static std::atomic<int> have[kMaxDevices];
+    if (!ensure_dyn_smem(step_kernel<T>, have, kMaxDynSmem)) return -1;
     // every launch asks for the full 227 KB, update-only ones included: a different dynamic size would make the
     // driver re-partition L1/shared memory between consecutive launches of the marker loop
     (void)smem;
@@ -1308,11 +1320,8 @@ void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int mar
 }
 void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, cudaStream_t s) {
     const int smem = G * 256 * (int)sizeof(double);
-    static int attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(beta_sq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        attr = smem;
-    }
+    static std::atomic<int> have[kMaxDevices];
+    if (smem > 48 * 1024) ensure_dyn_smem(beta_sq_kernel, have, smem);
     beta_sq_kernel<<<T, 256, smem, s>>>(betas, group, Mloc, G, out);
 }
 void launch_group_consts(int T, int G, int K, int N, const double* sigmag, const double* sigmae, const double* pi, const double* cva,
