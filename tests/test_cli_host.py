@@ -212,7 +212,6 @@ def test_cli_predict_rejects_a_history_of_another_size(data, tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(reason="predict.cu: first run on hardware pending", strict=False)
 @pytest.mark.parametrize("vranks", [1, 3])
 def test_cli_predict_matches_oracle(data, oracle, vranks):
     out = os.path.join(data["tmp"], f"pred_{vranks}")
