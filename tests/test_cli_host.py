@@ -232,3 +232,15 @@ def test_cli_predict_matches_oracle(data, oracle, vranks):
         assert np.array_equal(idx, np.flatnonzero(keep)) and [r_[2] for r_ in rows] == [299 - i for i in idx]
         for c, name in ((3, "beta"), (4, "tdist"), (5, "se"), (6, "pval")):
             np.testing.assert_allclose([r_[c] for r_ in rows], want[name][idx], rtol=1e-9, atol=2e-15, err_msg=name)
+
+
+def test_cli_trunc_markers(data, tmp_path):
+    """--trunc-markers n keeps the first n markers (dimensions.hpp:12-14); the group file may list more (bayes.cpp:844-852)."""
+    r = run(base_args(data, str(tmp_path / "o")) + ["--trunc-markers", "120", "--check-inputs", "--dump-inputs", str(tmp_path)])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "--trunc-markers 120" in r.stdout and "M = 120 markers" in r.stdout
+    groups = np.fromfile(tmp_path / "groups.i32", dtype=np.int32)
+    want = np.array([int(l.split()[1]) for l in open(data["paths"]["gri"])], dtype=np.int32)
+    assert groups.size >= 120 and np.array_equal(groups[:120], want[:120])
+    r = run(base_args(data, str(tmp_path / "o")) + ["--trunc-markers", "100000", "--check-inputs"])   # larger than Mt: no effect
+    assert r.returncode == 0 and "M = 300 markers" in r.stdout
