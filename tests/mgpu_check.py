@@ -60,6 +60,8 @@ def main():
         hist.append(st)
     eps = np.stack([e.epsilon(t) for t in range(T)])
     e.close()
+    if len(sys.argv) > 2 and sys.argv[2] == "predict":
+        predict_check(rank, world, local, inp, N, M, T)
     gathered = [None] * world
     dist.all_gather_object(gathered, (lo, n, hist, eps))
     ok = True
@@ -83,6 +85,42 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     return 0 if ok else 1
+
+
+def predict_check(rank, world, local, inp, N, M, T):
+    """Bayes::predict (bayes.cpp:14-284) over the marker shards: one all-reduce of the genetic values, every GPU its
+    blocks' statistics; against the oracle with the same total number of blocks.  Rank 0 prints MGPU_PREDICT_OK."""
+    Vl = 2
+    R = Vl * world
+    rng = np.random.default_rng(5)
+    hist = rng.normal(0, 0.02, size=(3, M)) * (rng.random((3, M)) < 0.3)
+    keep = (rng.random(M) > 0.04).astype(np.uint8)
+    e = api.Engine(N=N, Mt=M, T=T, G=1, K=2, vranks=R, world_size=world, world_rank=rank, device=local)
+    uid = [api.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    e.comm_init(uid[0])
+    lo, n = e.marker_begin, e.marker_count
+    e.upload_bed(inp["bed"][lo:lo + n])
+    e.finalize_bed()
+    for t in range(T):
+        e.set_phenotype(t, inp["eps0"][t], inp["mask4"][t], int(inp["nonas"][t]))
+    e.compute_marker_stats()
+    got = [e.predict(t, inp["eps0"][t], hist.mean(axis=0)[lo:lo + n], keep[lo:lo + n]) for t in range(T)]
+    e.close()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (lo, n, got))
+    if rank == 0:
+        for t in range(T):
+            mave, msig = O.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
+            want = O.predict(inp["bed"], inp["mask4"][t], int(inp["nonas"][t]), inp["eps0"][t], mave, msig, hist, N=N, R=R, keep=keep)
+            scale = np.abs(want["g"]).max()
+            for (lo_g, n_g, got_g) in gathered:
+                assert np.abs(got_g[t]["g"] - want["g"][:N]).max() <= 1e-11 * scale
+                k = keep[lo_g:lo_g + n_g] != 0
+                for name in ("beta", "tdist", "se", "pval"):
+                    np.testing.assert_allclose(got_g[t][name][k], want[name][lo_g:lo_g + n_g][k], rtol=1e-9, atol=1e-13, err_msg=name)
+                    assert np.all(np.isnan(got_g[t][name][~k]))
+        print(f"MGPU_PREDICT_OK world={world} R={R}", flush=True)
 
 
 if __name__ == "__main__":

@@ -19,3 +19,14 @@ def test_two_gpu_chain_matches_oracle(sync_rate):
            "--master-port", str(29611 + sync_rate), os.path.join(ROOT, "tests", "mgpu_check.py"), str(sync_rate)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "MGPU_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.xfail(reason="multi-GPU predict: not yet run on hardware", strict=False)
+def test_two_gpu_predict_matches_oracle():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29617", os.path.join(ROOT, "tests", "mgpu_check.py"), "1", "predict"]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "MGPU_PREDICT_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
