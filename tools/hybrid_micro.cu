@@ -1,8 +1,10 @@
 // Microbenchmark 4 (prepared for round 2, DESIGN.md section 5 "next levers" item 1): can the direct decode path
 // (SHF + DFMA per genotype, fp64/ALU pipes) run next to the table look-up path (PRMT + LDS.64 + DADD per four
 // genotypes, LSU pipe) in the same warps, and what does the mix deliver in genotypes per clock and SM?
-//   kernel<L, D>: per iteration a warp handles L look-up words (4 quads each) and D direct words (16 genotypes each)
+//   k<L, D>: per iteration every warp handles L look-up words (4 quads each) and D direct words (16 genotypes each)
 //   held in registers (an LCG makes new ones; bytes are kept below 81 for the look-ups).
+//   ks<WL>: warp-specialised -- WL warps do look-ups only, the others the direct path only (the form a hybrid step
+//   kernel would take: the direct warps keep their rows' residuals in registers, the look-up warps keep theirs in tables).
 // The table geometry is the product's (layout.h): 81 entries x 256 B per region, 2 regions per slot, 5 slots.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/hybrid_micro tools/hybrid_micro.cu
 #include <cstdio>
@@ -51,13 +53,17 @@ __device__ __forceinline__ void direct_word(uint32_t w, double& D, const double 
     }
 }
 
-template <int L, int D>
-__global__ void __launch_bounds__(512, 1) k(double* out, const double* zero, int iters) {
+__device__ __forceinline__ void fill_tables() {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(smem);
     double* tab = reinterpret_cast<double*>(smem + (kBase - b0));
     for (int i = threadIdx.x; i < kSlots * kSlot / 8; i += blockDim.x) tab[i] = 1e-3 * (i & 1023);
     __syncthreads();
+}
+
+// the stream of one warp: L look-up words and D direct words per iteration
+template <int L, int D>
+__device__ __forceinline__ double stream(const double* zero, int iters) {
     const uint32_t lanebase = (threadIdx.x & 15) * 8;
     uint32_t lw[L > 0 ? L : 1], dw[D > 0 ? D : 1];
     double lacc[L > 0 ? L : 1], dacc[D > 0 ? D : 1], Dm[D > 0 ? D : 1], wt[16];
@@ -88,7 +94,21 @@ __global__ void __launch_bounds__(512, 1) k(double* out, const double* zero, int
     for (int i = 0; i < (L > 0 ? L : 1); i++) s += lacc[i];
 #pragma unroll
     for (int i = 0; i < (D > 0 ? D : 1); i++) s += dacc[i] + Dm[i];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    return s;
+}
+
+// every warp runs the same mix
+template <int L, int D>
+__global__ void __launch_bounds__(512, 1) k(double* out, const double* zero, int iters) {
+    fill_tables();
+    out[blockIdx.x * blockDim.x + threadIdx.x] = stream<L, D>(zero, iters);
+}
+// warp-specialised: warps below WL run look-ups only (8 words per iteration), the others the direct path only (4 words)
+template <int WL>
+__global__ void __launch_bounds__(512, 1) ks(double* out, const double* zero, int iters_lookup, int iters_direct) {
+    fill_tables();
+    const bool lookup = (int)(threadIdx.x >> 5) < WL;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = lookup ? stream<8, 0>(zero, iters_lookup) : stream<0, 4>(zero, iters_direct);
 }
 
 template <int L, int D>
@@ -107,6 +127,25 @@ void run(int warps, int nsm, double* out, double* zero) {
     printf("look-up words %d + direct words %d per iteration, %2d warps/SM: %7.3f ms  %6.2f genotypes/clk/SM (look-up share %5.1f, direct %5.1f)  (%s)\n",
            L, D, warps, ms, per_clk, per_clk * L / (L + D), per_clk * D / (L + D), cudaGetErrorString(cudaGetLastError()));
 }
+// iteration counts are set so that both roles finish together when the direct warps sustain `ratio` times the per-warp
+// genotype rate of the look-up warps; the printed split shows what each role delivered in the common time
+template <int WL>
+void run_spec(int warps, int nsm, double* out, double* zero, double ratio) {
+    const int it_l = 2048, it_d = (int)(2048 * ratio * 8 / 4), smem = 232448;
+    cudaFuncSetAttribute(ks<WL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    ks<WL><<<nsm, warps * 32, smem>>>(out, zero, 8, 8);
+    cudaEventRecord(a);
+    ks<WL><<<nsm, warps * 32, smem>>>(out, zero, it_l, it_d);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    const double gl = (double)WL * 32 * it_l * 16.0 * 8, gd = (double)(warps - WL) * 32 * it_d * 16.0 * 4;
+    const double cyc = ms * 1e-3 * clk * 1e3;
+    printf("specialised: %2d look-up warps + %2d direct warps, direct/look-up per-warp rate %.2f: %7.3f ms  %6.2f genotypes/clk/SM (look-up %5.1f, direct %5.1f)  (%s)\n",
+           WL, warps - WL, ratio, ms, (gl + gd) / cyc, gl / cyc, gd / cyc, cudaGetErrorString(cudaGetLastError()));
+}
+
 int main() {
     int nsm; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
     double *out, *zero;
@@ -117,6 +156,10 @@ int main() {
         run<8, 1>(warps, nsm, out, zero); run<8, 2>(warps, nsm, out, zero); run<6, 2>(warps, nsm, out, zero);
         run<4, 2>(warps, nsm, out, zero); run<4, 4>(warps, nsm, out, zero);
     }
+    for (double ratio : {0.5, 0.75, 1.0, 1.5}) {
+        run_spec<12>(16, nsm, out, zero, ratio); run_spec<13>(16, nsm, out, zero, ratio); run_spec<14>(16, nsm, out, zero, ratio);
+    }
+    run_spec<16>(16, nsm, out, zero, 1.0);      // all look-up, through the specialised kernel (control)
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
