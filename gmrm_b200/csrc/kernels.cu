@@ -153,6 +153,7 @@ __global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int 
 // counts of each dosage under the trait's NA mask: the sums of the
 // reference's loops are sums of small integers, hence these counts exactly.
 // =====================================================================================
+// [stats-begin]  (tests/test_stats_kernel_emulated.py compiles the text up to [stats-end] for the host, see tests/emu/)
 __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
                                                     const uint8_t* __restrict__ mask4, const uint32_t* __restrict__ miss_off,
                                                     const uint32_t* __restrict__ miss_idx, const int32_t* __restrict__ nonas,
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ 
         }
     }
 }
+// [stats-end]
 
 // =====================================================================================
 // residual helpers

@@ -36,6 +36,8 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
     emu_warp_barrier[warp]->arrive_and_wait();
     return r;
 }
+inline int __shfl_xor_sync(unsigned m, int v, int o) { return (int)__shfl_xor_sync(m, (double)v, o); }   // exact for |v| < 2^53
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 using std::max;
 using std::min;
 
