@@ -10,6 +10,7 @@ namespace gmrm {
 // =====================================================================================
 // small device helpers
 // =====================================================================================
+// [helpers-begin]  (tests/test_step_kernel_emulated.py compiles [helpers-*] and [step-*] for the host, see tests/emu/)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ double warp_sum_fixed(double v) {   // fixed xor tree: reproducible
@@ -30,6 +31,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* red) {
         for (int i = 0; i < nw; i++) t += red[i];
     return t;
 }
+// [helpers-end]
 
 // =====================================================================================
 // .bed ingestion: PLINK bytes <-> base-3 quad bytes + missing lists (bit-exact, invertible)
@@ -275,6 +277,7 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // At the end the CTA writes partial[v][t][cta] and its sum of residuals spart[t][cta]; the sampler kernel
 // adds the nsm partials of a marker in a fixed order.
 // =====================================================================================
+// [step-begin]
 __device__ __forceinline__ uint32_t ldg_stream_u32(const uint8_t* p) {
     uint32_t v;
     asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -842,6 +845,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     if (profme) atomicAdd(&p.prof[7], 1ull);
 #undef GMRM_TICK
 }
+// [step-end]
 
 // =====================================================================================
 // K2: one warp per virtual rank: finish the dot product, sample, publish.

@@ -5,6 +5,7 @@
 #include <barrier>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
@@ -17,6 +18,10 @@ inline EmuDim3 blockDim, gridDim;
 inline std::unique_ptr<std::barrier<>> emu_block_barrier;
 inline std::vector<std::unique_ptr<std::barrier<>>> emu_warp_barrier;
 inline std::vector<double> emu_warp_buf;     // [warp][32]
+inline std::vector<uint64_t> emu_warp_buf64;  // [warp][32] raw 64-bit payloads (indexed shuffles)
+
+// shared memory of the CTA being run: "absolute shared addresses" are offsets into this array
+alignas(256) inline uint8_t emu_smem_storage[256 * 1024];
 
 #define __global__
 #define __device__
@@ -24,6 +29,11 @@ inline std::vector<double> emu_warp_buf;     // [warp][32]
 #define __forceinline__ inline
 #define __shared__ static
 #define __launch_bounds__(...)
+#define __align__(n) alignas(n)
+
+struct int2 { int x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
 
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
@@ -38,6 +48,43 @@ inline double __shfl_xor_sync(unsigned, double v, int o) {
 }
 inline int __shfl_xor_sync(unsigned m, int v, int o) { return (int)__shfl_xor_sync(m, (double)v, o); }   // exact for |v| < 2^53
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+// indexed shuffle: every lane of the warp publishes its value, then reads lane `src`'s
+template <typename T> inline T emu_shfl_idx(T v, int src) {
+    static_assert(sizeof(T) <= 8, "payload");
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t raw = 0; memcpy(&raw, &v, sizeof(T));
+    emu_warp_buf64[warp * 32 + lane] = raw;
+    emu_warp_barrier[warp]->arrive_and_wait();
+    raw = emu_warp_buf64[warp * 32 + ((unsigned)src & 31u)];
+    emu_warp_barrier[warp]->arrive_and_wait();
+    T r; memcpy(&r, &raw, sizeof(T));
+    return r;
+}
+inline int __shfl_sync(unsigned, int v, int src) { return emu_shfl_idx(v, src); }
+inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl_idx(v, src); }
+template <typename T> inline T __ldcg(const T* p) { return *p; }
+inline long long clock64() { return 0; }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline void __trap() { abort(); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned atomicOr(unsigned* p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicExch(int* p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const uint8_t*)p - emu_smem_storage); }
+template <typename T> inline T emu_lds(uint32_t addr) { T v; memcpy(&v, emu_smem_storage + addr, sizeof(T)); return v; }
+template <typename T> inline void emu_sts(uint32_t addr, T v) { memcpy(emu_smem_storage + addr, &v, sizeof(T)); }
+// prmt.b32 in its default mode: result byte i = byte (selector nibble i & 7) of {b, a}; bit 3 of a nibble replicates the sign
+inline uint32_t emu_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    const uint64_t src = ((uint64_t)b << 32) | a;
+    uint32_t d = 0;
+    for (int i = 0; i < 4; i++) {
+        const uint32_t n = (sel >> (4 * i)) & 0xfu;
+        uint32_t byte = (uint32_t)(src >> (8 * (n & 7u))) & 0xffu;
+        if (n & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+        d |= byte << (8 * i);
+    }
+    return d;
+}
 using std::max;
 using std::min;
 
@@ -52,6 +99,7 @@ inline void emu_launch(EmuDim3 grid, EmuDim3 block, const std::function<void()>&
             emu_warp_barrier.clear();
             for (unsigned w = 0; w < nwarps; w++) emu_warp_barrier.push_back(std::make_unique<std::barrier<>>(std::min(32u, nthreads - 32 * w)));
             emu_warp_buf.assign((size_t)nwarps * 32, 0.0);
+            emu_warp_buf64.assign((size_t)nwarps * 32, 0);
             std::vector<std::thread> th;
             for (unsigned t = 0; t < nthreads; t++)
                 th.emplace_back([&, t] {

@@ -1,0 +1,150 @@
+"""CPU: the step kernel of the Gibbs path (gmrm_b200/csrc/kernels.cu: pending updates -> look-up tables -> column
+stream) executed on the host through tests/emu/cuda_emu.h, its inline PTX rewritten statement by statement
+(tests/emu/asm_to_host.py: PRMT, LDS/STS with absolute shared addresses, streaming loads), and compared with the oracle:
+Bayes::dot_product's sums (src/bayes.cpp:749-766) and Phenotype::update_epsilon (src/phenotype.cpp:326-390).
+
+One std::thread per CUDA thread (512 per CTA), barriers for __syncthreads and the warp shuffles.  It checks the
+kernel's logic -- table geometry, row ownership, the transposed butterfly, the published-list update with missing
+genotypes and NAs -- on shapes that take seconds; it says nothing about the CUDA build or its speed, which stay with
+the GPU parity tests.  Test infrastructure only: the product has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from gmrm_b200 import api, synth
+from test_predict_kernels_emulated import p, to_device_layout
+
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+import asm_to_host  # noqa: E402
+
+SRC = os.path.join(ROOT, "gmrm_b200", "csrc", "kernels.cu")
+EMU = os.path.join(ROOT, "tests", "emu")
+
+TAIL = r'''
+extern "C" int emu_step(const uint8_t* bed, int N, int nsm, const int32_t* cols, int V, double* eps, const uint8_t* mask4, int T,
+                        int tc, int rpp, int npass, double* partial, double* spart, const double* plist, int pV,
+                        const uint32_t* miss_off, const uint32_t* miss_idx) {
+    using namespace gmrm;
+    const Layout L = make_layout(N, nsm);
+    int32_t err = 0;
+    for (int t0 = 0; t0 < T; t0 += tc) {
+        StepParams q{};
+        q.bed = bed; q.col_stride = L.col_stride; q.nrows = L.nrows; q.cols = cols; q.V = V; q.eps = eps; q.npad = L.npad;
+        q.Ttot = T; q.t0 = t0; q.rows_per_pass = rpp; q.npass = npass; q.partial = partial; q.spart = spart;
+        q.mask4 = mask4; q.pV = pV; q.err = &err; q.pf = 1;
+        if (plist) { q.pG = 1; q.plist = plist; q.pbed[0] = bed; q.pmiss_off[0] = miss_off; q.pmiss_idx[0] = miss_idx; }
+        const int Tl = std::min(tc, T - t0);
+        emu_launch(EmuDim3(nsm), EmuDim3(kStepThreads), [&] {
+            switch (Tl) {
+            case 1: step_kernel<1>(q); break;
+            case 2: step_kernel<2>(q); break;
+            case 3: step_kernel<3>(q); break;
+            case 4: step_kernel<4>(q); break;
+            }
+        });
+    }
+    return err;
+}
+'''
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    text = open(SRC).read()
+    helpers = text[text.index("// [helpers-begin]"):text.index("// [helpers-end]")]
+    step = text[text.index("// [step-begin]"):text.index("// [step-end]")]
+    body, n = asm_to_host.rewrite(helpers + step)
+    assert n >= 14                                              # every inline-PTX statement of the region has a host form
+    body = body.replace("#pragma unroll\n", "")
+    decl = "extern __shared__ __align__(16) uint8_t smem_raw[];"
+    assert decl in body
+    body = body.replace(decl, "uint8_t* smem_raw = emu_smem_storage + 16;")
+    d = tmp_path_factory.mktemp("emu_step")
+    cpp = d / "step_emu.cpp"
+    cpp.write_text('#include "cuda_emu.h"\n#include "kernels.cuh"\nnamespace gmrm {\n' + body + "\n}\n" + TAIL)
+    so = d / "libstep_emu.so"
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
+                    "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-I", os.path.join(EMU, "fake_cuda"), "-I", EMU,
+                    "-I", os.path.join(ROOT, "gmrm_b200", "csrc"), str(cpp), "-o", str(so)], check=True)
+    return C.CDLL(str(so))
+
+
+def dosages(bed, N):
+    codes = (bed[:, :, None] >> (2 * np.arange(4))) & 3
+    return np.where(codes == 0, 2.0, np.where(codes == 2, 1.0, 0.0)).reshape(bed.shape[0], -1)[:, :N]
+
+
+@pytest.mark.parametrize("N,nsm,T,M,na,miss", [(777, 1, 3, 33, 0.02, 0.01), (1795, 2, 2, 40, 0.0, 0.02), (5119, 1, 1, 50, 0.01, 0.0),
+                                               (3000, 3, 1, 21, 0.03, 0.03), (1024, 1, 4, 18, 0.0, 0.0)])
+def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M, na, miss):
+    d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=na, missing_rate=miss, seed=N % 71)
+    pp = d["paths"]
+    inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
+    tri, miss_off, miss_idx, nrows = to_device_layout(inp["bed"], N, nsm)
+    npad, stride = nrows * 256, nrows * 64
+    mask4 = np.zeros((T, stride), dtype=np.uint8)
+    mask4[:, : inp["mask4"].shape[1]] = inp["mask4"]
+    eps = np.zeros((T, npad))
+    eps[:, :N] = inp["eps0"][:, :N]
+    a = dosages(inp["bed"], N)
+    rng = np.random.default_rng(M)
+
+    def launch(cols, plist=None, pV=0):
+        V = len(cols)
+        plan = api.step_plan(N, nsm, V, T, want_ranges=False)
+        assert plan is not None
+        cols_a = np.ascontiguousarray(cols, dtype=np.int32) if V else np.zeros(1, np.int32)
+        partial = np.full((max(V, 1), T, nsm), np.nan)
+        spart = np.full((T, nsm), np.nan)
+        rc = emu.emu_step(p(tri), N, nsm, p(cols_a), V, p(eps), p(mask4), T, plan["traits_per_launch"], plan["rows_per_pass"],
+                          plan["npass"], p(partial), p(spart), p(plist), pV, p(miss_off), p(miss_idx))
+        assert rc == 0
+        return partial, spart
+
+    # (1) dot products of a shuffled subset of the columns, with a hole (-1 = no marker for that virtual rank)
+    cols = rng.permutation(M)[: max(3, (2 * M) // 3)].astype(np.int32)
+    cols[1] = -1
+    partial, spart = launch(cols)
+    for t in range(T):
+        got = partial[:, t, :].sum(axis=1)
+        want = a[np.maximum(cols, 0)] @ eps[t, :N]
+        ok = cols >= 0
+        assert np.abs(got[ok] - want[ok]).max() <= 1e-12 * max(np.abs(want).max(), 1.0)
+        assert abs(spart[t].sum() - eps[t].sum()) <= 1e-12 * max(np.abs(eps[t]).sum(), 1.0)
+
+    # (2) a published list of the previous step (ordered, compacted: header count + items {lam, mave, col, v}), then dots again
+    pV = 12
+    ld = 2 + 3 * pV
+    plist = np.zeros(T * ld)
+    want_eps = [np.concatenate([eps[t, :N], np.zeros((-N) % 4)]) for t in range(T)]
+    for t in range(T):
+        mave, msig = oracle.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
+        k = int(rng.integers(1, pV + 1)) if t != 1 else 0               # trait 1 publishes nothing
+        pub = np.sort(rng.choice(M, size=k, replace=False))
+        plist[t * ld: t * ld + 1].view(np.int32)[0] = k
+        for i, j in enumerate(pub):
+            db = float(rng.normal(0, 0.05))
+            item = plist[t * ld + 2 + 3 * i: t * ld + 5 + 3 * i]
+            item[0], item[1] = db * msig[j], mave[j]
+            item[2:3].view(np.int32)[:] = (int(j), i)
+            oracle.update_eps(want_eps[t], inp["mask4"][t], inp["bed"][j], db, mave[j], msig[j])
+    cols2 = rng.permutation(M)[:9].astype(np.int32)
+    partial, spart = launch(cols2, plist, pV)
+    for t in range(T):
+        np.testing.assert_allclose(eps[t, :N], want_eps[t][:N], rtol=0, atol=1e-13)
+        assert not eps[t, N:].any()
+        got = partial[:, t, :].sum(axis=1)
+        want = a[cols2] @ want_eps[t][:N]
+        assert np.abs(got - want).max() <= 1e-12 * max(np.abs(want).max(), 1.0)
+
+    # (3) update-only launch (V = 0): the flush at the end of an iteration
+    before = eps.copy()
+    launch([], plist, pV)
+    for t in range(T):
+        changed = np.abs(eps[t] - before[t]).max()
+        assert (changed > 0) == (plist[t * ld: t * ld + 1].view(np.int32)[0] > 0)
