@@ -850,6 +850,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 // =====================================================================================
 // K2: one warp per virtual rank: finish the dot product, sample, publish.
 // =====================================================================================
+// [sample-begin]  (tests/test_marker_loop_emulated.py compiles the text up to [sample-end] for the host, see tests/emu/)
 struct DotPieces { double dpa, dpb; };
 
 // sum a*eps and sum b*eps of trait t for the marker of virtual rank r (all lanes get the result)
@@ -1074,6 +1075,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
     }
     if (tid == 0) *p.ticket = 0u;
 }
+// [sample-end]
 
 // test hook behind gmrm_dot_products: out[v*T+t] = Bayes::dot_product
 __global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, double* __restrict__ out) {

@@ -62,6 +62,23 @@ template <typename T> inline T emu_shfl_idx(T v, int src) {
 }
 inline int __shfl_sync(unsigned, int v, int src) { return emu_shfl_idx(v, src); }
 inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl_idx(v, src); }
+inline int __shfl_up_sync(unsigned, int v, unsigned delta) {
+    const unsigned lane = threadIdx.x & 31;
+    const int r = emu_shfl_idx(v, lane >= delta ? (int)(lane - delta) : (int)lane);
+    return lane >= delta ? r : v;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    emu_warp_buf64[warp * 32 + lane] = pred ? 1u : 0u;
+    emu_warp_barrier[warp]->arrive_and_wait();
+    unsigned m = 0;
+    for (unsigned l = 0; l < 32; l++) m |= (unsigned)emu_warp_buf64[warp * 32 + l] << l;
+    emu_warp_barrier[warp]->arrive_and_wait();
+    return m;
+}
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline long long clock64() { return 0; }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }
