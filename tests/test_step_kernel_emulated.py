@@ -50,6 +50,34 @@ extern "C" int emu_step(const uint8_t* bed, int N, int nsm, const int32_t* cols,
     }
     return err;
 }
+
+// update-only launch with the lists of TWO GPUs (world_size 2, list exchange): list g holds columns of shard g, whose
+// bytes and missing lists are read from "GPU g's" buffers (peer memory on hardware); this GPU is shard 0.
+extern "C" int emu_update_two_lists(const uint8_t* bed0, const uint8_t* bed1, int N, int nsm, double* eps, const uint8_t* mask4, int T,
+                                    int tc, int rpp, int npass, const double* plists /* [2][T][ld] */, int pV,
+                                    const uint32_t* moff0, const uint32_t* midx0, const uint32_t* moff1, const uint32_t* midx1) {
+    using namespace gmrm;
+    const Layout L = make_layout(N, nsm);
+    int32_t err = 0;
+    for (int t0 = 0; t0 < T; t0 += tc) {
+        StepParams q{};
+        q.bed = bed0; q.col_stride = L.col_stride; q.nrows = L.nrows; q.V = 0; q.eps = eps; q.npad = L.npad;
+        q.Ttot = T; q.t0 = t0; q.rows_per_pass = rpp; q.npass = npass; q.mask4 = mask4; q.pV = pV; q.err = &err; q.pf = 1;
+        q.pG = 2; q.plist = plists;
+        q.pbed[0] = bed0; q.pmiss_off[0] = moff0; q.pmiss_idx[0] = midx0;
+        q.pbed[1] = bed1; q.pmiss_off[1] = moff1; q.pmiss_idx[1] = midx1;
+        const int Tl = std::min(tc, T - t0);
+        emu_launch(EmuDim3(nsm), EmuDim3(kStepThreads), [&] {
+            switch (Tl) {
+            case 1: step_kernel<1>(q); break;
+            case 2: step_kernel<2>(q); break;
+            case 3: step_kernel<3>(q); break;
+            case 4: step_kernel<4>(q); break;
+            }
+        });
+    }
+    return err;
+}
 '''
 
 
@@ -148,3 +176,44 @@ def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M
     for t in range(T):
         changed = np.abs(eps[t] - before[t]).max()
         assert (changed > 0) == (plist[t * ld: t * ld + 1].view(np.int32)[0] > 0)
+
+
+def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
+    """world_size 2, list exchange (bayes.cpp:495-553 replaced by published lists): the update phase applies GPU 0's list, then
+    GPU 1's -- global virtual-rank order -- reading every published column from the shard that owns it."""
+    N, M, T, nsm, pV = 1290, 48, 2, 2, 7
+    d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=0.02, missing_rate=0.02, seed=12)
+    pp = d["paths"]
+    inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
+    half = M // 2
+    shards = [to_device_layout(inp["bed"][:half], N, nsm), to_device_layout(inp["bed"][half:], N, nsm)]
+    nrows = shards[0][3]
+    npad, stride = nrows * 256, nrows * 64
+    mask4 = np.zeros((T, stride), dtype=np.uint8)
+    mask4[:, : inp["mask4"].shape[1]] = inp["mask4"]
+    eps = np.zeros((T, npad))
+    eps[:, :N] = inp["eps0"][:, :N]
+    rng = np.random.default_rng(3)
+    ld = 2 + 3 * pV
+    plists = np.zeros((2, T, ld))
+    want = [np.concatenate([eps[t, :N], np.zeros((-N) % 4)]) for t in range(T)]
+    for t in range(T):
+        mave, msig = oracle.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
+        for g in range(2):                                         # GPU order = virtual-rank order
+            k = int(rng.integers(1, pV + 1))
+            pub = np.sort(rng.choice(half, size=k, replace=False))  # columns local to shard g
+            plists[g, t, :1].view(np.int32)[0] = k
+            for i, jl in enumerate(pub):
+                j = g * half + int(jl)
+                db = float(rng.normal(0, 0.05))
+                item = plists[g, t, 2 + 3 * i: 5 + 3 * i]
+                item[0], item[1] = db * msig[j], mave[j]
+                item[2:3].view(np.int32)[:] = (int(jl), i)
+                oracle.update_eps(want[t], inp["mask4"][t], inp["bed"][j], db, mave[j], msig[j])
+    plan = api.step_plan(N, nsm, 0, T, want_ranges=False)
+    rc = emu.emu_update_two_lists(p(shards[0][0]), p(shards[1][0]), N, nsm, p(eps), p(mask4), T, plan["traits_per_launch"],
+                                  plan["rows_per_pass"], plan["npass"], p(plists), pV, p(shards[0][1]), p(shards[0][2]),
+                                  p(shards[1][1]), p(shards[1][2]))
+    assert rc == 0
+    for t in range(T):
+        np.testing.assert_allclose(eps[t, :N], want[t][:N], rtol=0, atol=1e-13)
