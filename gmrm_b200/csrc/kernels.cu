@@ -36,6 +36,7 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* red) {
 // =====================================================================================
 // .bed ingestion: PLINK bytes <-> base-3 quad bytes + missing lists (bit-exact, invertible)
 // =====================================================================================
+// [ingest-begin]  (tests/test_chain_emulated.py compiles the [ingest|eps|epilogue] regions for the host too, see tests/emu/)
 __global__ void transcode_kernel(const uint8_t* __restrict__ plink, int nmark, Layout L, uint8_t* __restrict__ dst,
                                  uint32_t* __restrict__ miss_counts) {
     const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -119,6 +120,7 @@ __global__ void decode_namask_kernel(const uint8_t* __restrict__ mask4, Layout L
     if (i >= L.N) return;
     na[i] = ((mask4[i >> 2] >> (i & 3)) & 1u) ? 1.0 : 0.0;   // na_lut (lut/mk_lut_na.cpp:25-29)
 }
+// [ingest-end]
 
 // Synthetic PLINK bytes: per-marker MAF ~ U(lo, hi), dosage ~ Binomial(2, p).
 __global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int first_marker, Layout L, uint32_t seed,
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ 
 // =====================================================================================
 // residual helpers
 // =====================================================================================
+// [eps-begin]
 // Phenotype::offset_epsilon twice (bayes.cpp:351,359): eps += mu_old*na; eps -= mu_new*na
 __global__ void __launch_bounds__(256) eps_offset_kernel(double* __restrict__ eps, const uint8_t* __restrict__ mask4, Layout L,
                                                          const double* __restrict__ mu_old, const double* __restrict__ mu_new) {
@@ -252,6 +255,7 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
     const double tot = block_sum_fixed(s, red);
     if (threadIdx.x == 0) out[blockIdx.x] = tot;
 }
+// [eps-end]
 
 // =====================================================================================
 // K1: one marker-step of one GPU -- apply the previous step's published updates, build the look-up
@@ -1091,6 +1095,7 @@ __global__ void __launch_bounds__(128) finish_dots_kernel(const SampleParams p, 
 // =====================================================================================
 // per-iteration prologue / epilogue
 // =====================================================================================
+// [epilogue-begin]
 // marker of (step s, local virtual rank v): Bayes::set_block_of_markers (bayes.cpp:903-925) + midx
 __global__ void steptab_kernel(int32_t* __restrict__ tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin,
                                int shuffle, uint32_t seed, int it, const int32_t* __restrict__ rep_perm) {
@@ -1185,6 +1190,7 @@ __global__ void global_draw_kernel(const GlobalDrawParams p) {
     else unit = draw_gamma(0.5 * a, p.seed, STREAM_SIGMAE, (uint32_t)p.it, 0u, (uint32_t)t);
     p.sigmae[t] = inv_scaled_chisq_from_unit(a, b, unit);
 }
+// [epilogue-end]
 
 // =====================================================================================
 // launchers

@@ -62,11 +62,13 @@ template <typename T> inline T emu_shfl_idx(T v, int src) {
 }
 inline int __shfl_sync(unsigned, int v, int src) { return emu_shfl_idx(v, src); }
 inline double __shfl_sync(unsigned, double v, int src) { return emu_shfl_idx(v, src); }
-inline int __shfl_up_sync(unsigned, int v, unsigned delta) {
+template <typename T> inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
     const unsigned lane = threadIdx.x & 31;
-    const int r = emu_shfl_idx(v, lane >= delta ? (int)(lane - delta) : (int)lane);
+    const T r = emu_shfl_idx(v, lane >= delta ? (int)(lane - delta) : (int)lane);
     return lane >= delta ? r : v;
 }
+inline uint32_t __shfl_sync(unsigned, uint32_t v, int src) { return emu_shfl_idx(v, src); }
+inline unsigned atomicAnd(unsigned* p, unsigned v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned __ballot_sync(unsigned, int pred) {
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     emu_warp_buf64[warp * 32 + lane] = pred ? 1u : 0u;
