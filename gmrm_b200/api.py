@@ -215,6 +215,14 @@ class Engine:
         out["g"] = g
         return out
 
+    def genetic_values(self, t: int, beta: np.ndarray) -> np.ndarray:
+        """g = scale(X) @ beta over ALL shards (gmrm_genetic_values; bayes.cpp:87-136): beta holds this shard's markers."""
+        b = np.ascontiguousarray(beta, dtype=np.float64)
+        assert b.size == self.marker_count
+        g = np.empty(self.N)
+        _check(lib().gmrm_genetic_values(self._h, t, _dp(b), _dp(g)))
+        return g
+
     def decode_marker(self, local_id: int):
         a = np.empty(self.N); b = np.empty(self.N)
         _check(lib().gmrm_decode_marker(self._h, local_id, _dp(a), _dp(b)))
@@ -272,6 +280,15 @@ class Engine:
         b = np.empty(self.marker_count); c = np.empty(self.marker_count, dtype=np.int32)
         _check(lib().gmrm_fetch_outputs(self._h, t, _dp(b), _ip(c)))
         return b, c
+
+    def fetch_state(self) -> dict:
+        """The global parameters snapshotted by stage_outputs() (no blocking device copy)."""
+        T, G, K = self.T, self.G, self.K
+        d = {"sigmag": np.empty((T, G)), "sigmae": np.empty(T), "pi": np.empty((T, G, K)), "mu": np.empty(T),
+             "m0": np.empty((T, G), dtype=np.int32), "cass": np.empty((T, G, K), dtype=np.int32)}
+        st = State(_dp(d["sigmag"]), _dp(d["sigmae"]), _dp(d["pi"]), _dp(d["mu"]), _ip(d["m0"]), _ip(d["cass"]))
+        _check(lib().gmrm_fetch_state(self._h, C.byref(st)))
+        return d
 
     def epsilon(self, t: int) -> np.ndarray:
         out = np.empty(self.N)

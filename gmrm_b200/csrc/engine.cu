@@ -124,6 +124,7 @@ struct gmrm_engine {
     // pinned host memory on the copy stream while the next iteration runs
     DevBuf<double> out_betas; DevBuf<int32_t> out_comp;
     double* h_out_betas = nullptr; int32_t* h_out_comp = nullptr;
+    double* h_out_state = nullptr;   // pinned: [sigmag T*G | sigmae T | pi T*G*K | mu T] doubles, then [m0 T*G | cass T*G*K] int32
     cudaEvent_t ev_staged = nullptr, ev_out = nullptr;
     bool out_pending = false;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
@@ -181,6 +182,7 @@ struct gmrm_engine {
         if (ev_out) cudaEventDestroy(ev_out);
         if (h_out_betas) cudaFreeHost(h_out_betas);
         if (h_out_comp) cudaFreeHost(h_out_comp);
+        if (h_out_state) cudaFreeHost(h_out_state);
         for (auto& e : dot_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -784,6 +786,36 @@ int gmrm_predict(gmrm_engine* e, int32_t t, const double* y, const double* beta_
     return check_step_error(e);
 }
 
+// Genetic values alone (the first sum of Bayes::predict, src/bayes.cpp:87-136): g = sum over ALL markers of all shards
+// of ((a - mave) msig) beta under the trait's NA mask.  One pass over the shard's genotypes + one all-reduce.
+int gmrm_genetic_values(gmrm_engine* e, int32_t t, const double* beta, double* g_out) {
+    if (!e || !beta || !g_out) return fail(GMRM_EINVAL, "null argument");
+    if (t < 0 || t >= e->cfg.T) return fail(GMRM_EINVAL, "trait %d out of range", t);
+    if (!e->stats_done) return fail(GMRM_EINVAL, "marker statistics not computed");
+    if (e->cfg.world_size > 1 && !e->comm) return fail(GMRM_EINVAL, "world_size > 1 needs gmrm_comm_init");
+    CU(cudaSetDevice(e->cfg.device));
+    const Layout& L = e->L;
+    const int Mloc = e->Mloc;
+    cudaStream_t s = e->stream;
+    DevBuf<double> d_beta, part, g, gk;
+    int rc;
+    const int blk = 65536;                                    // markers per launch_gvalues call (<= 64 chunks each)
+    if ((rc = d_beta.alloc(std::max(Mloc, 1))) || (rc = part.alloc((size_t)gvalue_chunks(std::min(Mloc, blk)) * L.npad)) ||
+        (rc = g.alloc((size_t)L.npad)) || (rc = gk.alloc((size_t)L.npad)))
+        return rc;
+    if (Mloc > 0) CU(cudaMemcpyAsync(d_beta.p, beta, (size_t)Mloc * 8, cudaMemcpyHostToDevice, s));
+    if ((rc = g.zero(s))) return rc;
+    for (int b0 = 0; b0 < Mloc; b0 += blk) {
+        launch_gvalues(e->bed.p, L, e->miss_off.p, e->miss_idx.p, b0, std::min(Mloc, b0 + blk), e->mave.p + (size_t)t * Mloc,
+                       e->msig.p + (size_t)t * Mloc, d_beta.p, nullptr, e->mask4.p + (size_t)t * L.col_stride, part.p, gk.p, g.p, s);
+        CU(cudaGetLastError());
+    }
+    if (e->cfg.world_size > 1) NC(g_nccl.AllReduce(g.p, g.p, (size_t)L.npad, kNcclFloat64, kNcclSum, e->comm, s));
+    CU(cudaMemcpyAsync(g_out, g.p, (size_t)L.N * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return GMRM_OK;
+}
+
 // ------------------------------------------------------------------------------------- the chain
 int gmrm_init_chain(gmrm_engine* e, const double* sigmag_init) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
@@ -938,7 +970,7 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
             if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
             launches += 1;
         }
-        if (delta_exchange || st == Mm - 1 || e->force_flush) {
+        if (delta_exchange || st == Mm - 1 || e->force_flush || e->timing_detail > 1) {   // detail 2: the update phase as its own launch, timed alone
             if ((rc = launch_step_all(e, nullptr, 0, pend, nullptr, &nl))) return rc;
             pend.any = false;
         }
@@ -1051,6 +1083,8 @@ int gmrm_get_epsilon(gmrm_engine* e, int32_t t, double* eps) {
 // gmrm_stage_outputs snapshots them on the device and starts the device-to-host copy on a second stream;
 // gmrm_fetch_outputs waits for that copy and hands the values out.  Calling run_iteration in between overlaps the
 // copy with the next iteration.
+static size_t state_doubles(const gmrm_engine* e) { const size_t T = e->cfg.T, G = e->cfg.G, K = e->cfg.K; return T * G + T + T * G * K + T; }
+static size_t state_ints(const gmrm_engine* e) { const size_t T = e->cfg.T, G = e->cfg.G, K = e->cfg.K; return T * G + T * G * K; }
 int gmrm_stage_outputs(gmrm_engine* e) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
     CU(cudaSetDevice(e->cfg.device));
@@ -1060,6 +1094,7 @@ int gmrm_stage_outputs(gmrm_engine* e) {
         rc = e->out_comp.alloc(n); if (rc) return rc;
         CU(cudaHostAlloc((void**)&e->h_out_betas, n * 8, cudaHostAllocDefault));
         CU(cudaHostAlloc((void**)&e->h_out_comp, n * 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&e->h_out_state, state_doubles(e) * 8 + state_ints(e) * 4, cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&e->ev_staged, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
         if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
@@ -1071,6 +1106,20 @@ int gmrm_stage_outputs(gmrm_engine* e) {
     CU(cudaStreamWaitEvent(e->copy_stream, e->ev_staged, 0));
     CU(cudaMemcpyAsync(e->h_out_betas, e->out_betas.p, n * 8, cudaMemcpyDeviceToHost, e->copy_stream));
     CU(cudaMemcpyAsync(e->h_out_comp, e->out_comp.p, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+    {   // the global parameters of the same iteration (what .csv records): read on the engine's stream, in order with
+        // the chain, so that the next iteration cannot overwrite them first -- a few hundred bytes
+        const size_t T = e->cfg.T, G = e->cfg.G, K = e->cfg.K;
+        double* hd = e->h_out_state;
+        int32_t* hi = reinterpret_cast<int32_t*>(hd + state_doubles(e));
+        CU(cudaMemcpyAsync(hd, e->sigmag.p, T * G * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hd + T * G, e->sigmae.p, T * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hd + T * G + T, e->pi.p, T * G * K * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hd + T * G + T + T * G * K, e->mu.p, T * 8, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hi, e->m0.p, T * G * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaMemcpyAsync(hi + T * G, e->cass.p, T * G * K * 4, cudaMemcpyDeviceToHost, e->stream));
+        CU(cudaEventRecord(e->ev_staged, e->stream));
+        CU(cudaStreamWaitEvent(e->copy_stream, e->ev_staged, 0));
+    }
     CU(cudaEventRecord(e->ev_out, e->copy_stream));
     e->out_pending = true;
     return GMRM_OK;
@@ -1082,6 +1131,22 @@ int gmrm_fetch_outputs(gmrm_engine* e, int32_t t, double* betas, int32_t* comp) 
     CU(cudaEventSynchronize(e->ev_out));
     if (betas) memcpy(betas, e->h_out_betas + (size_t)t * e->Mloc, (size_t)e->Mloc * 8);
     if (comp) memcpy(comp, e->h_out_comp + (size_t)t * e->Mloc, (size_t)e->Mloc * 4);
+    return GMRM_OK;
+}
+int gmrm_fetch_state(gmrm_engine* e, gmrm_state* o) {
+    if (!e || !o) return fail(GMRM_EINVAL, "null argument");
+    if (!e->out_pending) return fail(GMRM_EINVAL, "no staged outputs: call gmrm_stage_outputs first");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventSynchronize(e->ev_out));
+    const size_t T = e->cfg.T, G = e->cfg.G, K = e->cfg.K;
+    const double* hd = e->h_out_state;
+    const int32_t* hi = reinterpret_cast<const int32_t*>(hd + state_doubles(e));
+    if (o->sigmag) memcpy(o->sigmag, hd, T * G * 8);
+    if (o->sigmae) memcpy(o->sigmae, hd + T * G, T * 8);
+    if (o->pi) memcpy(o->pi, hd + T * G + T, T * G * K * 8);
+    if (o->mu) memcpy(o->mu, hd + T * G + T + T * G * K, T * 8);
+    if (o->m0) memcpy(o->m0, hi, T * G * 4);
+    if (o->cass) memcpy(o->cass, hi + T * G, T * G * K * 4);
     return GMRM_OK;
 }
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out) {

@@ -163,8 +163,10 @@ int gmrm_get_epsilon(gmrm_engine* e, int32_t trait, double* eps);          /* N 
  * A gmrm_run_iteration between the two overlaps the copy with the next iteration. */
 int gmrm_stage_outputs(gmrm_engine* e);
 int gmrm_fetch_outputs(gmrm_engine* e, int32_t trait, double* betas, int32_t* comp);
+/* the global parameters snapshotted by the same gmrm_stage_outputs call (gmrm_get_state without a blocking copy) */
+int gmrm_fetch_state(gmrm_engine* e, gmrm_state* out);
 int gmrm_get_timing(gmrm_engine* e, gmrm_timing* out);
-int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step) */
+int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + step kernel (2 events/step); 2: every phase (6 events/step), the residual update of every step as its own launch */
 
 /* --- association pass: Bayes::predict, src/bayes.cpp:14-284, for one trait on this GPU's shard.
  * The reference's MPI ranks are the engine's virtual ranks (cfg.vranks): block r of markers is tested against
@@ -177,6 +179,11 @@ int gmrm_set_timing_detail(gmrm_engine* e, int32_t level); /* 0: totals; 1: + st
  *   beta, tdist, se, pval   marker_count doubles each or NULL (bayes.cpp:199-208); NaN for skipped markers */
 int gmrm_predict(gmrm_engine* e, int32_t trait, const double* y, const double* beta_mean, const uint8_t* keep, double* g,
                  double* beta, double* tdist, double* se, double* pval);
+
+/* The genetic values alone (bayes.cpp:87-136; scale(X) %*% beta of example/data_sim.R:33): g[i] = na_i * sum over ALL markers
+ * of every shard of ((a - mave) msig) beta.  beta: marker_count doubles (this shard's markers); g: N doubles, identical on
+ * every GPU (one all-reduce).  Needs gmrm_compute_marker_stats. */
+int gmrm_genetic_values(gmrm_engine* e, int32_t trait, const double* beta, double* g);
 
 /* --- test hook without a device: launch plan of the step kernel and the rows each CTA owns in each pass */
 int gmrm_debug_step_plan(int32_t N, int32_t nsm, int32_t V, int32_t T, int32_t* traits_per_launch, int32_t* rows_per_pass,

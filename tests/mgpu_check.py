@@ -16,12 +16,10 @@ from gmrm_b200 import api, synth          # noqa: E402
 from oracle import oracle_py as O         # noqa: E402
 
 
-def main():
-    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
-    sync_rate = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, M, T, G, Vl, iters, seed = 3001, 1203, 2, 2, 8, 4, 77
+def chain_check(rank, world, local, sync_rate, Vl=8):
+    """The check itself, inside an initialised process group (also called by bench.py before it times N > 1 GPUs).
+    Raises on any mismatch; returns a small record on success."""
+    N, M, T, G, iters, seed = 3001, 1203, 2, 2, 4, 77
     R = Vl * world
     obj = [None]
     if rank == 0:
@@ -60,11 +58,25 @@ def main():
         hist.append(st)
     eps = np.stack([e.epsilon(t) for t in range(T)])
     e.close()
-    if len(sys.argv) > 2 and sys.argv[2] == "predict":
-        predict_check(rank, world, local, inp, N, M, T)
     gathered = [None] * world
     dist.all_gather_object(gathered, (lo, n, hist, eps))
-    ok = True
+    err = None
+    try:
+        _compare(inp, gathered, N, R, T, world, sync_rate, iters, seed, rank)
+    except AssertionError as ex:
+        err = f"rank {rank}: {ex}"[:600]
+    errs = [None] * world
+    dist.all_gather_object(errs, err)
+    errs = [x for x in errs if x]
+    if errs:
+        raise AssertionError("; ".join(errs))
+    return {"sync_rate": sync_rate, "R": R, "world": world, "iterations": iters, "inputs": inp}
+
+
+def _compare(inp, gathered, N, R, T, world, sync_rate, iters, seed, rank):
+    if sync_rate == 1:          # list exchange: ONE chain, every GPU holds the same residuals bit for bit
+        for (_, _, _, eps_g) in gathered[1:]:
+            assert np.array_equal(eps_g, gathered[0][3]), "residual replicas are not bit-identical"
     if rank == 0:
         # sync_rate 1: list exchange, every GPU holds the residuals of ONE chain with R virtual ranks (the reference under
         # mpirun -n R); sync_rate > 1: one residual replica per GPU, deltas all-reduced every sync_rate steps
@@ -81,10 +93,21 @@ def main():
         # replicas agree with each other and with the oracle's replica 0 up to rounding
         for (_, _, _, eps_g) in gathered:
             np.testing.assert_allclose(eps_g, res["eps_final"][:, :N], rtol=0, atol=1e-10)
-        print(f"MGPU_OK world={world} sync_rate={sync_rate} R={R}", flush=True)
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    sync_rate = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    info = chain_check(rank, world, local, sync_rate)
+    if len(sys.argv) > 2 and sys.argv[2] == "predict":
+        predict_check(rank, world, local, info["inputs"], 3001, 1203, 2)
+    if rank == 0:
+        print(f"MGPU_OK world={world} sync_rate={sync_rate} R={info['R']}", flush=True)
     dist.barrier()
     dist.destroy_process_group()
-    return 0 if ok else 1
+    return 0
 
 
 def predict_check(rank, world, local, inp, N, M, T):
