@@ -24,6 +24,7 @@ struct Options {
     int gpus = 1;            // --gpus: GPUs of this node sharing the chain (one host thread each)
     int sync_rate = 1;       // --sync-rate
     unsigned burn_in = 0;    // --burn-in: iterations left out of the posterior-mean summary (.mbet)
+    std::string replay_file;     // --replay-file: logged variates of a reference run (layout: host.hpp, Replay), fed instead of the Philox streams
     bool check_inputs = false;   // --check-inputs: parse everything, print a summary, no GPU work
     std::string dump_inputs;     // --dump-inputs <dir>: with --check-inputs, write the parsed phenotypes / groups / mixtures as raw binaries (tests)
     bool selftest_predict = false;   // --selftest-predict: with --check-inputs and --predict, read the .bim pair and the .bet histories and print what was found (tests)
@@ -74,6 +75,23 @@ public:
 private:
     int csv_ = -1, bet_ = -1, cpn_ = -1;
 };
+
+// ---- replay of a reference run's random variates (north-star replay mode).
+// File: 8 bytes "GMRMRPL1", int32 R, Mm, T, G, K, iterations; T*G doubles sigmag_init; then per iteration
+// perm int32[R*Mm], u f64[Mm*R*T], z f64[Mm*R*T], mu_draw f64[T], sigg_unit f64[T*G], pi_unit f64[T*G*K], sige_unit f64[T]
+// -- the arrays of gmrm_replay (include/gmrm_b200.h), NaN where the reference drew nothing.
+struct Replay {
+    int R = 0, Mm = 0, T = 0, G = 0, K = 0, iterations = 0;
+    std::vector<double> sigmag_init;
+    struct It { std::vector<int32_t> perm; std::vector<double> u, z, mu_draw, sigg_unit, pi_unit, sige_unit; };
+    std::vector<It> its;
+};
+Replay read_replay_file(const std::string& path);
+
+// Default number of virtual ranks (markers in flight per step) for Mt markers on `gpus` GPUs: 2,048 per GPU, but never more than
+// Mt / 64 in total -- every virtual rank keeps at least 64 markers of its own, so a step samples at most 1/64 of the markers
+// against the same residuals (with Mt ranks the sampler would degenerate into a fully synchronous sweep).
+int default_vranks(int Mt, int gpus);
 
 // ---- association pass, the reference's --predict mode (predict.cpp)
 struct BimCross {

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 #include <limits>
@@ -153,6 +154,43 @@ void BedReader::read(int marker_begin, int count, uint8_t* dst) {
         }
         done += (size_t)r;
     }
+}
+
+Replay read_replay_file(const std::string& path) {
+    Replay r;
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) { printf("FATAL  : can not open the replay file %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    auto need = [&](void* dst, size_t bytes) {
+        if (fread(dst, 1, bytes, f) != bytes) { printf("FATAL  : replay file %s is truncated\n", path.c_str()); exit(EXIT_FAILURE); }
+    };
+    char magic[8];
+    need(magic, 8);
+    if (memcmp(magic, "GMRMRPL1", 8) != 0) { printf("FATAL  : %s is not a replay file\n", path.c_str()); exit(EXIT_FAILURE); }
+    int32_t h[6];
+    need(h, sizeof h);
+    r.R = h[0]; r.Mm = h[1]; r.T = h[2]; r.G = h[3]; r.K = h[4]; r.iterations = h[5];
+    if (r.R < 1 || r.Mm < 1 || r.T < 1 || r.G < 1 || r.K < 2 || r.iterations < 0) { printf("FATAL  : bad header in replay file %s\n", path.c_str()); exit(EXIT_FAILURE); }
+    const size_t T = r.T, G = r.G, K = r.K, nuz = (size_t)r.Mm * r.R * T;
+    r.sigmag_init.resize(T * G);
+    need(r.sigmag_init.data(), T * G * 8);
+    r.its.resize(r.iterations);
+    for (auto& it : r.its) {
+        it.perm.resize((size_t)r.R * r.Mm); it.u.resize(nuz); it.z.resize(nuz);
+        it.mu_draw.resize(T); it.sigg_unit.resize(T * G); it.pi_unit.resize(T * G * K); it.sige_unit.resize(T);
+        need(it.perm.data(), it.perm.size() * 4); need(it.u.data(), nuz * 8); need(it.z.data(), nuz * 8);
+        need(it.mu_draw.data(), T * 8); need(it.sigg_unit.data(), T * G * 8); need(it.pi_unit.data(), T * G * K * 8); need(it.sige_unit.data(), T * 8);
+    }
+    fclose(f);
+    return r;
+}
+
+int default_vranks(int Mt, int gpus) {
+    long long vr = 2048LL * gpus;
+    const long long cap = Mt / 64;
+    if (vr > cap) vr = cap;
+    vr -= vr % gpus;
+    if (vr < gpus) vr = gpus;
+    return (int)vr;
 }
 
 }  // namespace host

@@ -51,6 +51,7 @@ struct Shared {
     uint8_t nccl_id[128];
     void* peer_ptrs[8][5] = {};
     int vranks = 0;
+    host::Replay replay;                       // --replay-file (empty: production Philox streams)
     // --predict
     host::BimCross bim;
     std::vector<uint8_t> keep;                 // [Mt] 1 = the marker's id is in the reference .bim
@@ -172,7 +173,8 @@ void worker(int rank, Shared* sh, Barrier* bar) {
     const double t_stats = now();
     ck(gmrm_compute_marker_stats(e), "gmrm_compute_marker_stats");
     if (rank == 0) printf("INFO   : Time to compute the markers' statistics: %.2f seconds.\n", now() - t_stats);
-    ck(gmrm_init_chain(e, nullptr), "gmrm_init_chain");
+    const bool replaying = !sh->replay.its.empty();
+    ck(gmrm_init_chain(e, replaying ? sh->replay.sigmag_init.data() : nullptr), "gmrm_init_chain");
 
     // ---- output files (bayes.cpp:322-324): rank 0 deletes and creates, the others open
     std::vector<host::OutFiles*> outs(T, nullptr);
@@ -184,7 +186,9 @@ void worker(int rank, Shared* sh, Barrier* bar) {
 
     std::vector<double> sigmag((size_t)T * G), sigmae(T), pi((size_t)T * G * K), mu(T), betas(M);
     std::vector<int32_t> m0((size_t)T * G), cass((size_t)T * G * K), comp(M);
-    std::vector<std::vector<double>> bmean(T, std::vector<double>(o.burn_in < o.iterations ? M : 0, 0.0));
+    // posterior means of beta (<stem>.mbet) only when --burn-in asks for them: no read-back is staged for them otherwise
+    const bool want_mean = o.burn_in > 0 && o.burn_in < o.iterations;
+    std::vector<std::vector<double>> bmean(T, std::vector<double>(want_mean ? M : 0, 0.0));
     gmrm_state st{sigmag.data(), sigmae.data(), pi.data(), mu.data(), m0.data(), cass.data()};
     // betas / components leave the GPU through the staged path (gmrm_stage_outputs): their copy to pinned host memory
     // runs under the next iteration, and the files of iteration i are written after iteration i+1 has been enqueued
@@ -208,7 +212,14 @@ void worker(int rank, Shared* sh, Barrier* bar) {
     };
     for (unsigned it = 1; it <= o.iterations; it++) {
         const double ts = now();
-        ck(gmrm_run_iteration(e, (int32_t)it, nullptr), "gmrm_run_iteration");
+        gmrm_replay rp{};
+        if (replaying) {
+            if (it > sh->replay.its.size()) { printf("FATAL  : the replay file holds %d iterations, iteration %u asked for\n", (int)sh->replay.its.size(), it); exit(EXIT_FAILURE); }
+            const host::Replay::It& ri = sh->replay.its[it - 1];
+            rp.perm = ri.perm.data(); rp.u = ri.u.data(); rp.z = ri.z.data(); rp.mu_draw = ri.mu_draw.data();
+            rp.sigg_unit = ri.sigg_unit.data(); rp.pi_unit = ri.pi_unit.data(); rp.sige_unit = ri.sige_unit.data();
+        }
+        ck(gmrm_run_iteration(e, (int32_t)it, replaying ? &rp : nullptr), "gmrm_run_iteration");
         write_pending();                                     // iteration it-1: its copy has had a whole iteration
         ck(gmrm_get_state(e, &st), "gmrm_get_state");
         gmrm_timing tm{};
@@ -220,7 +231,7 @@ void worker(int rank, Shared* sh, Barrier* bar) {
                 printf("RESULT : i:%d r:%d p:%d  sum sigmaG = %20.15f  sigmaE = %20.15f\n", it, rank, t, sg, sigmae[t]);   // bayes.cpp:641
             }
         if (rank == 0) printf("RESULT : It %d  total proc time = %7.3f sec, with sync time = %7.3f\n", it, now() - ts, tm.exchange_ms * 1e-3);   // bayes.cpp:655
-        const bool save = it % o.thin == 0, mean = it > o.burn_in && !bmean[0].empty();
+        const bool save = it % o.thin == 0, mean = want_mean && it > o.burn_in;
         if (save || mean) {
             ck(gmrm_stage_outputs(e), "gmrm_stage_outputs");
             po.it = it; po.save = save; po.mean = mean;
@@ -229,7 +240,7 @@ void worker(int rank, Shared* sh, Barrier* bar) {
     }
     write_pending();
     // ---- superset: posterior means of beta over the iterations after --burn-in, <stem>.mbet (Mt doubles)
-    if (o.burn_in > 0 && o.burn_in < o.iterations)
+    if (want_mean)
         for (int t = 0; t < T; t++) {
             const double inv = 1.0 / (double)(o.iterations - o.burn_in);
             for (auto& v : bmean[t]) v *= inv;
@@ -313,14 +324,34 @@ int main(int argc, char** argv) {
     printf("INFO   : Reading groups from %s.\n", o.group_index_file.c_str());
     sh.group_index = host::read_group_index_file(o.group_index_file, o.ngroups, sh.dims.Mt);
     // virtual ranks: the run is the reference under `mpirun -n vranks`
-    int vr = o.vranks > 0 ? o.vranks : 2048 * o.gpus;   // default: 2,048 markers in flight per GPU (the benchmarked setting)
+    // default: 2,048 markers in flight per GPU (the benchmarked setting), capped at Mt / 64 in total (host.hpp)
+    int vr = o.vranks > 0 ? o.vranks : host::default_vranks(sh.dims.Mt, o.gpus);
+    if (!o.replay_file.empty()) {                        // a replayed run IS the reference under `mpirun -n R`: R comes from the log
+        sh.replay = host::read_replay_file(o.replay_file);
+        const host::Replay& r = sh.replay;
+        if (r.T != (int)sh.phens.size() || r.G != o.ngroups || r.K != o.nmixtures || r.Mm != (sh.dims.Mt + r.R - 1) / r.R) {
+            printf("FATAL  : replay file %s was logged for T=%d G=%d K=%d R=%d Mm=%d, the run has T=%d G=%d K=%d Mt=%d\n", o.replay_file.c_str(),
+                   r.T, r.G, r.K, r.R, r.Mm, (int)sh.phens.size(), o.ngroups, o.nmixtures, sh.dims.Mt);
+            return EXIT_FAILURE;
+        }
+        if (o.vranks > 0 && o.vranks != r.R) printf("WARNING: --vranks %d ignored, the replay file was logged with %d ranks\n", o.vranks, r.R);
+        vr = r.R;
+        printf("INFO   : replaying the logged variates of %d iterations of a %d-rank reference run\n", r.iterations, r.R);
+    }
     if (vr > sh.dims.Mt) vr = sh.dims.Mt;
-    vr -= vr % o.gpus;
+    if (vr % o.gpus) {
+        if (!o.replay_file.empty()) { printf("FATAL  : %d logged ranks cannot be shared evenly by %d GPUs\n", vr, o.gpus); return EXIT_FAILURE; }
+        vr -= vr % o.gpus;
+    }
     if (vr < o.gpus) {
         printf("FATAL  : %d markers cannot be shared by %d GPUs\n", sh.dims.Mt, o.gpus);
         return EXIT_FAILURE;
     }
     sh.vranks = vr;
+    if ((long long)vr * 64 > sh.dims.Mt)                  // few markers per virtual rank: most of the sweep samples against stale residuals
+        printf("WARNING: %d virtual ranks for %d markers (%d markers each): every step samples %.1f %% of the markers against the same residuals, "
+               "like the reference under `mpirun -n %d`; pass a smaller --vranks (default: at most Mt/64) unless that is intended.\n",
+               vr, sh.dims.Mt, sh.dims.Mt / vr, 100.0 * vr / sh.dims.Mt, vr);
     printf("INFO   : %d GPU(s), %d virtual ranks (markers in flight per step), sync rate %d\n", o.gpus, vr, o.sync_rate);
     if (o.check_inputs) {
         for (const auto& p : sh.phens) printf("INFO   : %s: %d observed, %d NA\n", p.path.c_str(), p.nonas, p.nas);

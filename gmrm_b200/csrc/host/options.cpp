@@ -137,6 +137,7 @@ Options parse_options(int argc, char** argv, int rank) {
         else if (!strcmp(a, "--dump-inputs")) { o.dump_inputs = value_of(argc, argv, i); ss << "--dump-inputs " << o.dump_inputs << "\n"; }
         else if (!strcmp(a, "--selftest-predict")) { o.selftest_predict = true; ss << "--selftest-predict 1\n"; }
         else if (!strcmp(a, "--selftest-outputs")) { o.selftest_outputs = true; ss << "--selftest-outputs 1\n"; }
+        else if (!strcmp(a, "--replay-file")) { o.replay_file = value_of(argc, argv, i); ss << "--replay-file " << o.replay_file << "\n"; }
         else if (!strcmp(a, "--gpus")) { o.gpus = (int)positive("--gpus", value_of(argc, argv, i), 1, "strictly positive"); ss << "--gpus " << o.gpus << "\n"; }
         else fatal(std::string("FATAL: option \"") + a + "\" unknown");
     }
@@ -154,6 +155,11 @@ Options parse_options(int argc, char** argv, int rank) {
         if (o.ref_bim_file.empty()) fatal("FATAL  : you need to pass a reference bim file with --ref-bim-file when activating --predict");
     }
     if (o.mimic_hydra && o.phen_files.size() > 1) fatal("FATAL  : with --mimic-hydra, only a single phenotype can be processed.");
+    if (rank == 0 && o.mimic_hydra)   // the flag only picks the reference's Mersenne-Twister seeds and shuffle stream (bayes.cpp:798-799, phenotype.cpp:316)
+        std::cout << "WARNING: --mimic-hydra selects the reference's PRNG seeding; this build draws from counter-based Philox streams "
+                     "(or replays logged variates, --replay-file): the flag has no effect here." << std::endl;
+    if (rank == 0 && !o.S.empty())    // options.hpp:35: get_s() has no caller in the reference either
+        std::cout << "WARNING: --S is parsed and checked but not used (the reference never reads it either)." << std::endl;
     if (o.predict) return o;                                                      // options.hpp:11-12: the mixture file is not read with --predict
     read_group_mixture_file(o, rank);
     return o;

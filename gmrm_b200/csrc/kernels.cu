@@ -378,11 +378,49 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
     // published markers handled per round: their bytes of this CTA's rows are staged in shared memory (the table
     // area, free at this point) with all loads in flight at once -- the columns were streamed a step ago and are
     // mostly out of L2, so fetching them entry by entry would expose one HBM round trip per 8 entries
+    // exclusive prefix of the segment counts of all lists (GPU-major = global virtual-rank order), at the end of the staging area
+    const int S = publist_segments(p.pV), nseg = p.pG * S;
+    bytes_cap -= ((nseg + 1) * 4 + 15) & ~15;
+    int* segpre = reinterpret_cast<int*>(bytes + bytes_cap);
     const int cap = max(1, min(kPubCap, bytes_cap / max(nq, 1)));
     for (int t = 0; t < T; t++) {
         const int tt = p.t0 + t;
         double* eps_t = p.eps + (int64_t)tt * p.npad;
         const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride;
+        {
+            constexpr int kPer = 8;                     // segments per thread: nseg <= 8 * NT
+            const int per = (nseg + NT - 1) / NT;
+            int loc[kPer], sum = 0;
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                const int i = tid * per + j;
+                loc[j] = 0;
+                if (j < per && i < nseg) {              // .cg: peers rewrite these buffers between launches
+                    const int g = i / S, sg = i - g * S;
+                    loc[j] = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles));
+                }
+                sum += loc[j];
+            }
+            int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += y;
+            }
+            __syncthreads();                            // wcnt / segpre of the previous trait are consumed
+            if ((tid & 31) == 31) wcnt[tid >> 5] = incl;
+            __syncthreads();
+            int base = incl - sum;
+            for (int w = 0; w < (tid >> 5); w++) base += wcnt[w];
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+                const int i = tid * per + j;
+                if (j < per && i < nseg) { segpre[i] = base; base += loc[j]; }
+            }
+            if (tid == NT - 1) segpre[nseg] = base;     // the last thread's running total is the grand total
+            __syncthreads();
+        }
+        const int total = segpre[nseg];
         for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
             double e[2][4], e0[2][4];
             uint32_t nmask[2];                          // 0x18 in byte k: individual k is not observed -> zero entry
@@ -400,17 +438,6 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             }
             GMRM_ATICK()   // [40] lut + eps/mask loads
             bool touched = false;
-            // the lists arrive compacted and ordered (sampler kernel); list g of GPU g, GPUs in rank order = global
-            // virtual-rank order
-            int pre[kMaxGpus + 1];
-            pre[0] = 0;
-#pragma unroll
-            for (int g = 0; g < kMaxGpus; g++) {
-                int c = 0;
-                if (g < p.pG) c = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV)));
-                pre[g + 1] = pre[g] + c;
-            }
-            const int total = pre[kMaxGpus];
             GMRM_ATICK()   // [41] list headers
             {
                 for (int r0 = 0; r0 < total; r0 += cap) {
@@ -418,10 +445,13 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                     __syncthreads();
                     if (tid < n) {
                         const int x = r0 + tid;
-                        int g = 0;
-#pragma unroll
-                        for (int q = 1; q < kMaxGpus; q++) g += (x >= pre[q]) ? 1 : 0;
-                        const double* ip = p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + 2 + 3 * (size_t)(x - pre[g]);
+                        int lo = 0, hi = nseg;               // the segment holding item x: segpre[lo] <= x < segpre[lo + 1]
+                        while (hi - lo > 1) {
+                            const int mid = (lo + hi) >> 1;
+                            if (segpre[mid] <= x) lo = mid; else hi = mid;
+                        }
+                        const int g = lo / S, sg = lo - g * S;
+                        const double* ip = p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles + 2 + 3 * (size_t)(x - segpre[lo]);
                         PubItem it;                          // .cg loads: peers rewrite this buffer between launches
                         it.lam = __ldcg(ip); it.mave = __ldcg(ip + 1);
                         const int2 cv = __ldcg(reinterpret_cast<const int2*>(ip + 2));
@@ -920,8 +950,9 @@ __global__ void group_consts_kernel(int T, int G, int K, int N, const double* __
 // Latency-ordered: the kernel is one dependent chain per warp, so independent loads are issued together --
 // round 1: column index, the marker's partial sums and the residual sums (none depends on the column);
 // round 2 (needs the column): missing-list bounds, group, mave, msig, beta;  round 3: sigmaG, sampler constants.
-__device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lane) {
-    const int col = p.cols[v];
+// The published item of lane t < T (trait t) is returned in (lam, mave); lam == 0: nothing to publish.
+__device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lane, int col, double& out_lam, double& out_mave) {
+    out_lam = 0.0; out_mave = 0.0;
     // ---- round 1: sum a*eps partials and sum eps, trait by trait (fixed order), while `col` is in flight
     double my_coded = 0.0, my_sall = 0.0;
     for (int t = 0; t < p.T; t++) {
@@ -941,10 +972,7 @@ __device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lan
         const double coded = warp_sum_fixed(s), sall = warp_sum_fixed(sa);
         if (lane == t) { my_coded = coded; my_sall = sall; }
     }
-    if (col < 0) {
-        if (lane < p.T) { p.pub[(int64_t)v * p.T + lane].lam = 0.0; p.pub[(int64_t)v * p.T + lane].mave = 0.0; }
-        return;
-    }
+    if (col < 0) return;
     // ---- round 2
     const uint32_t m0 = p.miss_off[col], m1 = p.miss_off[col + 1];
     const int grp = p.group[col];
@@ -993,90 +1021,52 @@ __device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lan
         p.comp[mi] = d.comp;                                               // bayes.cpp:462
         atomicAdd(&p.cass[(t * p.G + grp) * p.K + d.comp], 1);              // 460
     }
-    PubEntry e;
-    e.lam = fabs(d.dbeta) > 0.0 ? d.dbeta * msig : 0.0;                    // 483-487, phenotype.cpp:328
-    e.mave = mave;
-    p.pub[(int64_t)v * p.T + t] = e;
-    if (e.lam != 0.0) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), 1ull);
+    out_lam = fabs(d.dbeta) > 0.0 ? d.dbeta * msig : 0.0;                  // 483-487, phenotype.cpp:328
+    out_mave = mave;
 }
 
-
-// One warp per virtual rank; the last CTA to finish compacts the step's published entries, in virtual-rank order,
-// into this GPU's list (what the next step kernel -- on every GPU, after the all-gather -- applies).
-__global__ void __launch_bounds__(128) sample_kernel(const SampleParams p) {
-    const int v = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (v < p.V) sample_one(p, v, lane);
-    __shared__ bool last;
-    if (lane < p.T) __threadfence();                         // the lanes that wrote a pub entry make it visible device-wide ...
+// One warp per virtual rank, kSegCap virtual ranks per CTA.  The CTA compacts its published items (virtual-rank order) into
+// ITS segment of this GPU's list -- and, across GPUs, into the same segment of every peer's copy over NVLink -- so no
+// CTA waits for another; the last CTA to finish only raises the flags the peers' next step kernels wait on.
+constexpr int kSampleMaxT = 32;
+__global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams p) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int v = blockIdx.x * kSegCap + warp;
+    __shared__ double s_lam[kSampleMaxT][kSegCap], s_mave[kSampleMaxT][kSegCap];
+    __shared__ int s_col[kSegCap], s_npub;
+    if (tid == 0) s_npub = 0;
+    const int col = v < p.V ? p.cols[v] : -1;
+    double lam = 0.0, mave = 0.0;
+    if (v < p.V) sample_one(p, v, lane, col, lam, mave);
+    if (lane < p.T) { s_lam[lane][warp] = lam; s_mave[lane][warp] = mave; }
+    if (lane == 0) s_col[warp] = col;
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;   // ... before the CTA takes its ticket
+    const bool push = p.world > 1 && p.peer_list[0] != nullptr;
+    const size_t S = publist_segments(p.V);
+    for (int t = warp; t < p.T; t += kSegCap) {              // warp w compacts the traits w, w + 16, ...
+        const bool live = lane < kSegCap && s_lam[t][lane < kSegCap ? lane : 0] != 0.0;
+        const uint32_t bal = __ballot_sync(0xffffffffu, live);
+        const int pos = __popc(bal & ((1u << lane) - 1u)), n = __popc(bal);
+        const size_t off = ((size_t)t * S + blockIdx.x) * kSegDoubles;
+        PubItem it;
+        if (live) { it.lam = s_lam[t][lane]; it.mave = s_mave[t][lane]; it.col = s_col[lane]; it.v = blockIdx.x * kSegCap + lane; }
+        for (int g = 0; g < (push ? p.world : 1); g++) {     // own list first (g == rank when pushing: peer_list[rank] is the own block)
+            double* seg = (push ? p.peer_list[g] : p.plist) + off;
+            if (lane == 0) *reinterpret_cast<int32_t*>(seg) = n;
+            if (live) reinterpret_cast<PubItem*>(seg + 2)[pos] = it;
+        }
+        if (lane == 0 && n) atomicAdd(&s_npub, n);
+    }
+    if (push) __threadfence_system();                        // this CTA's segments are visible to the peers ...
+    __syncthreads();
+    if (tid == 0 && s_npub) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), (unsigned long long)s_npub);
+    if (!push) return;
+    __shared__ bool last;
+    if (tid == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;    // ... before it takes its ticket
     __syncthreads();
     if (!last) return;
-    __threadfence();
-    // ordered compaction, 16 x 128 entries at a time: coalesced loads all in flight, one ballot per warp and chunk,
-    // one 64-element scan
-    const int tid = threadIdx.x, warp = tid >> 5;
-    __shared__ int cnts[64], offs[64];
-    __shared__ int s_total;
-    for (int t = 0; t < p.T; t++) {
-        double* list = p.plist + (size_t)t * publist_doubles(p.V);
-        PubItem* items = reinterpret_cast<PubItem*>(list + 2);
-        int base = 0;
-        for (int x0 = 0; x0 < p.V; x0 += 16 * 128) {
-            double lam[16];
-            uint32_t bal[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int x = x0 + i * 128 + tid;
-                lam[i] = x < p.V ? __ldcg(&p.pub[(int64_t)x * p.T + t].lam) : 0.0;
-            }
-            __syncthreads();                                 // cnts / offs of the previous round are consumed
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                bal[i] = __ballot_sync(0xffffffffu, lam[i] != 0.0);
-                if (lane == 0) cnts[i * 4 + warp] = __popc(bal[i]);
-            }
-            __syncthreads();
-            if (warp == 0) {                                 // exclusive scan of the 64 (chunk, warp) counts
-                const int c0 = cnts[2 * lane], c1 = cnts[2 * lane + 1];
-                int incl = c0 + c1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += y;
-                }
-                offs[2 * lane] = incl - c0 - c1;
-                offs[2 * lane + 1] = incl - c1;
-                if (lane == 31) s_total = incl;
-            }
-            __syncthreads();
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                if (lam[i] != 0.0) {
-                    const int x = x0 + i * 128 + tid;
-                    PubItem it;
-                    it.lam = lam[i]; it.mave = __ldcg(&p.pub[(int64_t)x * p.T + t].mave); it.col = p.cols[x]; it.v = x;
-                    items[base + offs[i * 4 + warp] + __popc(bal[i] & ((1u << lane) - 1u))] = it;
-                }
-            }
-            base += s_total;
-        }
-        if (tid == 0) *reinterpret_cast<int32_t*>(list) = base;
-        if (p.world > 1 && p.peer_list[0] != nullptr) {          // push header + items into every peer's copy (NVLink stores)
-            __syncthreads();
-            const int nd = 2 + 3 * base;
-            for (int g = 0; g < p.world; g++) {
-                if (g == p.rank) continue;
-                double* dst = p.peer_list[g] + (size_t)t * publist_doubles(p.V);
-                for (int i = tid; i < nd; i += 128) dst[i] = list[i];
-            }
-        }
-    }
-    if (p.world > 1 && p.peer_list[0] != nullptr) {
-        __threadfence_system();                              // the lists are visible to the peers before the flags
-        __syncthreads();
-        if (tid < p.world) *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
-    }
+    __threadfence_system();                                  // every CTA's segments before the flags
+    if (tid < p.world) *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
     if (tid == 0) *p.ticket = 0u;
 }
 // [sample-end]
@@ -1319,7 +1309,7 @@ int launch_step(const Layout& L, int T, const StepParams& p, cudaStream_t s) {
 
 void launch_sample(const SampleParams& p, cudaStream_t s) {
     if (p.V <= 0) return;
-    sample_kernel<<<(p.V + 3) / 4, 128, 0, s>>>(p);
+    sample_kernel<<<publist_segments(p.V), kSegCap * 32, 0, s>>>(p);
 }
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
     if (p.V <= 0) return;

@@ -28,10 +28,16 @@ struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3
     double lam;     // dbeta * msig   (0 == nothing to apply)
     double mave;
 };
-// The step's published updates of one GPU and trait, compacted in virtual-rank order by the sampler kernel:
-// a 16-byte header (int32 count) followed by up to V items.  This is what the GPUs all-gather.
+// The step's published updates of one GPU and trait: a SEGMENTED list in virtual-rank order.  Every CTA of the sampler
+// kernel samples kSegCap consecutive virtual ranks and writes their published items, compacted and in order, into its own
+// segment -- a 16-byte header (int32 count) followed by up to kSegCap items -- with no dependency on any other CTA (and,
+// across GPUs, straight into the peers' copies of the list).  The consumer (step kernel) turns the segment counts into a
+// prefix and walks the items of all segments of all GPUs in global virtual-rank order.
 struct PubItem { double lam, mave; int32_t col, v; };     // col: column local to the publishing GPU
-__host__ __device__ constexpr size_t publist_doubles(int V) { return 2 + 3 * (size_t)V; }
+constexpr int kSegCap = 16;                                // virtual ranks per sampler CTA == items a segment can hold
+constexpr int kSegDoubles = 2 + 3 * kSegCap;               // header + items, in doubles
+__host__ __device__ constexpr int publist_segments(int V) { return (V + kSegCap - 1) / kSegCap; }
+__host__ __device__ constexpr size_t publist_doubles(int V) { return (size_t)publist_segments(V) * kSegDoubles; }
 
 // One marker-step on one GPU: (a) apply the updates published by the previous step to this CTA's rows of
 // the residuals, (b) build the look-up tables of those rows, (c) stream the step's V columns through them.
@@ -51,8 +57,8 @@ struct StepParams {
     // pending updates (previous step), applied in virtual-rank order: pG lists of pV entries, list g published by
     // GPU g about ITS markers -- columns, genotypes and missing lists of list g are read from GPU g's buffers
     // (peer memory over NVLink when g is not this GPU)
-    int32_t pG, pV;                      // lists, capacity of a list (0 lists: nothing pending)
-    const double* plist;                 // [pG][Ttot][publist_doubles(pV)]
+    int32_t pG, pV;                      // lists, virtual ranks behind a list (0 lists: nothing pending)
+    const double* plist;                 // [pG][Ttot][publist_doubles(pV)]: publist_segments(pV) segments each
     const unsigned long long* xflags;    // [pG] or nullptr: wait until every list's flag has reached wait_seq
     unsigned long long wait_seq;
     const uint8_t* pbed[kMaxGpus];
@@ -90,11 +96,11 @@ struct SampleParams {
     const double* gc;        // [T][G][4K] per-iteration sampler constants (group_consts_kernel)
     const int32_t* nonas;    // [T]
     int32_t* cass;           // [T][G*K]
-    PubEntry* pub;           // [V][T] scratch: every marker's entry (lam == 0: nothing published)
-    double* plist;           // [T][publist_doubles(V)] this GPU's compacted list (written by the last CTA to finish)
-    unsigned int* ticket;    // CTA counter for that, zero between launches
-    // peer-memory exchange (world > 1): the last CTA also stores the list into every peer's buffer over NVLink and
-    // then raises this GPU's flag there to `seq`
+    PubEntry* pub;           // unused (kept for the layout of older callers)
+    double* plist;           // [T][publist_doubles(V)] this GPU's list: CTA c writes segment c of every trait
+    unsigned int* ticket;    // CTA counter of the peer-memory exchange, zero between launches
+    // peer-memory exchange (world > 1): every CTA also stores its segments into every peer's buffer over NVLink; the
+    // last CTA to finish then raises this GPU's flag there to `seq`
     int32_t world, rank;
     double* peer_list[kMaxGpus];                 // where GPU g wants THIS GPU's list (nullptr: no exchange)
     unsigned long long* peer_flag[kMaxGpus];     // this GPU's flag in GPU g's flag array

@@ -118,7 +118,7 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
             sp.betas = betas.data(); sp.comp = comp.data(); sp.group = group; sp.sigmag = sigmag.data(); sp.gc = gc.data(); sp.nonas = nonas;
             sp.cass = cass.data(); sp.pub = pub.data(); sp.plist = plist.data(); sp.ticket = &ticket; sp.world = 1; sp.rank = 0;
             sp.seq = (unsigned long long)s + 1; sp.err = &err; sp.npublished = &npub;
-            emu_launch(EmuDim3((R + 3) / 4), EmuDim3(128), [&] { sample_kernel(sp); });
+            emu_launch(EmuDim3(publist_segments(R)), EmuDim3(kSegCap * 32), [&] { sample_kernel(sp); });
         }
         cols = nullptr;
         step(0, true, plan + 3);                             // flush

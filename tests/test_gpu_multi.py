@@ -21,7 +21,6 @@ def test_two_gpu_chain_matches_oracle(sync_rate):
     assert p.returncode == 0 and "MGPU_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
 
 
-@pytest.mark.xfail(reason="multi-GPU predict: not yet run on hardware", strict=False)
 def test_two_gpu_predict_matches_oracle():
     import torch
     if torch.cuda.device_count() < 2:

@@ -4,16 +4,13 @@ oracle's restatement, which tests/test_oracle_predict.py pins to the reference's
 fp64 work: the GPU sums the markers' contributions in chunk order, the reference in OpenMP-atomic order; the bar is
 1e-11 of the largest genetic value for g and 1e-9 relative for the statistics (written below).
 
-Status: the pass has run on a B200 once, through the CLI on one dataset (1 and 3 marker blocks, profiles/r1_predict_hw_check.txt,
-the case of tests/test_cli_host.py::test_cli_predict_matches_oracle: equal to the oracle to 6e-13).  The wider shapes below (several
-CTA counts, blocks of one marker, N = 20,000) were written after the round's GPU minutes were spent and have not run yet; until they
-have, a failure here is reported as xfail instead of stopping the suite (XPASS in the log = confirmed)."""
+Status: green on B200s since round 1's driver run (GPUTEST_r01: XPASS) and round 2's first call (gpurun_out/r2c1)."""
 import numpy as np
 import pytest
 
 from gmrm_b200 import synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="predict: these shapes have not run on hardware yet (the CLI case has)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")

