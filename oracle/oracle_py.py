@@ -263,3 +263,20 @@ def load_inputs(bed_path, dim_path, phen_paths, gri_path, grm_path):
     cva = np.array([[float(x) for x in l.split()] for l in open(grm_path) if l.strip()])
     return {"N": N, "Mt": Mt, "bed": bed, "eps0": np.stack(eps), "mask4": np.stack(masks),
             "nonas": np.array(nonas, dtype=np.int32), "group_index": gi, "cva": cva}
+
+
+def write_replay_file(path, res, iterations=None):
+    """The variates of an oracle.gibbs(..., rng_mode=0, replay_dir=...) run in the layout gmrm_b200_cli --replay-file reads
+    (gmrm_b200/csrc/host/host.hpp, struct Replay): header, sigmag_init, then the arrays of gmrm_replay per iteration."""
+    I, R, Mm = res["perm"].shape
+    T = res["u"].shape[3]
+    G, K = res["pi_unit"].shape[2], res["pi_unit"].shape[3]
+    n = I if iterations is None else iterations
+    with open(path, "wb") as f:
+        f.write(b"GMRMRPL1")
+        f.write(np.array([R, Mm, T, G, K, n], dtype=np.int32).tobytes())
+        f.write(np.ascontiguousarray(res["sigmag_init"], dtype=np.float64).tobytes())
+        for i in range(n):
+            f.write(np.ascontiguousarray(res["perm"][i], dtype=np.int32).tobytes())
+            for name in ("u", "z", "mu_draw", "sigg_unit", "pi_unit", "sige_unit"):
+                f.write(np.ascontiguousarray(res[name][i], dtype=np.float64).tobytes())
