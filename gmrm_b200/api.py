@@ -242,6 +242,15 @@ class Engine:
         _check(lib().gmrm_init_chain(self._h, _dp(a)))
 
     def run_iteration(self, it: int, replay: dict | None = None):
+        self.run_iteration_async(it, replay)
+        self.wait_iteration()
+
+    def wait_iteration(self):
+        self._keep = None
+        _check(lib().gmrm_wait_iteration(self._h))
+
+    def run_iteration_async(self, it: int, replay: dict | None = None):
+        """Enqueue iteration `it` and return at once; wait_iteration() reports its errors and timings."""
         rp = None
         keep = []
         if replay is not None:
@@ -253,7 +262,8 @@ class Engine:
                 a = np.ascontiguousarray(a, dtype=np.int32 if name == "perm" else np.float64)
                 keep.append(a)
                 setattr(rp, name, _ip(a) if name == "perm" else _dp(a))
-        _check(lib().gmrm_run_iteration(self._h, it, C.byref(rp) if rp is not None else None))
+        self._keep = keep                         # the replay arrays stay alive until the wait
+        _check(lib().gmrm_run_iteration_async(self._h, it, C.byref(rp) if rp is not None else None))
 
     def state(self) -> dict:
         T, G, K = self.T, self.G, self.K

@@ -155,6 +155,7 @@ struct gmrm_engine {
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
     bool force_flush = false;        // GMRM_FORCE_FLUSH=1: update-only launch after every step (timing aid)
     int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
+    int pdl = 1;                     // GMRM_PDL=0: plain launches in the marker loop (no programmatic dependent launch)
     int step_warps = 16;             // consumer warps of the step kernel (GMRM_STEP_WARPS=20: measured alternative)
     DevBuf<PubEntry> pub;
     DevBuf<int64_t> npub;
@@ -167,6 +168,10 @@ struct gmrm_engine {
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> dot_ev;
+    // gmrm_run_iteration_async / gmrm_wait_iteration: what the enqueued iteration leaves for the wait
+    bool it_pending = false;
+    int it_Mm = 0; int64_t it_launches = 0; bool it_multi = false;
+    int32_t* h_err = nullptr; int64_t* h_pub = nullptr;     // pinned
     int timing_detail = 0;           // 0: iteration totals only; 1: + the step kernel (2 events per step); 2: every phase (6 events per step)
     gmrm_timing last{};
 
@@ -183,6 +188,8 @@ struct gmrm_engine {
         if (h_out_betas) cudaFreeHost(h_out_betas);
         if (h_out_comp) cudaFreeHost(h_out_comp);
         if (h_out_state) cudaFreeHost(h_out_state);
+        if (h_err) cudaFreeHost(h_err);
+        if (h_pub) cudaFreeHost(h_pub);
         for (auto& e : dot_ev) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
@@ -228,6 +235,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     e->Mm = (c->Mt + c->vranks - 1) / c->vranks;
     if (const char* v = getenv("GMRM_STEP_WARPS")) e->step_warps = atoi(v) == 20 ? 20 : 16;
     if (const char* v = getenv("GMRM_STEP_PF")) e->step_pf = atoi(v);
+    if (const char* v = getenv("GMRM_PDL")) e->pdl = atoi(v) != 0;
     if (const char* v = getenv("GMRM_FORCE_FLUSH")) e->force_flush = atoi(v) != 0;
     if (getenv("GMRM_STEP_PROF")) {
         if (e->prof.alloc(64) != 0 || e->prof.zero(nullptr) != 0) { delete e; return GMRM_ECUDA; }
@@ -556,7 +564,7 @@ static size_t list_block(const gmrm_engine* e) { return (size_t)e->cfg.T * publi
 static double* lists_of(gmrm_engine* e, unsigned long long seq) { return e->plist.p + (e->list_exchange ? (size_t)(seq & 1) * e->cfg.world_size * list_block(e) : 0); }
 static double* own_list(gmrm_engine* e, unsigned long long seq) { return lists_of(e, seq) + (e->list_exchange ? (size_t)e->cfg.world_rank * list_block(e) : 0); }
 
-static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch) {
+static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch, bool in_loop = false) {
     const int T = e->cfg.T;
     int tc = e->step_tc, rpp = e->step_rpp;
     if (V > e->Vl || V == 0) {                                  // test hook with its own marker count / update-only launch
@@ -582,6 +590,7 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         p.err = e->err.p;
         p.prof = e->prof.p;
         p.pf = e->step_pf;
+        p.pdl = e->pdl && in_loop;
         const int rc = launch_step(e->L, std::min(tc, T - t0), p, e->stream);
         if (rc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         if (nlaunch) (*nlaunch)++;
@@ -868,8 +877,14 @@ static int upload_opt(DevBuf<double>& buf, const double* src, size_t n, cudaStre
 }
 
 int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
+    const int rc = gmrm_run_iteration_async(e, it, rp);
+    return rc ? rc : gmrm_wait_iteration(e);
+}
+
+int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
     if (!e->chain_ready) return fail(GMRM_EINVAL, "call gmrm_init_chain first");
+    if (e->it_pending) return fail(GMRM_EINVAL, "an iteration is already enqueued: call gmrm_wait_iteration first");
     if (e->cfg.world_size > 1 && !e->comm) return fail(GMRM_EINVAL, "world_size > 1 needs gmrm_comm_init");
     CU(cudaSetDevice(e->cfg.device));
     const gmrm_config& c = e->cfg;
@@ -948,11 +963,11 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
         const int32_t* cols = e->steptab.p + (size_t)st * Vl;
         int nl = 0;
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st], s));
-        if ((rc = launch_step_all(e, cols, Vl, pend, e->partial.p, &nl))) return rc;
+        if ((rc = launch_step_all(e, cols, Vl, pend, e->partial.p, &nl, st > 0))) return rc;   // step 0 follows memsets, not a kernel of the loop
         if (e->timing_detail) CU(cudaEventRecord(e->dot_ev[6 * st + 1], s));
         e->xseq++;                                           // this step's lists: sequence number xseq, buffer parity xseq & 1
         SampleParams sp = sample_params(e, cols, Vl, e->partial.p);
-        sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z;
+        sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z; sp.pdl = e->pdl;
         if (e->list_exchange && e->list_p2p) {               // the sampler pushes the list into every peer's buffer and raises our flag there
             sp.world = c.world_size; sp.rank = c.world_rank; sp.seq = e->xseq;
             for (int g = 0; g < c.world_size; g++) {
@@ -1007,11 +1022,29 @@ int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* rp) {
     CU(cudaEventRecord(e->ev[3], s));
     CU(cudaGetLastError());
 
-    int32_t herr = 0;
-    int64_t hpub = 0;
-    CU(cudaMemcpyAsync(&herr, e->err.p, 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(&hpub, e->npub.p, 8, cudaMemcpyDeviceToHost, s));
+    if (!e->h_err) {
+        CU(cudaHostAlloc((void**)&e->h_err, 4, cudaHostAllocDefault));
+        CU(cudaHostAlloc((void**)&e->h_pub, 8, cudaHostAllocDefault));
+    }
+    CU(cudaMemcpyAsync(e->h_err, e->err.p, 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(e->h_pub, e->npub.p, 8, cudaMemcpyDeviceToHost, s));
+    e->it_pending = true; e->it_Mm = Mm; e->it_launches = launches; e->it_multi = multi;
+    return GMRM_OK;
+}
+
+int gmrm_wait_iteration(gmrm_engine* e) {
+    if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (!e->it_pending) return fail(GMRM_EINVAL, "no iteration enqueued");
+    CU(cudaSetDevice(e->cfg.device));
+    const gmrm_config& c = e->cfg;
+    cudaStream_t s = e->stream;
+    const int Mm = e->it_Mm;
+    const int64_t launches = e->it_launches;
+    const bool multi = e->it_multi;
+    e->it_pending = false;
     CU(cudaStreamSynchronize(s));
+    const int32_t herr = *e->h_err;
+    const int64_t hpub = *e->h_pub;
     float ms_loop = 0, ms_all = 0;
     CU(cudaEventElapsedTime(&ms_loop, e->ev[1], e->ev[2]));
     CU(cudaEventElapsedTime(&ms_all, e->ev[0], e->ev[3]));

@@ -219,8 +219,9 @@ void worker(int rank, Shared* sh, Barrier* bar) {
             rp.perm = ri.perm.data(); rp.u = ri.u.data(); rp.z = ri.z.data(); rp.mu_draw = ri.mu_draw.data();
             rp.sigg_unit = ri.sigg_unit.data(); rp.pi_unit = ri.pi_unit.data(); rp.sige_unit = ri.sige_unit.data();
         }
-        ck(gmrm_run_iteration(e, (int32_t)it, replaying ? &rp : nullptr), "gmrm_run_iteration");
-        write_pending();                                     // iteration it-1: its copy has had a whole iteration
+        ck(gmrm_run_iteration_async(e, (int32_t)it, replaying ? &rp : nullptr), "gmrm_run_iteration_async");
+        write_pending();                                     // iteration it-1: its files are written while iteration it runs
+        ck(gmrm_wait_iteration(e), "gmrm_wait_iteration");
         ck(gmrm_get_state(e, &st), "gmrm_get_state");
         gmrm_timing tm{};
         gmrm_get_timing(e, &tm);

@@ -31,6 +31,11 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* red) {
         for (int i = 0; i < nw; i++) t += red[i];
     return t;
 }
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still draining; pdl_wait() returns once the predecessor has completed and its writes
+// are visible, pdl_trigger() lets the successor's CTAs be scheduled from here on.  Both are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // [helpers-end]
 
 // =====================================================================================
@@ -355,8 +360,9 @@ __device__ __forceinline__ int global_row(const PassRows& pr, int local_row) {
 // bytes of the table area; an update-only launch (V == 0) sizes it for staging kPubCap published columns
 __host__ __device__ inline int step_area_bytes(int V, int T, int rows_per_pass, int npass) {
     if (V > 0) return rows_per_pass * T * kSlotBytes;
-    const long long want = (long long)kPubCap * npass * rows_per_pass * kRowBytes;
-    return (int)(want < 163840 ? want : 163840);
+    // column bytes of kPubCap entries + their pair tables + the prefix of the lists' segment counts
+    const long long want = (long long)kPubCap * npass * rows_per_pass * kRowBytes + kPubCap * 64 + 8192;
+    return (int)(want < 180224 ? want : 180224);
 }
 
 // ---- (a) pending updates: Phenotype::update_epsilon (phenotype.cpp:326-329,375-390) for every published marker
@@ -378,6 +384,12 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
     // published markers handled per round: their bytes of this CTA's rows are staged in shared memory (the table
     // area, free at this point) with all loads in flight at once -- the columns were streamed a step ago and are
     // mostly out of L2, so fetching them entry by entry would expose one HBM round trip per 8 entries
+    // pair tables at the head of the staging area (256-aligned: it starts at kTabBase): for entries 2i, 2i+1 of a round the 16
+    // sums v_a[d_a] + v_b[d_b] (digit 3 = contributes nothing), 128 B -- one entry per 8-byte bank pair, so ANY mix of
+    // indices within a half-warp is conflict-free -- and one look-up then serves TWO published markers of an individual
+    double* ptab = reinterpret_cast<double*>(bytes);
+    const uint32_t ptab_u32 = smem_u32(ptab);
+    bytes += kPubCap * 64; bytes_cap -= kPubCap * 64;
     // exclusive prefix of the segment counts of all lists (GPU-major = global virtual-rank order), at the end of the staging area
     const int S = publist_segments(p.pV), nseg = p.pG * S;
     bytes_cap -= ((nseg + 1) * 4 + 15) & ~15;
@@ -423,7 +435,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
         const int total = segpre[nseg];
         for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
             double e[2][4], e0[2][4];
-            uint32_t nmask[2];                          // 0x18 in byte k: individual k is not observed -> zero entry
+            uint32_t nmask[2];                          // 0x78 in byte k: individual k is not observed -> zero entry (15 of a pair table, 3 of a single one)
             int gq[2];                                  // global quad (byte of the column) of local quad q
             bool have[2];
 #pragma unroll
@@ -432,7 +444,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                 have[qq] = q < nq;
                 gq[qq] = have[qq] ? global_row(pr, q >> 6) * kRowBytes + (q & 63) : 0;
                 const uint32_t na = have[qq] ? mask_t[gq[qq]] : 0u;
-                nmask[qq] = ((na & 1u) ? 0u : 0x18u) | ((na & 2u) ? 0u : 0x1800u) | ((na & 4u) ? 0u : 0x180000u) | ((na & 8u) ? 0u : 0x18000000u);
+                nmask[qq] = ((na & 1u) ? 0u : 0x78u) | ((na & 2u) ? 0u : 0x7800u) | ((na & 4u) ? 0u : 0x780000u) | ((na & 8u) ? 0u : 0x78000000u);
 #pragma unroll
                 for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * (int64_t)gq[qq] + k] : 0.0; e0[qq][k] = e[qq][k]; }
             }
@@ -492,6 +504,10 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                             }
                         }
                         if (tid < n) info[tid].nmiss_g = ((mo1 - mo0) << 4) | (info[tid].nmiss_g & 15u);
+                        for (int i = tid; i < ((n + 7) & ~7) * 8; i += NT) {     // 16 sums per pair of entries (padded entries are all-zero)
+                            const int pp = i >> 4, d1 = i & 3, d2 = (i >> 2) & 3;
+                            ptab[i] = stage[2 * pp].v[d1] + stage[2 * pp + 1].v[d2];
+                        }
                         __syncthreads();
                     }
                     GMRM_ATICK()   // [42] stage fill + column bytes
@@ -506,25 +522,26 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                             }
                         const uint32_t gbase = stage_u32 + (uint32_t)g0 * 32u;   // 256-aligned: stage is, g0 is a multiple of 8
                         // fast path (no entry of the group has missing genotypes): one branch-free block for the 8
-                        // entries -- padded entries are all-zero, unobserved / absent quads hit the zero slot -- so that
-                        // the look-ups of later entries are in flight while earlier ones are added
+                        // entries, two per look-up through the pair tables -- padded entries are all-zero, unobserved /
+                        // absent quads hit the zero entry -- so that later look-ups are in flight while earlier ones are added
                         uint32_t anymiss = 0;
 #pragma unroll
                         for (int j = 0; j < 8; j++) anymiss |= info[g0 + j].nmiss_g >> 4;
                         if (!anymiss) {
-#define GMRM_APPLY_FAST(J)                                                                                          \
+#define GMRM_APPLY_PAIR(J)                                                                                          \
     _Pragma("unroll") for (int qq = 0; qq < 2; qq++) {                                                            \
-        uint32_t off;                                                                                             \
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(lut_u32 + by[J][qq] * 4u));                      \
-        off |= nmask[qq];                                                                                         \
-        e[qq][0] += lds_f64_imm<J * 32>(byte_into<0>(off, gbase));   /* * na (phenotype.cpp:388) */               \
-        e[qq][1] += lds_f64_imm<J * 32>(byte_into<1>(off, gbase));                                                \
-        e[qq][2] += lds_f64_imm<J * 32>(byte_into<2>(off, gbase));                                                \
-        e[qq][3] += lds_f64_imm<J * 32>(byte_into<3>(off, gbase));                                                \
+        uint32_t o1, o2;                                                                                          \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o1) : "r"(lut_u32 + by[2 * J][qq] * 4u));                   \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o2) : "r"(lut_u32 + by[2 * J + 1][qq] * 4u));               \
+        const uint32_t off = (o2 * 4u + o1) | nmask[qq];   /* byte k: 8 * (d_a + 4 d_b) of individual k, <= 80 */  \
+        e[qq][0] += lds_f64_imm<J * 128>(byte_into<0>(off, pbase));   /* * na (phenotype.cpp:388) */              \
+        e[qq][1] += lds_f64_imm<J * 128>(byte_into<1>(off, pbase));                                               \
+        e[qq][2] += lds_f64_imm<J * 128>(byte_into<2>(off, pbase));                                               \
+        e[qq][3] += lds_f64_imm<J * 128>(byte_into<3>(off, pbase));                                               \
     }
-                            GMRM_APPLY_FAST(0) GMRM_APPLY_FAST(1) GMRM_APPLY_FAST(2) GMRM_APPLY_FAST(3)
-                            GMRM_APPLY_FAST(4) GMRM_APPLY_FAST(5) GMRM_APPLY_FAST(6) GMRM_APPLY_FAST(7)
-#undef GMRM_APPLY_FAST
+                            const uint32_t pbase = ptab_u32 + (uint32_t)g0 * 64u;    // 512-aligned: 4 pair tables per group of 8
+                            GMRM_APPLY_PAIR(0) GMRM_APPLY_PAIR(1) GMRM_APPLY_PAIR(2) GMRM_APPLY_PAIR(3)
+#undef GMRM_APPLY_PAIR
                             continue;
                         }
 #define GMRM_APPLY(J)                                                                                              \
@@ -549,7 +566,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             if (have[qq]) {                                                                                       \
                 uint32_t off;                                                                                     \
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(lut_u32 + by[J][qq] * 4u));              \
-                off |= nmask[qq];                                                                                 \
+                off |= nmask[qq] & 0x18181818u;                                                                   \
                 if (hasmiss) {   /* missing here: a = b = 0, no change */                                         \
                     const int q = q0 + qq * NT + tid;                                                             \
                     const uint32_t sk = (bitmap[q >> 3] >> ((q & 7) * 4)) & 0xfu;                                 \
@@ -825,6 +842,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 #define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
     for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
+    // everything above touched only this CTA's shared memory, the launch parameters and read-only inputs (the step table,
+    // the genotypes): it may run while the sampler kernel of the previous step is still finishing
+    pdl_wait();
+    pdl_trigger();                                        // the sampler's CTAs may be scheduled as soon as SMs free up; they wait likewise
     if (p.xflags != nullptr) {                            // peer-memory exchange: every GPU's list of the previous step has landed
         if (tid < p.pG) {
             const volatile unsigned long long* f = p.xflags + tid;
@@ -1035,7 +1056,9 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
     __shared__ double s_lam[kSampleMaxT][kSegCap], s_mave[kSampleMaxT][kSegCap];
     __shared__ int s_col[kSegCap], s_npub;
     if (tid == 0) s_npub = 0;
+    pdl_trigger();                                           // the next step kernel may start its prologue (shared-memory set-up, L2 prefetch)
     const int col = v < p.V ? p.cols[v] : -1;
+    pdl_wait();                                              // the step kernel's partial sums are complete and visible
     double lam = 0.0, mave = 0.0;
     if (v < p.V) sample_one(p, v, lane, col, lam, mave);
     if (lane < p.T) { s_lam[lane][warp] = lam; s_mave[lane][warp] = mave; }
@@ -1292,8 +1315,13 @@ static int step_launch_t(const Layout& L, const StepParams& p, cudaStream_t s) {
     // every launch asks for the full 227 KB, update-only ones included: a different dynamic size would make the
     // driver re-partition L1/shared memory between consecutive launches of the marker loop
     (void)smem;
-    step_kernel<T><<<L.nsm, kStepThreads, kMaxDynSmem, s>>>(p);
-    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)L.nsm); cfg.blockDim = dim3(kStepThreads); cfg.dynamicSmemBytes = kMaxDynSmem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = p.pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, step_kernel<T>, p) == cudaSuccess ? 0 : -2;
 }
 // T = traits of this launch (1..4); p.rows_per_pass * T <= kMaxSlots
 int launch_step(const Layout& L, int T, const StepParams& p, cudaStream_t s) {
@@ -1309,7 +1337,13 @@ int launch_step(const Layout& L, int T, const StepParams& p, cudaStream_t s) {
 
 void launch_sample(const SampleParams& p, cudaStream_t s) {
     if (p.V <= 0) return;
-    sample_kernel<<<publist_segments(p.V), kSegCap * 32, 0, s>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)publist_segments(p.V)); cfg.blockDim = dim3(kSegCap * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = p.pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, sample_kernel, p);
 }
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s) {
     if (p.V <= 0) return;

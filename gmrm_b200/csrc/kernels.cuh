@@ -68,6 +68,7 @@ struct StepParams {
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     int32_t* err;
     int32_t pf;              // 1: L2 prefetch ahead of the streaming loads
+    int32_t pdl;             // host side: launch with the programmatic-serialization attribute (the prologue overlaps the previous kernel)
     unsigned long long* prof;   // debug (GMRM_STEP_PROF): 8 cycle counters, see stream_rows / producers
 };
 
@@ -109,6 +110,7 @@ struct SampleParams {
     const double* rep_z;
     int32_t* err;            // device error flag
     int64_t* npublished;
+    int32_t pdl;             // host side: launch with the programmatic-serialization attribute
 };
 
 // launchers (kernels.cu)

@@ -153,6 +153,11 @@ int gmrm_init_chain(gmrm_engine* e, const double* sigmag_init);
 /* One Gibbs iteration `it` (1-based), bayes.cpp:340-656, asynchronous on the engine's stream
  * except for the final small read-back of the global parameters. */
 int gmrm_run_iteration(gmrm_engine* e, int32_t it, const gmrm_replay* replay);
+/* The same in two halves: _async enqueues the iteration and returns at once (the host is free to write the previous
+ * iteration's files, bayes.cpp:659-669, while the GPU works); gmrm_wait_iteration waits for it and reports its errors and
+ * timings.  gmrm_run_iteration == _async + wait.  At most one iteration may be enqueued. */
+int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* replay);
+int gmrm_wait_iteration(gmrm_engine* e);
 
 int gmrm_get_state(gmrm_engine* e, gmrm_state* out);
 int gmrm_get_betas(gmrm_engine* e, int32_t trait, double* betas);          /* shard-local, marker_count */

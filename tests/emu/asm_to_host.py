@@ -81,6 +81,8 @@ def _translate(instr, outs, ins):
         return f"{outs[0]} = emu_prmt({ins[0]}, {ins[1]}, {ins[2]});"
     if i.startswith("prefetch.global.L2") or i.startswith("cp.async.bulk.prefetch.L2"):
         return "(void)0;"
+    if i.startswith("griddepcontrol."):                      # programmatic dependent launch: launches are serial on the host
+        return "(void)0;"
     raise ValueError(f"asm_to_host: no host form for PTX instruction: {instr!r}")
 
 
