@@ -32,6 +32,7 @@ WORKLOADS = {
     "c2": dict(N=20_000, M=50_000, T=1, G=1),               # configs[1]
     "c4": dict(N=200_000, M=500_000, T=4, G=1),             # configs[3]
     "c5": dict(N=458_000, M=1_000_000, T=1, G=20),          # configs[4]
+    "ukbn": dict(N=458_000, M=50_000, T=1, G=1),            # UKB individuals, C2's marker count (long-chain probes)
     "tiny": dict(N=20_000, M=8_192, T=1, G=1),              # quick functional run
 }
 MIXTURES = (0.0, 1e-4, 1e-3, 1e-2)                           # example/test.grm

@@ -114,6 +114,7 @@ struct gmrm_engine {
     cudaStream_t stream = nullptr;
     int Vl = 0, r0 = 0, marker_begin = 0, Mloc = 0, Mm = 0;
     bool bed_final = false, stats_done = false, chain_ready = false, groups_set = false;
+    bool buffers_exported = false;   // peers hold pointers / IPC handles of bed, miss_off, miss_idx: they must not be reallocated any more
     std::vector<char> phen_set;
     std::vector<double> h_cva;
     std::vector<int32_t> h_nonas;
@@ -210,6 +211,8 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     if (c->vranks < c->world_size || c->vranks % c->world_size != 0 || c->vranks > c->Mt)
         return fail(GMRM_EINVAL, "vranks=%d must be a multiple of world_size=%d and <= Mt=%d", c->vranks, c->world_size, c->Mt);
     if (c->sync_rate < 1) return fail(GMRM_EINVAL, "sync_rate must be >= 1");
+    if (c->G > 112)   // beta_sq_kernel keeps G x 256 partial sums in shared memory (227 KB per CTA)
+        return fail(GMRM_EINVAL, "G=%d marker groups: at most 112 are supported (shared memory of the per-group sum of squares)", c->G);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -378,6 +381,7 @@ static int ingest_staged(gmrm_engine* e, const uint8_t* staged, int lb, int n) {
 
 int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, int32_t marker_count) {
     if (!e || !bed) return fail(GMRM_EINVAL, "null argument");
+    if (e->buffers_exported) return fail(GMRM_EINVAL, "genotypes cannot be re-uploaded after the buffers were exported to the other GPUs");
     if (marker_count < 0 || marker_begin < e->marker_begin || marker_begin + marker_count > e->marker_begin + e->Mloc)
         return fail(GMRM_EINVAL, "markers [%d, %d) outside this shard [%d, %d)", marker_begin, marker_begin + marker_count,
                     e->marker_begin, e->marker_begin + e->Mloc);
@@ -418,6 +422,7 @@ int gmrm_upload_bed(gmrm_engine* e, const uint8_t* bed, int32_t marker_begin, in
 
 int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_hi, double missing_rate) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (e->buffers_exported) return fail(GMRM_EINVAL, "genotypes cannot be regenerated after the buffers were exported to the other GPUs");
     CU(cudaSetDevice(e->cfg.device));
     const int chunk = chunk_markers(e);
     int rc = ensure_stage(e, (size_t)std::min(chunk, e->Mloc) * e->L.mbytes);
@@ -433,6 +438,7 @@ int gmrm_generate_bed(gmrm_engine* e, uint32_t seed, double maf_lo, double maf_h
 
 int gmrm_finalize_bed(gmrm_engine* e) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
+    if (e->buffers_exported) return fail(GMRM_EINVAL, "the missing-genotype lists cannot be rebuilt after the buffers were exported to the other GPUs");
     CU(cudaSetDevice(e->cfg.device));
     std::vector<uint32_t> cnt(e->Mloc, 0), off((size_t)e->Mloc + 1, 0);
     for (auto& c : e->miss_chunks)
@@ -1261,6 +1267,7 @@ int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[320]) {
     CU(cudaIpcGetMemHandle(&h, e->miss_idx.p)); memcpy(handles + 128, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->plist.p)); memcpy(handles + 192, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->xflags.p)); memcpy(handles + 256, &h, 64);
+    e->buffers_exported = true;
     return GMRM_OK;
 }
 static int set_peer(gmrm_engine* e, int rank, void* const p[5]) {
@@ -1291,6 +1298,7 @@ int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[5]) {
     if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p; ptrs[3] = e->plist.p; ptrs[4] = e->xflags.p;
+    e->buffers_exported = true;
     return GMRM_OK;
 }
 int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[5]) {

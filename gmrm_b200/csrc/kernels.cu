@@ -661,8 +661,10 @@ __device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0
 }
 
 // ---- (c) stream the V columns through the tables of NR rows
-template <int NR, int T>
-__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part) {
+// GP: the per-marker partial sums live in global memory (p.partial, this CTA's slots) instead of shared memory -- for steps
+// of more markers than shared memory can hold partials for next to the tables; `first`: the step's first pass (nothing to add to)
+template <int NR, int T, bool GP>
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, bool first) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
     const uint32_t low = (uint32_t)l16 * 8u;
@@ -746,6 +748,16 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         for (int i = 0; i < kPairs; i++)
 #pragma unroll
             for (int t = 0; t < T; t++) acc[i][t] = 0.0;
+        // global partials: the owner lane's running sums of this batch's marker, loaded here and used after the look-ups
+        [[maybe_unused]] double pold[T];
+        [[maybe_unused]] double* pslot = nullptr;
+        if constexpr (GP) {
+            const int v = b * kBatch + 2 * own + h;
+            const bool owner = (l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V;
+            if (owner) pslot = p.partial + ((int64_t)v * p.Ttot + p.t0) * gridDim.x + blockIdx.x;
+#pragma unroll
+            for (int t = 0; t < T; t++) pold[t] = (owner && !first) ? pslot[(int64_t)t * gridDim.x] : 0.0;
+        }
 
 #define GMRM_LOOKUP(RR, K)                                                    \
     _Pragma("unroll") for (int i = 0; i < kPairs; i++)                             \
@@ -797,7 +809,11 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
             const int v = b * kBatch + 2 * own + h;
-            if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V) part[v * T + t] += b1;
+            if constexpr (GP) {
+                if (pslot) pslot[(int64_t)t * gridDim.x] = pold[t] + b1;
+            } else {
+                if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V) part[v * T + t] += b1;
+            }
         }
     }
 }
@@ -818,7 +834,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     const int area = step_area_bytes(p.V, T, p.rows_per_pass, npass);                        // tables / update staging
     PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)area);                      // 256-aligned
     double* part = reinterpret_cast<double*>(stage + kPubCap);
-    PubInfo* info = reinterpret_cast<PubInfo*>(part + (size_t)p.V * T);
+    const bool gp = step_part_global(p.V, T);             // partial sums in global memory: no shared-memory array
+    PubInfo* info = reinterpret_cast<PubInfo*>(part + (gp ? 0 : (size_t)p.V * T));
     uint32_t* lut = reinterpret_cast<uint32_t*>(info + kPubCap);
     PassRows& pr = *reinterpret_cast<PassRows*>(lut + 82);
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(&pr + 1);
@@ -841,7 +858,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     int nk = 8;
 #define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
-    for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
+    if (!gp)
+        for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
     // everything above touched only this CTA's shared memory, the launch parameters and read-only inputs (the step table,
     // the genotypes): it may run while the sampler kernel of the previous step is still finishing
     pdl_wait();
@@ -867,18 +885,34 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     double es[T];
 #pragma unroll
     for (int t = 0; t < T; t++) es[t] = 0.0;
+    bool gp_started = false;
     for (int pass = 0; pass < npass; pass++) {
         const int r_lo = pr.start[pass], nrp = pr.count[pass];
         build_tables<T, NT>(p, r_lo, nrp, es);
         __syncthreads();
         GMRM_TICK()                                       // [9 + 3*pass] sync + build
-        switch (nrp) {
-        case 1: stream_rows<1, T>(p, r_lo, part); break;
-        case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part); break;
-        case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part); break;
-        case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part); break;
-        case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part); break;
-        default: break;
+        // (with global partials a CTA without rows in the step's first pass still has to zero its slots: nrp == 0 below)
+        if (gp) {
+            const bool first = !gp_started;
+            switch (nrp) {
+            case 0: break;
+            case 1: stream_rows<1, T, true>(p, r_lo, part, first); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, true>(p, r_lo, part, first); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, true>(p, r_lo, part, first); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, true>(p, r_lo, part, first); break;
+            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T, true>(p, r_lo, part, first); break;
+            default: break;
+            }
+            if (nrp > 0) gp_started = true;
+        } else {
+            switch (nrp) {
+            case 1: stream_rows<1, T, false>(p, r_lo, part, false); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, false>(p, r_lo, part, false); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, false>(p, r_lo, part, false); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, false>(p, r_lo, part, false); break;
+            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T, false>(p, r_lo, part, false); break;
+            default: break;
+            }
         }
         GMRM_TICK()                                       // [10 + 3*pass] this warp's streaming
         if (p.pf && pass + 1 < npass && pr.count[pass + 1] > 0) prefetch_pass_head(p, pr.start[pass + 1], pr.count[pass + 1]);
@@ -887,9 +921,16 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     __syncthreads();
     GMRM_TICK()
-    for (int i = tid; i < p.V * T; i += NT) {
-        const int v = i / T, t = i - v * T;
-        p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
+    if (!gp) {
+        for (int i = tid; i < p.V * T; i += NT) {
+            const int v = i / T, t = i - v * T;
+            p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
+        }
+    } else if (!gp_started) {                             // a CTA that owns no rows at all (more CTAs than rows): its slots are zero
+        for (int i = tid; i < p.V * T; i += NT) {
+            const int v = i / T, t = i - v * T;
+            p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = 0.0;
+        }
     }
 #pragma unroll
     for (int t = 0; t < T; t++) {
@@ -1271,7 +1312,7 @@ int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
     if (step_npass(L, rows_per_pass) > kMaxPasses) return -1;
     const int nrmax = step_npass(L, rows_per_pass) * rows_per_pass;   // bound on the rows one CTA owns
     const int64_t bytes = (int64_t)kTabBase + (int64_t)step_area_bytes(V, T, rows_per_pass, step_npass(L, rows_per_pass)) + (int64_t)kPubCap * 32 +
-                          (int64_t)V * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 4 * 32 * 4;
+                          (step_part_global(V, T) ? 0 : (int64_t)V * T * 8) + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 4 * 32 * 4;
     return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 

@@ -20,64 +20,7 @@ struct MarkerDraw {
     int need_z;     // 1 when a normal was consumed
 };
 
-// u: uniform in [0,1); zdraw(): returns the standard normal, called only when a non-null component
-// is chosen.  cva/cvai/pi: this marker's group rows, K entries each.
-template <class ZDraw>
-GMRM_HD MarkerDraw sample_marker(double dot_raw,   // msig*(sum a*eps - mave*sum b*eps), bayes.cpp:418
-                                 double beta, double sigmae, double sigmag, const double* cva,
-                                 const double* cvai, const double* pi, int K, int N, int nonas,
-                                 double u, ZDraw zdraw) {
-    MarkerDraw r;
-    r.need_z = 0;
-    if (sigmag == 0.0) {                                     // bayes.cpp:396-400: no draw, no cass, beta = 0
-        r.beta_new = 0.0; r.dbeta = 0.0; r.comp = -1;
-        return r;
-    }
-    const double sige_g = sigmae / sigmag;                   // 403
-    const double sigg_e = 1.0 / sige_g;                      // 404
-    const double inv2sige = 1.0 / (2.0 * sigmae);            // 405
-    double denom[kMaxK], muk[kMaxK], logl[kMaxK];
-    for (int i = 1; i <= K - 1; i++) denom[i - 1] = (double)(N - 1) + sige_g * cvai[i];   // 413-416
-    const double num = dot_raw + beta * (double)(nonas - 1);                              // 421
-    for (int i = 1; i <= K - 1; i++) muk[i] = num / denom[i - 1];                         // 425-426
-    for (int i = 0; i < K; i++) {                                                         // 428-433
-        logl[i] = log(pi[i]);
-        if (i > 0) logl[i] += -0.5 * log(sigg_e * (double)(nonas - 1) * cva[i] + 1.0) + muk[i] * num * inv2sige;
-    }
-    bool zero_acum = false;                                                               // 437-445
-    double tmp1 = 0.0;
-    for (int i = 0; i < K; i++) {
-        if (fabs(logl[i] - logl[0]) > 700.0) zero_acum = true;
-        tmp1 += exp(logl[i] - logl[0]);
-    }
-    double acum = zero_acum ? 0.0 : 1.0 / tmp1;
-    r.beta_new = 0.0; r.comp = K - 1;
-    for (int i = 0; i < K; i++) {                                                         // 450-477
-        if (u <= acum || i == K - 1) {
-            if (i == 0) {
-                r.beta_new = 0.0;
-            } else {
-                r.beta_new = muk[i] + sqrt(sigmae / denom[i - 1]) * zdraw();                    // 456, distributions.hpp:48-53
-                r.need_z = 1;
-            }
-            r.comp = i;
-            break;
-        } else {
-            bool zero_inc = false;
-            for (int j = i + 1; j < K; j++)
-                if (fabs(logl[j] - logl[i + 1]) > 700.0) zero_inc = true;
-            if (!zero_inc) {
-                double esum = 0.0;
-                for (int k = 0; k < K; k++) esum += exp(logl[k] - logl[i + 1]);
-                acum += 1.0 / esum;
-            }
-        }
-    }
-    r.dbeta = beta - r.beta_new;                                                          // 479
-    return r;
-}
-
-// Same sampler with the marker-independent pieces precomputed per (trait, group) by group_consts_kernel
+// The per-marker mixture draw with the marker-independent pieces precomputed per (trait, group) by group_consts_kernel
 // (kernels.cu): gc = [denom | log pi | -0.5 log(..) | sd], slot 0 of the first block = 1/(2 sigmaE).
 // The arithmetic per marker is the reference's, term for term (bayes.cpp:421-477).
 template <class ZDraw>

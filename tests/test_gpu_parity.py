@@ -269,7 +269,9 @@ def test_replay_c2_full_size_first_10_iterations(api, oracle, tmp_path):
 
 
 # ------------------------------------------------------------------ production (Philox) streams
-@pytest.mark.parametrize("N,M,T,G,R,nsm", [(2000, 500, 1, 1, 1, 1), (4100, 900, 2, 2, 32, 2), (20000, 3000, 1, 1, 128, 0)])
+# the last two cases sample more than 2,048 (marker, trait) pairs per step: partial sums in global memory, several list segments
+@pytest.mark.parametrize("N,M,T,G,R,nsm", [(2000, 500, 1, 1, 1, 1), (4100, 900, 2, 2, 32, 2), (20000, 3000, 1, 1, 128, 0),
+                                           (9000, 9000, 1, 1, 3000, 0), (3001, 2600, 2, 2, 1290, 3)])
 def test_production_streams_match_oracle(api, oracle, tmp_path, N, M, T, G, R, nsm):
     """Counter-based device RNG: the oracle follows the same Philox streams on the CPU, so whole
     trajectories (permutation, component draws, betas, variances) are comparable for any seed."""

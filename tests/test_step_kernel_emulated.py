@@ -233,3 +233,37 @@ def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
     assert rc == 0
     for t in range(T):
         np.testing.assert_allclose(eps[t, :N], want[t][:N], rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("N,nsm,T,V", [(1795, 2, 1, 2100), (777, 3, 2, 1100)])
+def test_emulated_step_kernel_with_partial_sums_in_global_memory(emu, oracle, tmp_path, N, nsm, T, V):
+    """More markers per step than shared memory holds partial sums for (V * T > 2,048): the CTAs accumulate in their slots of
+    the global partial array, pass after pass (first pass stores, later passes add); the third CTA of the second case owns no
+    rows in some passes.  Dots against the oracle's decode, holes included."""
+    M = 40
+    d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=0.01, missing_rate=0.01, seed=7)
+    pp = d["paths"]
+    inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
+    tri, miss_off, miss_idx, nrows = to_device_layout(inp["bed"], N, nsm)
+    npad, stride = nrows * 256, nrows * 64
+    mask4 = np.zeros((T, stride), dtype=np.uint8)
+    mask4[:, : inp["mask4"].shape[1]] = inp["mask4"]
+    eps = np.zeros((T, npad))
+    eps[:, :N] = inp["eps0"][:, :N]
+    a = dosages(inp["bed"], N)
+    rng = np.random.default_rng(V)
+    cols = rng.integers(0, M, size=V).astype(np.int32)
+    cols[rng.integers(0, V, size=5)] = -1
+    plan = api.step_plan(N, nsm, V, T, want_ranges=False)
+    assert plan is not None and plan["traits_per_launch"] == T
+    partial = np.full((V, T, nsm), np.nan)
+    spart = np.full((T, nsm), np.nan)
+    rc = emu.emu_step(p(tri), N, nsm, p(cols), V, p(eps), p(mask4), T, plan["traits_per_launch"], plan["rows_per_pass"],
+                      plan["npass"], p(partial), p(spart), None, 0, p(miss_off), p(miss_idx))
+    assert rc == 0
+    ok = cols >= 0
+    for t in range(T):
+        got = partial[:, t, :].sum(axis=1)
+        want = a[np.maximum(cols, 0)] @ eps[t, :N]
+        assert np.isfinite(got[ok]).all()
+        assert np.abs(got[ok] - want[ok]).max() <= 1e-12 * max(np.abs(want).max(), 1.0)
