@@ -661,23 +661,23 @@ __device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0
 }
 
 // ---- (c) stream the V columns through the tables of NR rows
-// GP: the per-marker partial sums live in global memory (p.partial, this CTA's slots) instead of shared memory -- for steps
-// of more markers than shared memory can hold partials for next to the tables; `first`: the step's first pass (nothing to add to)
-template <int NR, int T, bool GP>
-__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, bool first) {
+// Markers [v0, v0 + Vc) of the step (a chunk whose Vc * T partial sums fit the shared-memory array `part`).
+template <int NR, int T>
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
     const uint32_t low = (uint32_t)l16 * 8u;
-    const int nb = (p.V + kBatch - 1) / kBatch;
+    const int nb = (Vc + kBatch - 1) / kBatch;
     int b = warp;
     if (b >= nb) return;
     const uint8_t* base = p.bed + (int64_t)row0 * kRowBytes + l16 * 4;
+    const int32_t* ccols = p.cols + v0;
 
     // raw column index (may be -1: no marker); the clamp is applied where the value is USED -- clamping here would make
     // the warp wait for this load at once instead of a batch later (measured: 17 % of the stream's stall samples)
     auto loadcols = [&](int bb) -> int {
         const int v = bb * kBatch + (l16 & (kBatch - 1));
-        return (bb < nb && v < p.V) ? p.cols[v] : 0;
+        return (bb < nb && v < Vc) ? ccols[v] : 0;
     };
     // register prefetch: Wn holds the next batch, Wn2 (GMRM_STEP_DEPTH == 2) the one after
     uint32_t Wn[kPairs][NR];
@@ -748,16 +748,6 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         for (int i = 0; i < kPairs; i++)
 #pragma unroll
             for (int t = 0; t < T; t++) acc[i][t] = 0.0;
-        // global partials: the owner lane's running sums of this batch's marker, loaded here and used after the look-ups
-        [[maybe_unused]] double pold[T];
-        [[maybe_unused]] double* pslot = nullptr;
-        if constexpr (GP) {
-            const int v = b * kBatch + 2 * own + h;
-            const bool owner = (l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V;
-            if (owner) pslot = p.partial + ((int64_t)v * p.Ttot + p.t0) * gridDim.x + blockIdx.x;
-#pragma unroll
-            for (int t = 0; t < T; t++) pold[t] = (owner && !first) ? pslot[(int64_t)t * gridDim.x] : 0.0;
-        }
 
 #define GMRM_LOOKUP(RR, K)                                                    \
     _Pragma("unroll") for (int i = 0; i < kPairs; i++)                             \
@@ -809,11 +799,7 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
             const int v = b * kBatch + 2 * own + h;
-            if constexpr (GP) {
-                if (pslot) pslot[(int64_t)t * gridDim.x] = pold[t] + b1;
-            } else {
-                if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < p.V) part[v * T + t] += b1;
-            }
+            if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < Vc) part[v * T + t] += b1;
         }
     }
 }
@@ -834,8 +820,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     const int area = step_area_bytes(p.V, T, p.rows_per_pass, npass);                        // tables / update staging
     PubStage* stage = reinterpret_cast<PubStage*>(tabs + (size_t)area);                      // 256-aligned
     double* part = reinterpret_cast<double*>(stage + kPubCap);
-    const bool gp = step_part_global(p.V, T);             // partial sums in global memory: no shared-memory array
-    PubInfo* info = reinterpret_cast<PubInfo*>(part + (gp ? 0 : (size_t)p.V * T));
+    // a step of more markers than `part` holds sums for is streamed in chunks of kPartSmemDoubles / T markers per pass; each
+    // chunk's sums are then added to the CTA's slots of the global partial array (L2-resident) before the next chunk
+    const int Vc_max = kPartSmemDoubles / T, npart = min(p.V, Vc_max) * T;
+    const bool chunked = p.V > Vc_max;
+    PubInfo* info = reinterpret_cast<PubInfo*>(part + (size_t)npart);
     uint32_t* lut = reinterpret_cast<uint32_t*>(info + kPubCap);
     PassRows& pr = *reinterpret_cast<PassRows*>(lut + 82);
     uint32_t* bitmap = reinterpret_cast<uint32_t*>(&pr + 1);
@@ -858,8 +847,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     int nk = 8;
 #define GMRM_TICK() if (profme) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     if (p.V > 0 && p.pf && npass > 0 && pr.count[0] > 0) prefetch_pass_head(p, pr.start[0], pr.count[0]);
-    if (!gp)
-        for (int i = tid; i < p.V * T; i += NT) part[i] = 0.0;
+    for (int i = tid; i < npart; i += NT) part[i] = 0.0;
     // everything above touched only this CTA's shared memory, the launch parameters and read-only inputs (the step table,
     // the genotypes): it may run while the sampler kernel of the previous step is still finishing
     pdl_wait();
@@ -885,35 +873,34 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     double es[T];
 #pragma unroll
     for (int t = 0; t < T; t++) es[t] = 0.0;
-    bool gp_started = false;
+    bool flushed = false;                                 // chunked steps: the global slots hold the sums of earlier passes
     for (int pass = 0; pass < npass; pass++) {
         const int r_lo = pr.start[pass], nrp = pr.count[pass];
         build_tables<T, NT>(p, r_lo, nrp, es);
         __syncthreads();
         GMRM_TICK()                                       // [9 + 3*pass] sync + build
-        // (with global partials a CTA without rows in the step's first pass still has to zero its slots: nrp == 0 below)
-        if (gp) {
-            const bool first = !gp_started;
+        for (int v0 = 0; v0 < p.V; v0 += Vc_max) {
+            const int Vc = min(Vc_max, p.V - v0);
             switch (nrp) {
-            case 0: break;
-            case 1: stream_rows<1, T, true>(p, r_lo, part, first); break;
-            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, true>(p, r_lo, part, first); break;
-            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, true>(p, r_lo, part, first); break;
-            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, true>(p, r_lo, part, first); break;
-            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T, true>(p, r_lo, part, first); break;
+            case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part, v0, Vc); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part, v0, Vc); break;
+            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc); break;
             default: break;
             }
-            if (nrp > 0) gp_started = true;
-        } else {
-            switch (nrp) {
-            case 1: stream_rows<1, T, false>(p, r_lo, part, false); break;
-            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T, false>(p, r_lo, part, false); break;
-            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T, false>(p, r_lo, part, false); break;
-            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T, false>(p, r_lo, part, false); break;
-            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T, false>(p, r_lo, part, false); break;
-            default: break;
+            if (chunked && nrp > 0) {                     // this chunk's sums of this pass -> the CTA's global slots
+                __syncthreads();
+                for (int i = tid; i < Vc * T; i += NT) {
+                    const int v = v0 + i / T, t = i % T;
+                    double* slot = p.partial + ((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta;
+                    *slot = flushed ? *slot + part[i] : part[i];
+                    part[i] = 0.0;
+                }
+                __syncthreads();
             }
         }
+        if (chunked && nrp > 0) flushed = true;
         GMRM_TICK()                                       // [10 + 3*pass] this warp's streaming
         if (p.pf && pass + 1 < npass && pr.count[pass + 1] > 0) prefetch_pass_head(p, pr.start[pass + 1], pr.count[pass + 1]);
         if (pass + 1 < npass) __syncthreads();            // everyone is done with these tables
@@ -921,12 +908,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     __syncthreads();
     GMRM_TICK()
-    if (!gp) {
+    if (!chunked) {
         for (int i = tid; i < p.V * T; i += NT) {
             const int v = i / T, t = i - v * T;
             p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
         }
-    } else if (!gp_started) {                             // a CTA that owns no rows at all (more CTAs than rows): its slots are zero
+    } else if (!flushed) {                                // a CTA that owns no rows at all (more CTAs than rows): its slots are zero
         for (int i = tid; i < p.V * T; i += NT) {
             const int v = i / T, t = i - v * T;
             p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = 0.0;
@@ -1312,7 +1299,7 @@ int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass) {
     if (step_npass(L, rows_per_pass) > kMaxPasses) return -1;
     const int nrmax = step_npass(L, rows_per_pass) * rows_per_pass;   // bound on the rows one CTA owns
     const int64_t bytes = (int64_t)kTabBase + (int64_t)step_area_bytes(V, T, rows_per_pass, step_npass(L, rows_per_pass)) + (int64_t)kPubCap * 32 +
-                          (step_part_global(V, T) ? 0 : (int64_t)V * T * 8) + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 4 * 32 * 4;
+                          (int64_t)(V < kPartSmemDoubles / T ? V : kPartSmemDoubles / T) * T * 8 + (int64_t)kPubCap * 8 + 82 * 4 + (int64_t)sizeof(PassRows) + (int64_t)((nrmax * 8 + 1) & ~1) * 4 + 32 * 8 + 4 * 32 * 4;
     return bytes <= kMaxDynSmem ? (int)bytes : -1;
 }
 

@@ -20,10 +20,10 @@ namespace gmrm {
 #ifndef GMRM_STEP_DEPTH
 #define GMRM_STEP_DEPTH 1
 #endif
-// Per-marker partial sums of a step: in shared memory while V * T of them fit next to the full set of table slots
-// (16 KB: 2,048 markers x 1 trait), in global memory (the CTA's slots of StepParams::partial, L2-resident) beyond that.
+// Per-marker partial sums of a step live in shared memory, kPartSmemDoubles of them (16 KB next to the full set of table
+// slots); a step of more (marker, trait) pairs is streamed in chunks of that size per pass, each chunk's sums being added to
+// the CTA's slots of StepParams::partial (L2-resident) before the next chunk.
 constexpr int kPartSmemDoubles = 2048;
-__host__ __device__ constexpr bool step_part_global(int V, int T) { return (long long)V * T > kPartSmemDoubles; }
 constexpr int kBatch = GMRM_STEP_BATCH;   // markers per warp batch (one marker per half-warp: kBatch/2 pairs)
 constexpr int kMaxGpus = 8;
 constexpr int kPubCap = 128;           // published updates staged per round of the update phase

@@ -146,6 +146,37 @@ def test_cli_outputs_match_oracle(data, oracle, vranks, thin):
         np.testing.assert_allclose(mb, np.mean([res["betas"][i][t] for i in range(2, iters)], axis=0), rtol=1e-8, atol=1e-13)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("sync_rate", [1, 3])
+def test_cli_two_gpus_match_oracle(data, oracle, sync_rate):
+    """--gpus 2: two host threads in one process, one engine each, peers' buffers passed as plain pointers (sync rate 1: list
+    exchange over peer memory; sync rate 3: all-reduced residual deltas) against the oracle with the same 16 virtual ranks."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = os.path.join(data["tmp"], f"out_2gpu_{sync_rate}")
+    iters, seed, vranks = 4, 77, 16
+    r = run(base_args(data, out) + ["--iterations", str(iters), "--seed", str(seed), "--vranks", str(vranks), "--gpus", "2",
+                                     "--sync-rate", str(sync_rate)])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    p = data["paths"]
+    inp = oracle.load_inputs(p["bed"], p["dim"], p["phen"], p["gri"], p["grm"])
+    res = oracle.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=inp["N"], R=vranks,
+                       nrep=1 if sync_rate == 1 else 2, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
+    for t in range(2):
+        stem = os.path.splitext(os.path.basename(p["phen"][t]))[0]
+        its, bet = oracle.read_bet(os.path.join(out, stem + ".bet"))
+        _, cpn = oracle.read_cpn(os.path.join(out, stem + ".cpn"))
+        assert list(its) == list(range(1, iters + 1))
+        for i in range(iters):
+            assert np.array_equal(cpn[i], res["comp"][i][t])
+            np.testing.assert_allclose(bet[i], res["betas"][i][t], rtol=1e-8, atol=1e-13)
+        csv = oracle.read_csv(os.path.join(out, stem + ".csv"))
+        for i in range(iters):
+            np.testing.assert_allclose(csv[i]["sigmag"], res["sigmag"][i][t], rtol=1e-8)
+            np.testing.assert_allclose(csv[i]["sigmae"], res["sigmae"][i][t], rtol=1e-8)
+
+
 # ------------------------------------------------------------------ --predict (Bayes::predict, bayes.cpp:14-284)
 def write_predict_inputs(d, out, M, niter=3, seed=5):
     """A .bim pair (reference reversed, every 50th id replaced) and a .bet history per trait, as the Gibbs mode writes it."""
