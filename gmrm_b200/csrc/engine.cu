@@ -133,6 +133,10 @@ struct gmrm_engine {
     DevBuf<double> delta, delta_tot, gc;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
     DevBuf<uint32_t> miss_off, miss_idx, miss_cnt;
+    // individuals without a phenotype, per trait (what the marker statistics take out of the whole-column dosage counts)
+    std::vector<std::vector<uint32_t>> h_na;
+    DevBuf<uint32_t> na_off, na_idx;
+    bool na_dirty = true;
     // missing-genotype lists are collected per uploaded chunk (the base-3 bytes do not carry them) and
     // assembled into one CSR by gmrm_finalize_bed
     struct MissChunk { int begin = 0, count = 0; std::vector<uint32_t> cnt; DevBuf<uint32_t>* idx = nullptr; uint64_t total = 0; };
@@ -250,6 +254,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
         return fail(GMRM_EINVAL, "%d virtual ranks per GPU do not fit the step kernel's shared memory (partials + one table slot)", vl);
     }
     e->phen_set.assign(c->T, 0);
+    e->h_na.assign(c->T, {});
     e->h_nonas.assign(c->T, 0);
 
     int rc = 0;
@@ -275,7 +280,11 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T)); A(e->gc.alloc((size_t)T * G * 4 * K));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
     A(e->miss_off.alloc((size_t)e->Mloc + 1)); A(e->miss_idx.alloc(1));
-    e->list_exchange = c->world_size > 1 && c->sync_rate == 1;
+    // Exchange at sync_rate 1 (GMRM_EXCHANGE): "lists" (default) -- every GPU applies every GPU's published updates itself, reading
+    // the other shards' columns over NVLink; "delta" -- every GPU applies its own updates and the residual deltas are all-reduced
+    // (what sync_rate > 1 always does); "nccl" -- lists, gathered by NCCL instead of pushed by the sampler kernel
+    const char* xmode = getenv("GMRM_EXCHANGE");
+    e->list_exchange = c->world_size > 1 && c->sync_rate == 1 && !(xmode && strcmp(xmode, "delta") == 0);
     if (c->world_size > kMaxGpus) { delete e; return fail(GMRM_EINVAL, "world_size %d > %d", c->world_size, kMaxGpus); }
     if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
     if (const char* v = getenv("GMRM_EXCHANGE")) e->list_p2p = strcmp(v, "nccl") != 0;
@@ -490,10 +499,11 @@ int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint
     std::vector<double> h((size_t)L.npad, 0.0);
     std::vector<uint8_t> nm((size_t)L.col_stride, 0);
     int seen = 0;
+    std::vector<uint32_t> nas;
     for (int i = 0; i < L.N; i++) {
         const bool obs = (mask4[i / 4] >> (i % 4)) & 1;
         h[i] = obs ? eps0[i] : 0.0;
-        if (!obs) continue;
+        if (!obs) { nas.push_back((uint32_t)i); continue; }
         seen++;
         nm[i / 4] |= (uint8_t)(1u << (i % 4));
     }
@@ -503,6 +513,8 @@ int gmrm_set_phenotype(gmrm_engine* e, int32_t t, const double* eps0, const uint
     CU(cudaMemcpyAsync(e->nonas.p + t, &nonas, 4, cudaMemcpyHostToDevice, e->stream));
     CU(cudaStreamSynchronize(e->stream));
     e->h_nonas[t] = nonas;
+    e->h_na[t] = std::move(nas);
+    e->na_dirty = true;
     e->phen_set[t] = 1;
     e->stats_done = false;
     e->chain_ready = false;
@@ -538,13 +550,29 @@ int gmrm_set_groups(gmrm_engine* e, const int32_t* group_index, const double* cv
 }
 
 // ------------------------------------------------------------------------------ marker statistics
+static int upload_na_lists(gmrm_engine* e) {
+    if (!e->na_dirty) return 0;
+    const int T = e->cfg.T;
+    std::vector<uint32_t> off((size_t)T + 1, 0), idx;
+    for (int t = 0; t < T; t++) { idx.insert(idx.end(), e->h_na[t].begin(), e->h_na[t].end()); off[t + 1] = (uint32_t)idx.size(); }
+    int rc = e->na_off.alloc((size_t)T + 1); if (rc) return rc;
+    rc = e->na_idx.alloc(std::max<size_t>(idx.size(), 1)); if (rc) return rc;
+    CU(cudaMemcpyAsync(e->na_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    if (!idx.empty()) CU(cudaMemcpyAsync(e->na_idx.p, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    e->na_dirty = false;
+    return 0;
+}
+
 int gmrm_compute_marker_stats(gmrm_engine* e) {
     if (!e) return fail(GMRM_EINVAL, "null engine");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     for (int t = 0; t < e->cfg.T; t++)
         if (!e->phen_set[t]) return fail(GMRM_EINVAL, "phenotype %d not set", t);
     CU(cudaSetDevice(e->cfg.device));
-    launch_stats(e->bed.p, e->Mloc, e->L, e->mask4.p, e->miss_off.p, e->miss_idx.p, e->nonas.p, e->cfg.T, e->mave.p, e->msig.p, e->stream);
+    { const int rc = upload_na_lists(e); if (rc) return rc; }
+    launch_stats(e->bed.p, e->Mloc, e->L, e->mask4.p, e->miss_off.p, e->miss_idx.p, e->nonas.p, e->na_off.p, e->na_idx.p, e->cfg.T, e->mave.p,
+                 e->msig.p, e->stream);
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(e->stream));
     e->stats_done = true;
@@ -754,7 +782,9 @@ int gmrm_predict(gmrm_engine* e, int32_t t, const double* y, const double* beta_
     const uint8_t* keep_d = keep ? d_keep.p : nullptr;
     launch_iota(cols.p, Mloc, s);
     // sum (a b na)^2 per marker from the dosage counts under the trait's NA mask (bayes.cpp:190-195)
-    launch_stats(e->bed.p, Mloc, L, mask_t, e->miss_off.p, e->miss_idx.p, e->nonas.p + t, 1, d_scr.p, d_scr.p + std::max(Mloc, 1), s, d_xtx.p);
+    if ((rc = upload_na_lists(e))) return rc;
+    launch_stats(e->bed.p, Mloc, L, mask_t, e->miss_off.p, e->miss_idx.p, e->nonas.p + t, e->na_off.p + t, e->na_idx.p, 1, d_scr.p,
+                 d_scr.p + std::max(Mloc, 1), s, d_xtx.p);
     CU(cudaGetLastError());
 
     // pass 1: g = sum over all blocks of their genetic values (bayes.cpp:87-136)

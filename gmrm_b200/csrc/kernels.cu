@@ -163,62 +163,98 @@ __global__ void generate_plink_kernel(uint8_t* __restrict__ dst, int nmark, int 
 // reference's loops are sums of small integers, hence these counts exactly.
 // =====================================================================================
 // [stats-begin]  (tests/test_stats_kernel_emulated.py compiles the text up to [stats-end] for the host, see tests/emu/)
-__global__ void __launch_bounds__(128) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
-                                                    const uint8_t* __restrict__ mask4, const uint32_t* __restrict__ miss_off,
-                                                    const uint32_t* __restrict__ miss_idx, const int32_t* __restrict__ nonas,
-                                                    int T, double* __restrict__ mave, double* __restrict__ msig,
-                                                    double* __restrict__ xtx) {
-    const int j = blockIdx.x;
-    if (j >= nmark) return;
-    __shared__ uint8_t fld[kTabEntries];     // base-3 byte -> 2-bit dosage fields
-    __shared__ uint8_t exp4[16];             // NA nibble -> 2-bit fields (01 = observed)
-    __shared__ int red[3][4];
-    for (int e = threadIdx.x; e < kTabEntries; e += blockDim.x) fld[e] = (uint8_t)tri_to_fields(e);
-    if (threadIdx.x < 16) {
-        const uint32_t m = threadIdx.x;
-        exp4[m] = (uint8_t)((m & 1u) | ((m & 2u) << 1) | ((m & 4u) << 2) | ((m & 8u) << 3));
-    }
-    __syncthreads();
-    const uint32_t* col = reinterpret_cast<const uint32_t*>(bed + (int64_t)j * L.col_stride);
-    const int nwords = (int)(L.col_stride / 4);
-    const uint32_t m0 = miss_off[j], m1 = miss_off[j + 1];
-    for (int t = 0; t < T; t++) {
-        const uint8_t* nmb = mask4 + (int64_t)t * L.col_stride;
-        const uint32_t* nm = reinterpret_cast<const uint32_t*>(nmb);
-        int n0 = 0, n1 = 0, n2 = 0;
-        for (int i = threadIdx.x; i < nwords; i += blockDim.x) {
-            const uint32_t w = col[i], mw = nm[i];
-            const uint32_t f = fld[w & 0xffu] | (fld[(w >> 8) & 0xffu] << 8) | (fld[(w >> 16) & 0xffu] << 16) | (fld[w >> 24] << 24);
-            const uint32_t m = exp4[mw & 0xfu] | (exp4[(mw >> 8) & 0xfu] << 8) | (exp4[(mw >> 16) & 0xfu] << 16) | (exp4[(mw >> 24) & 0xfu] << 24);
-            const uint32_t lo = f & 0x55555555u, hi = (f >> 1) & 0x55555555u;
-            n1 += __popc(lo & ~hi & m);
-            n2 += __popc(hi & ~lo & m);
-            n0 += __popc(~(lo | hi) & 0x55555555u & m);
-        }
-        // missing genotypes were stored as dosage 0: take the observed ones out of n0
-        for (uint32_t i = m0 + threadIdx.x; i < m1; i += blockDim.x) {
-            const uint32_t ind = miss_idx[i];
-            n0 -= (nmb[ind >> 2] >> (ind & 3)) & 1;
-        }
+// One pass over a column, whatever the number of traits: the dosage-1 / dosage-2 counts over ALL individuals come from a
+// per-byte count table (conflict-free: one copy per lane); per trait the few individuals WITHOUT a phenotype are then
+// taken out again from a list (na_idx), and the observed individuals with a missing genotype from the marker's list.
+// Persistent CTAs (the table is built once); HBM-bound: ceil(N/4) bytes per marker.
+constexpr int kStatsThreads = 256;
+#if !defined(__CUDA_ARCH__) && !defined(__CUDACC__)
+inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) { return emu_prmt(a, b, sel); }   // host emulation
+#endif
+__device__ __forceinline__ int stats_block_sum(int v, int* red) {     // every thread gets the total
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n0 += __shfl_xor_sync(0xffffffffu, n0, o);
-            n1 += __shfl_xor_sync(0xffffffffu, n1, o);
-            n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int i = 0; i < kStatsThreads / 32; i++) t += red[i];
+    return t;
+}
+__global__ void __launch_bounds__(kStatsThreads) stats_kernel(const uint8_t* __restrict__ bed, int nmark, Layout L,
+                                                              const uint8_t* __restrict__ mask4, const uint32_t* __restrict__ miss_off,
+                                                              const uint32_t* __restrict__ miss_idx, const int32_t* __restrict__ nonas,
+                                                              const uint32_t* __restrict__ na_off, const uint32_t* __restrict__ na_idx,
+                                                              int T, double* __restrict__ mave, double* __restrict__ msig,
+                                                              double* __restrict__ xtx) {
+    __shared__ uint32_t cnt[kTabEntries * 64];   // [e][lane]: individuals of dosage 1 (bits 0-15) and 2 (bits 16-31) in byte e; stride 256 B
+    __shared__ uint8_t fld[kTabEntries];                        // base-3 byte -> 2-bit dosage fields
+    __shared__ int red[kStatsThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < kTabEntries * 32; i += kStatsThreads) {
+        const int e = i >> 5;
+        const uint32_t f = tri_to_fields((uint32_t)e), lo = f & 0x55u, hi = (f >> 1) & 0x55u;
+        cnt[e * 64 + (i & 31)] = (uint32_t)__popc(lo & ~hi) | ((uint32_t)__popc(hi & ~lo) << 16);
+    }
+    for (int e = tid; e < kTabEntries; e += kStatsThreads) fld[e] = (uint8_t)tri_to_fields((uint32_t)e);
+    __syncthreads();
+    const uint32_t lane4 = (uint32_t)lane * 4u;
+    const char* cntb = reinterpret_cast<const char*>(cnt);
+    const int nvec = (int)(L.col_stride / 16);
+    for (int j = blockIdx.x; j < nmark; j += gridDim.x) {
+        const uint8_t* colb = bed + (int64_t)j * L.col_stride;
+        const uint4* col = reinterpret_cast<const uint4*>(colb);
+        uint32_t acc = 0;                                       // packed counts of this thread's bytes (<= 4 per byte: no overflow below 16k bytes)
+        for (int i0 = tid; i0 < nvec; i0 += 4 * kStatsThreads) {
+            uint4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) w[u] = i0 + u * kStatsThreads < nvec ? __ldg(col + i0 + u * kStatsThreads) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t x[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {                   // byte k -> offset e * 256 + lane * 4: one byte permute each
+                    acc += *reinterpret_cast<const uint32_t*>(cntb + __byte_perm(x[q], lane4, 0x5504));
+                    acc += *reinterpret_cast<const uint32_t*>(cntb + __byte_perm(x[q], lane4, 0x5514));
+                    acc += *reinterpret_cast<const uint32_t*>(cntb + __byte_perm(x[q], lane4, 0x5524));
+                    acc += *reinterpret_cast<const uint32_t*>(cntb + __byte_perm(x[q], lane4, 0x5534));
+                }
+            }
         }
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = n0; red[1][threadIdx.x >> 5] = n1; red[2][threadIdx.x >> 5] = n2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const double c0 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-            const double c1 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-            const double c2 = red[2][0] + red[2][1] + red[2][2] + red[2][3];
-            const double suma = c1 + 2.0 * c2, sumb = c0 + c1 + c2;       // phenotype.cpp:536-537
-            const double av = suma / sumb;                                // 540
-            const double sumsqr = c0 * (0.0 - av) * (0.0 - av) + c1 * (1.0 - av) * (1.0 - av) + c2 * (2.0 - av) * (2.0 - av);  // 544-545
-            mave[(int64_t)t * nmark + j] = av;
-            msig[(int64_t)t * nmark + j] = 1.0 / sqrt(sumsqr / ((double)nonas[t] - 1.0));   // 548
-            if (xtx) xtx[(int64_t)t * nmark + j] = c1 + 4.0 * c2;        // sum (a b na)^2 of Bayes::predict, bayes.cpp:190-195
+        const int all1 = stats_block_sum((int)(acc & 0xffffu), red), all2 = stats_block_sum((int)(acc >> 16), red);
+        const uint32_t m0 = miss_off[j], m1 = miss_off[j + 1];
+        // pad slots of the last PLINK byte keep whatever bits the file had (00 = dosage 2 as PLINK writes them): not individuals
+        int pad1 = 0, pad2 = 0;
+        if (tid == 0)
+            for (int ind = L.N; ind < 4 * L.mbytes; ind++) {
+                const uint32_t d = ((uint32_t)fld[colb[ind >> 2]] >> (2 * (ind & 3))) & 3u;
+                pad1 += d == 1u; pad2 += d == 2u;
+            }
+        for (int t = 0; t < T; t++) {
+            const uint8_t* nmb = mask4 + (int64_t)t * L.col_stride;
+            // individuals without a phenotype: their dosages leave the counts (na_lut == 0, phenotype.cpp:500-530)
+            int d1 = pad1, d2 = pad2, mo = 0;
+            for (uint32_t i = na_off[t] + tid; i < na_off[t + 1]; i += kStatsThreads) {
+                const uint32_t ind = na_idx[i];
+                const uint32_t d = ((uint32_t)fld[colb[ind >> 2]] >> (2 * (ind & 3))) & 3u;
+                d1 += d == 1u; d2 += d == 2u;
+            }
+            // missing genotypes were stored as dosage 0: the observed ones are no dosage-0 individuals
+            for (uint32_t i = m0 + tid; i < m1; i += kStatsThreads) {
+                const uint32_t ind = miss_idx[i];
+                mo += (nmb[ind >> 2] >> (ind & 3)) & 1;
+            }
+            const int n1 = all1 - stats_block_sum(d1, red), n2 = all2 - stats_block_sum(d2, red);
+            const int n0 = nonas[t] - n1 - n2 - stats_block_sum(mo, red);
+            if (tid == 0) {
+                const double c0 = n0, c1 = n1, c2 = n2;
+                const double suma = c1 + 2.0 * c2, sumb = c0 + c1 + c2;       // phenotype.cpp:536-537
+                const double av = suma / sumb;                                // 540
+                const double sumsqr = c0 * (0.0 - av) * (0.0 - av) + c1 * (1.0 - av) * (1.0 - av) + c2 * (2.0 - av) * (2.0 - av);  // 544-545
+                mave[(int64_t)t * nmark + j] = av;
+                msig[(int64_t)t * nmark + j] = 1.0 / sqrt(sumsqr / ((double)nonas[t] - 1.0));   // 548
+                if (xtx) xtx[(int64_t)t * nmark + j] = c1 + 4.0 * c2;        // sum (a b na)^2 of Bayes::predict, bayes.cpp:190-195
+            }
         }
     }
 }
@@ -1108,16 +1144,22 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
         }
         if (lane == 0 && n) atomicAdd(&s_npub, n);
     }
-    if (push) __threadfence_system();                        // this CTA's segments are visible to the peers ...
-    __syncthreads();
+    __syncthreads();                                         // the CTA's segment stores are ordered before thread 0's fence below
     if (tid == 0 && s_npub) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), (unsigned long long)s_npub);
     if (!push) return;
+    // ONE system-scope fence per CTA (a fence by every thread -- 2,048 warps per step -- costs ~10 us of sampler time):
+    // barrier + thread 0's fence make this CTA's segments visible to the peers before it takes its ticket
     __shared__ bool last;
-    if (tid == 0) last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;    // ... before it takes its ticket
+    if (tid == 0) {
+        __threadfence_system();
+        last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!last) return;
-    __threadfence_system();                                  // every CTA's segments before the flags
-    if (tid < p.world) *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
+    if (tid < p.world) {                                     // every CTA's segments (ticket order) before the flags
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
+    }
     if (tid == 0) *p.ticket = 0u;
 }
 // [sample-end]
@@ -1266,9 +1308,11 @@ void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, con
     generate_plink_kernel<<<grid, 256, 0, s>>>(dst, nmark, first_global_marker, L, seed, maf_lo, maf_hi, missing_rate);
 }
 void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
-                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s, double* xtx) {
+                  const int32_t* nonas, const uint32_t* na_off, const uint32_t* na_idx, int T, double* mave, double* msig, cudaStream_t s,
+                  double* xtx) {
     if (nmark <= 0) return;
-    stats_kernel<<<nmark, 128, 0, s>>>(bed, nmark, L, mask4, miss_off, miss_idx, nonas, T, mave, msig, xtx);
+    const int ctas = nmark < 8 * L.nsm ? nmark : 8 * L.nsm;          // persistent: 8 CTAs of 256 threads per SM
+    stats_kernel<<<ctas, kStatsThreads, 0, s>>>(bed, nmark, L, mask4, miss_off, miss_idx, nonas, na_off, na_idx, T, mave, msig, xtx);
 }
 void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s) {
     dim3 grid((unsigned)((L.npad + 255) / 256), (unsigned)T);

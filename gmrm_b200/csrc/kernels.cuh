@@ -126,8 +126,10 @@ void launch_decode_column(const uint8_t* col, const Layout& L, const uint32_t* m
 void launch_decode_namask(const uint8_t* mask4, const Layout& L, double* na, cudaStream_t s);
 void launch_generate_plink(uint8_t* dst, int nmark, int first_global_marker, const Layout& L, uint32_t seed,
                            double maf_lo, double maf_hi, double missing_rate, cudaStream_t s);
+// na_off [T+1] / na_idx: per trait the individuals (< N) without a phenotype, ascending
 void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t* mask4, const uint32_t* miss_off, const uint32_t* miss_idx,
-                  const int32_t* nonas, int T, double* mave, double* msig, cudaStream_t s, double* xtx = nullptr);
+                  const int32_t* nonas, const uint32_t* na_off, const uint32_t* na_idx, int T, double* mave, double* msig, cudaStream_t s,
+                  double* xtx = nullptr);
 void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s);
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);

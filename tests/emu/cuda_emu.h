@@ -33,6 +33,7 @@ alignas(256) inline uint8_t emu_smem_storage[256 * 1024];
 
 struct int2 { int x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 struct alignas(16) double2 { double x, y; };
 
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }

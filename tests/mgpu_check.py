@@ -74,14 +74,15 @@ def chain_check(rank, world, local, sync_rate, Vl=8):
 
 
 def _compare(inp, gathered, N, R, T, world, sync_rate, iters, seed, rank):
-    if sync_rate == 1:          # list exchange: ONE chain, every GPU holds the same residuals bit for bit
+    delta_mode = sync_rate > 1 or os.environ.get("GMRM_EXCHANGE") == "delta"   # one residual replica per GPU, deltas all-reduced
+    if not delta_mode:          # list exchange: ONE chain, every GPU holds the same residuals bit for bit
         for (_, _, _, eps_g) in gathered[1:]:
             assert np.array_equal(eps_g, gathered[0][3]), "residual replicas are not bit-identical"
     if rank == 0:
         # sync_rate 1: list exchange, every GPU holds the residuals of ONE chain with R virtual ranks (the reference under
         # mpirun -n R); sync_rate > 1: one residual replica per GPU, deltas all-reduced every sync_rate steps
         res = O.gibbs(inp["bed"], inp["eps0"], inp["mask4"], inp["nonas"], inp["group_index"], inp["cva"], N=N, R=R,
-                      nrep=1 if sync_rate == 1 else world, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
+                      nrep=world if delta_mode else 1, iterations=iters, rng_mode=1, seed=seed, sync_rate=sync_rate)
         for (lo_g, n_g, hist_g, eps_g) in gathered:
             for i in range(iters):
                 assert np.array_equal(hist_g[i]["comp"], res["comp"][i][:, lo_g:lo_g + n_g]), f"comp differs it {i + 1}"

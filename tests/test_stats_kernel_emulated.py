@@ -18,10 +18,11 @@ EMU = os.path.join(ROOT, "tests", "emu")
 
 TAIL = r'''
 extern "C" void emu_stats(const uint8_t* bed, int nmark, int N, int nsm, const uint8_t* mask4, const uint32_t* miss_off,
-                          const uint32_t* miss_idx, const int32_t* nonas, int T, double* mave, double* msig, double* xtx) {
+                          const uint32_t* miss_idx, const int32_t* nonas, const uint32_t* na_off, const uint32_t* na_idx, int T,
+                          double* mave, double* msig, double* xtx, int ctas) {
     using namespace gmrm;
     const Layout L = make_layout(N, nsm);
-    emu_launch(EmuDim3(nmark), EmuDim3(128), [&] { stats_kernel(bed, nmark, L, mask4, miss_off, miss_idx, nonas, T, mave, msig, xtx); });
+    emu_launch(EmuDim3(ctas), EmuDim3(kStatsThreads), [&] { stats_kernel(bed, nmark, L, mask4, miss_off, miss_idx, nonas, na_off, na_idx, T, mave, msig, xtx); });
 }
 '''
 
@@ -50,7 +51,12 @@ def test_emulated_stats_kernel_matches_oracle(emu, oracle, tmp_path, N, M, T, na
     mask4[:, : inp["mask4"].shape[1]] = inp["mask4"]
     nonas = np.ascontiguousarray(inp["nonas"], dtype=np.int32)
     mave = np.full((T, M), np.nan); msig = np.full((T, M), np.nan); xtx = np.full((T, M), np.nan)
-    emu.emu_stats(p(tri), M, N, 1, p(mask4), p(miss_off), p(miss_idx), p(nonas), T, p(mave), p(msig), p(xtx))
+    obs_all = ((inp["mask4"][:, :, None] >> np.arange(4)) & 1).reshape(T, -1)[:, :N].astype(bool)
+    nas = [np.flatnonzero(~obs_all[t]).astype(np.uint32) for t in range(T)]              # individuals without a phenotype, per trait
+    na_off = np.concatenate([[0], np.cumsum([x.size for x in nas])]).astype(np.uint32)
+    na_idx = np.concatenate(nas + [np.zeros(1, np.uint32)]).astype(np.uint32)
+    emu.emu_stats(p(tri), M, N, 1, p(mask4), p(miss_off), p(miss_idx), p(nonas), p(na_off), p(na_idx), T, p(mave), p(msig), p(xtx),
+                  3)                                                                       # 3 persistent CTAs share the M markers
     codes = (inp["bed"][:, :, None] >> (2 * np.arange(4))) & 3
     a = np.where(codes == 0, 2.0, np.where(codes == 2, 1.0, 0.0)).reshape(M, -1)[:, :N]
     for t in range(T):
