@@ -151,6 +151,7 @@ struct gmrm_engine {
     unsigned long long* peer_xflags[kMaxGpus] = {};  // peers' (and own) flag arrays [world]
     void* ipc_opened[kMaxGpus][5] = {};
     bool list_p2p = true;            // lists are pushed into the peers' buffers by the sampler kernel (GMRM_EXCHANGE=nccl: all-gather)
+    bool merge_pending = false;      // delta exchange: the all-reduced deltas wait to be merged by the next step kernel (fused merge)
     unsigned long long xseq = 0;     // exchange sequence number: one per sampled step, identical on all GPUs
     unsigned long long pend_seq = 0; // sequence number of the step whose lists are pending
     DevBuf<unsigned long long> xflags;
@@ -621,6 +622,7 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
             p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
         }
         p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
+        p.merge_tot = (e->merge_pending && in_loop) ? e->delta_tot.p : nullptr;   // only launches of the marker loop take the fused merge
         p.err = e->err.p;
         p.prof = e->prof.p;
         p.pf = e->step_pf;
@@ -629,6 +631,7 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         if (rc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         if (nlaunch) (*nlaunch)++;
     }
+    if (in_loop) e->merge_pending = false;                       // every trait chunk merged its traits' rows
     return 0;
 }
 
@@ -1030,8 +1033,9 @@ int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) 
         if (delta_exchange) {
             NC(g_nccl.AllReduce(e->delta.p, e->delta_tot.p, (size_t)T * L.npad, kNcclFloat64, kNcclSum, e->comm, s));
             if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
-            launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, s);
-            launches += 2;
+            if (st == Mm - 1) { launch_eps_merge(e->eps.p, e->delta.p, e->delta_tot.p, L, T, s); launches += 1; }   // the epilogue reads eps
+            else e->merge_pending = true;                        // merged by the next step kernel, CTA by CTA (no extra launch)
+            launches += 1;
         }
         if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 4], s));
     }

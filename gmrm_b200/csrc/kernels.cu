@@ -901,6 +901,22 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         __threadfence();
         __syncthreads();
     }
+    if (p.merge_tot != nullptr && nr > 0) {               // residual deltas of the last exchange (all-reduced): what the OTHER shards changed
+        for (int t = 0; t < T; t++) {
+            const int64_t tb = (int64_t)(p.t0 + t) * p.npad;
+            for (int q = tid; q < nr * kRowBytes; q += NT) {
+                const int64_t o = tb + 4 * ((int64_t)global_row(pr, q >> 6) * kRowBytes + (q & 63));
+                double2* e2 = reinterpret_cast<double2*>(p.eps + o);
+                double2* l2 = reinterpret_cast<double2*>(p.delta + o);
+                const double2* t2 = reinterpret_cast<const double2*>(p.merge_tot + o);
+                const double2 ea = e2[0], eb = e2[1], la = l2[0], lb = l2[1], ta = t2[0], tb2 = t2[1];
+                e2[0] = make_double2(ea.x + (ta.x - la.x), ea.y + (ta.y - la.y));
+                e2[1] = make_double2(eb.x + (tb2.x - lb.x), eb.y + (tb2.y - lb.y));
+                l2[0] = make_double2(0.0, 0.0); l2[1] = make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+    }
     if (p.pG * p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     GMRM_TICK()                                           // [8] prologue + update phase

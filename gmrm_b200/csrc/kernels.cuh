@@ -70,6 +70,8 @@ struct StepParams {
     const uint32_t* pmiss_idx[kMaxGpus];
     const uint8_t* mask4;    // [Ttot][col_stride] NA nibble of every quad (bit k: individual 4q+k observed)
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
+    const double* merge_tot; // [Ttot][npad] or nullptr: all-reduced deltas of the last exchange, still to be merged: every CTA first
+                             // adds (merge_tot - delta) to its rows of eps and clears delta (the merge kernel, fused)
     int32_t* err;
     int32_t pf;              // 1: L2 prefetch ahead of the streaming loads
     int32_t pdl;             // host side: launch with the programmatic-serialization attribute (the prologue overlaps the previous kernel)
