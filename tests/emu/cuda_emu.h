@@ -35,6 +35,7 @@ struct int2 { int x, y; };
 struct uint4 { uint32_t x, y, z, w; };
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 struct alignas(16) double2 { double x, y; };
+inline double2 make_double2(double x, double y) { return double2{x, y}; }
 
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
