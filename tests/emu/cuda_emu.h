@@ -132,3 +132,15 @@ inline void emu_launch(EmuDim3 grid, EmuDim3 block, const std::function<void()>&
             for (auto& x : th) x.join();
         }
 }
+
+// individuals (< N) without a phenotype, per trait: what gmrm_set_phenotype collects for stats_kernel (engine.cu)
+inline void emu_na_lists(const uint8_t* mask4, int64_t col_stride, int T, int N, std::vector<uint32_t>& off, std::vector<uint32_t>& idx) {
+    off.assign((size_t)T + 1, 0u);
+    idx.clear();
+    for (int t = 0; t < T; t++) {
+        for (int i = 0; i < N; i++)
+            if (!((mask4[(int64_t)t * col_stride + (i >> 2)] >> (i & 3)) & 1)) idx.push_back((uint32_t)i);
+        off[(size_t)t + 1] = (uint32_t)idx.size();
+    }
+    if (idx.empty()) idx.push_back(0u);
+}

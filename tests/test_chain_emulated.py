@@ -53,7 +53,9 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
                 mask4[(size_t)t * L.col_stride + i / 4] |= (uint8_t)(1u << (i % 4));
             }
     // ---- statistics
-    emu_launch(EmuDim3(Mt), EmuDim3(128), [&] { stats_kernel(bed.data(), Mt, L, mask4.data(), off.data(), midx.data(), nonas, T, o_mave, o_msig, nullptr); });
+    std::vector<uint32_t> na_off, na_idx;
+    emu_na_lists(mask4.data(), L.col_stride, T, N, na_off, na_idx);
+    emu_launch(EmuDim3(std::min(Mt, 3)), EmuDim3(kStatsThreads), [&] { stats_kernel(bed.data(), Mt, L, mask4.data(), off.data(), midx.data(), nonas, na_off.data(), na_idx.data(), T, o_mave, o_msig, nullptr); });
     // ---- chain start (gmrm_init_chain)
     std::vector<int32_t> mtotgrp(G, 0);
     for (int j = 0; j < Mt; j++) mtotgrp[group[j]]++;

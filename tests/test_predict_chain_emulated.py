@@ -40,7 +40,9 @@ extern "C" int emu_predict(const uint8_t* plink, int N, int nsm, int Mt, int R, 
         if ((mask4_in[i / 4] >> (i % 4)) & 1) { yv[i] = y[i]; mask4[i / 4] |= (uint8_t)(1u << (i % 4)); }
     std::vector<double> mave(Mt), msig(Mt), xtx(Mt);
     const int32_t nn = nonas;
-    emu_launch(EmuDim3(Mt), EmuDim3(128), [&] { stats_kernel(bed.data(), Mt, L, mask4.data(), off.data(), midx.data(), &nn, 1, mave.data(), msig.data(), xtx.data()); });
+    std::vector<uint32_t> na_off, na_idx;
+    emu_na_lists(mask4.data(), L.col_stride, 1, N, na_off, na_idx);
+    emu_launch(EmuDim3(std::min(Mt, 3)), EmuDim3(kStatsThreads), [&] { stats_kernel(bed.data(), Mt, L, mask4.data(), off.data(), midx.data(), &nn, na_off.data(), na_idx.data(), 1, mave.data(), msig.data(), xtx.data()); });
     std::vector<int32_t> cols(Mt);
     emu_launch(EmuDim3((Mt + 255) / 256), EmuDim3(256), [&] { iota_kernel(cols.data(), Mt); });
 
