@@ -401,6 +401,56 @@ __host__ __device__ inline int step_area_bytes(int V, int T, int rows_per_pass, 
     return (int)(want < 180224 ? want : 180224);
 }
 
+// Exclusive prefix of the segment counts of all pending lists of trait tt (GPU-major = global virtual-rank order) into
+// segpre[0 .. nseg], segpre[nseg] = number of published items.  Whole CTA; ends with a barrier.
+template <int NT>
+__device__ __forceinline__ void seg_prefix(const StepParams& p, int tt, int S, int nseg, int* segpre, int* wcnt) {
+    const int tid = threadIdx.x;
+    constexpr int kPer = 8;                             // segments per thread: nseg <= 8 * NT
+    const int per = (nseg + NT - 1) / NT;
+    int loc[kPer], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const int i = tid * per + j;
+        loc[j] = 0;
+        if (j < per && i < nseg) {                      // .cg: peers rewrite these buffers between launches
+            const int g = i / S, sg = i - g * S;
+            loc[j] = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles));
+        }
+        sum += loc[j];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((tid & 31) >= o) incl += y;
+    }
+    __syncthreads();                                    // wcnt / segpre of the previous trait are consumed
+    if ((tid & 31) == 31) wcnt[tid >> 5] = incl;
+    __syncthreads();
+    int base = incl - sum;
+    for (int w = 0; w < (tid >> 5); w++) base += wcnt[w];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+        const int i = tid * per + j;
+        if (j < per && i < nseg) { segpre[i] = base; base += loc[j]; }
+    }
+    if (tid == NT - 1) segpre[nseg] = base;             // the last thread's running total is the grand total
+    __syncthreads();
+}
+
+// item x (global virtual-rank order) of the pending lists of trait tt: its list (publishing GPU) and its address
+__device__ __forceinline__ const double* seg_item(const StepParams& p, int tt, int S, int nseg, const int* segpre, int x, int* gpu) {
+    int lo = 0, hi = nseg;                              // the segment holding item x: segpre[lo] <= x < segpre[lo + 1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (segpre[mid] <= x) lo = mid; else hi = mid;
+    }
+    const int g = lo / S, sg = lo - g * S;
+    *gpu = g;
+    return p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles + 2 + 3 * (size_t)(x - segpre[lo]);
+}
+
 // ---- (a) pending updates: Phenotype::update_epsilon (phenotype.cpp:326-329,375-390) for every published marker
 // of the previous step, in virtual-rank order, restricted to this CTA's rows.  All NT threads of the CTA work.
 template <int T, int NT>
@@ -435,39 +485,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
         const int tt = p.t0 + t;
         double* eps_t = p.eps + (int64_t)tt * p.npad;
         const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride;
-        {
-            constexpr int kPer = 8;                     // segments per thread: nseg <= 8 * NT
-            const int per = (nseg + NT - 1) / NT;
-            int loc[kPer], sum = 0;
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                const int i = tid * per + j;
-                loc[j] = 0;
-                if (j < per && i < nseg) {              // .cg: peers rewrite these buffers between launches
-                    const int g = i / S, sg = i - g * S;
-                    loc[j] = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles));
-                }
-                sum += loc[j];
-            }
-            int incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((tid & 31) >= o) incl += y;
-            }
-            __syncthreads();                            // wcnt / segpre of the previous trait are consumed
-            if ((tid & 31) == 31) wcnt[tid >> 5] = incl;
-            __syncthreads();
-            int base = incl - sum;
-            for (int w = 0; w < (tid >> 5); w++) base += wcnt[w];
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                const int i = tid * per + j;
-                if (j < per && i < nseg) { segpre[i] = base; base += loc[j]; }
-            }
-            if (tid == NT - 1) segpre[nseg] = base;     // the last thread's running total is the grand total
-            __syncthreads();
-        }
+        seg_prefix<NT>(p, tt, S, nseg, segpre, wcnt);
         const int total = segpre[nseg];
         for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
             double e[2][4], e0[2][4];
@@ -492,14 +510,8 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                     const int n = min(cap, total - r0);
                     __syncthreads();
                     if (tid < n) {
-                        const int x = r0 + tid;
-                        int lo = 0, hi = nseg;               // the segment holding item x: segpre[lo] <= x < segpre[lo + 1]
-                        while (hi - lo > 1) {
-                            const int mid = (lo + hi) >> 1;
-                            if (segpre[mid] <= x) lo = mid; else hi = mid;
-                        }
-                        const int g = lo / S, sg = lo - g * S;
-                        const double* ip = p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles + 2 + 3 * (size_t)(x - segpre[lo]);
+                        int g;
+                        const double* ip = seg_item(p, tt, S, nseg, segpre, r0 + tid, &g);
                         PubItem it;                          // .cg loads: peers rewrite this buffer between launches
                         it.lam = __ldcg(ip); it.mave = __ldcg(ip + 1);
                         const int2 cv = __ldcg(reinterpret_cast<const int2*>(ip + 2));
@@ -637,6 +649,195 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             }
         }
     }
+}
+
+// ---- (a') the same updates with several GPUs in the list exchange, ROW-SHARDED: every GPU would otherwise apply every GPU's
+// updates to every row -- update work and NVLink column traffic that grow with the number of GPUs instead of shrinking.  Here
+// GPU `rs_rank` applies ALL lists (global virtual-rank order) to the local rows rs_rank, rs_rank + rs_world, ... of the CTA
+// only, stores the updated rows into the residual array of EVERY GPU over NVLink, and the same-index CTAs of the GPUs tell
+// each other through flags that their rows have landed (every row is computed by exactly one GPU: all GPUs hold identical
+// residuals by construction).  The few quads are spread over the CTA by splitting the staged entries of a round into
+// entry groups whose partial increments are summed in a fixed order; missing genotypes (stored as dosage 0) are taken out
+// again afterwards, entry by entry.
+template <int T, int NT>
+__device__ void apply_pending_sharded(const StepParams& p, const PassRows& pr, PubStage* stage, PubInfo* info, uint32_t* lut,
+                                      int* wcnt, uint8_t* bytes, int bytes_cap) {
+    const int tid = threadIdx.x, cta = blockIdx.x, nsm = gridDim.x;
+    const int G = p.rs_world, me = p.rs_rank;
+    const int nr = pr.total;
+    const int nsub = nr > me ? (nr - me + G - 1) / G : 0;       // local rows me, me + G, ... of this CTA
+    const int nq = nsub * kRowBytes;
+    for (int e = tid; e < kTabEntries; e += NT) {
+        const uint32_t f = tri_to_fields(e);
+        lut[e] = ((f & 3u) << 3) | (((f >> 2) & 3u) << 11) | (((f >> 4) & 3u) << 19) | (((f >> 6) & 3u) << 27);
+    }
+    const uint32_t lut_u32 = smem_u32(lut);
+    int EG = 1;                                                  // entry groups: 64 quads -> 8, 128 -> 4, up to 256 -> 2, more -> 1
+    while (EG < 8 && nq * (EG * 2) <= NT) EG *= 2;
+    const int W = NT / EG;                                       // threads per entry group == quads per chunk
+    double* ptab = reinterpret_cast<double*>(bytes);             // pair tables (see apply_pending)
+    const uint32_t ptab_u32 = smem_u32(ptab);
+    bytes += kPubCap * 64; bytes_cap -= kPubCap * 64;
+    double* redbuf = reinterpret_cast<double*>(bytes);           // [EG - 1][W][4] increments of the entry groups 1 ..
+    bytes += (EG - 1) * W * 32; bytes_cap -= (EG - 1) * W * 32;
+    double* corr = reinterpret_cast<double*>(bytes);             // [W][4] what the missing genotypes take out again
+    bytes += W * 32; bytes_cap -= W * 32;
+    const int S = publist_segments(p.pV), nseg = p.pG * S;
+    bytes_cap -= ((nseg + 1) * 4 + 15) & ~15;
+    int* segpre = reinterpret_cast<int*>(bytes + bytes_cap);
+    const int cap = max(8, min(kPubCap, bytes_cap / W) & ~7);
+    const int tq = tid % W, eg = tid / W;
+    for (int t = 0; t < T && nq > 0; t++) {
+        const int tt = p.t0 + t;
+        const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride;
+        seg_prefix<NT>(p, tt, S, nseg, segpre, wcnt);
+        const int total = segpre[nseg];
+        if (total == 0) continue;                                // CTA-uniform
+        for (int q0 = 0; q0 < nq; q0 += W) {
+            const int q = q0 + tq;
+            const bool have = q < nq;
+            const int gq = have ? global_row(pr, me + (q >> 6) * G) * kRowBytes + (q & 63) : 0;   // global quad = byte of the column
+            const uint32_t na = have ? mask_t[gq] : 0u;
+            const uint32_t nmask = ((na & 1u) ? 0u : 0x78u) | ((na & 2u) ? 0u : 0x7800u) | ((na & 4u) ? 0u : 0x780000u) | ((na & 8u) ? 0u : 0x78000000u);
+            const int rows_here = min(W >> 6, nsub - (q0 >> 6));
+            double d[4] = {0.0, 0.0, 0.0, 0.0};
+            if (eg == 0) { corr[tq * 4] = 0.0; corr[tq * 4 + 1] = 0.0; corr[tq * 4 + 2] = 0.0; corr[tq * 4 + 3] = 0.0; }
+            for (int r0 = 0; r0 < total; r0 += cap) {
+                const int n = min(cap, total - r0);
+                __syncthreads();
+                uint32_t mo0 = 0, mo1 = 0;
+                if (tid < n) {
+                    int g;
+                    const double* ip = seg_item(p, tt, S, nseg, segpre, r0 + tid, &g);
+                    PubItem it;                                  // .cg loads: peers rewrite this buffer between launches
+                    it.lam = __ldcg(ip); it.mave = __ldcg(ip + 1);
+                    const int2 cv = __ldcg(reinterpret_cast<const int2*>(ip + 2));
+                    it.col = cv.x; it.v = cv.y;
+                    PubStage& sg = stage[tid];
+                    const double mdb = -it.mave;                 // reference arithmetic: (mdb*b + a) * bs_, phenotype.cpp:328-329,388
+                    sg.v[0] = (mdb * 1.0 + 0.0) * it.lam;
+                    sg.v[1] = (mdb * 1.0 + 1.0) * it.lam;
+                    sg.v[2] = (mdb * 1.0 + 2.0) * it.lam;
+                    sg.v[3] = 0.0;
+                    info[tid].col = it.col;
+                    info[tid].nmiss_g = (uint32_t)g;             // the missing count is filled in below
+                    const uint32_t* mo = p.pmiss_off[g];         // bounds of the missing list: in flight with the column bytes
+                    mo0 = mo[it.col]; mo1 = mo[it.col + 1];
+                } else if (tid < ((n + 7) & ~7)) {               // pad the last group of 8 with no-op entries
+                    stage[tid].v[0] = stage[tid].v[1] = stage[tid].v[2] = stage[tid].v[3] = 0.0;
+                    info[tid].col = 0; info[tid].nmiss_g = 0u;
+                }
+                __syncthreads();
+                {   // the entries' bytes of this chunk's rows: all loads in flight at once (remote shards' columns over NVLink)
+                    const int npiece = n * rows_here * 4;        // 16-byte pieces: entry x chunk row x 4
+                    for (int i0 = tid; i0 < npiece; i0 += 4 * NT) {
+                        uint4 v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int i = i0 + j * NT;
+                            if (i < npiece) {
+                                const int en = i / (rows_here * 4), rem = i - en * (rows_here * 4), k = rem >> 2, part = rem & 3;
+                                const uint8_t* src = p.pbed[info[en].nmiss_g & 15u] + (int64_t)info[en].col * p.col_stride +
+                                                     (int64_t)global_row(pr, me + ((q0 >> 6) + k) * G) * kRowBytes + part * 16;
+                                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[j].x), "=r"(v[j].y), "=r"(v[j].z), "=r"(v[j].w) : "l"(src));
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int i = i0 + j * NT;
+                            if (i < npiece) {
+                                const int en = i / (rows_here * 4), rem = i - en * (rows_here * 4);
+                                *reinterpret_cast<uint4*>(bytes + (size_t)en * W + (size_t)rem * 16) = v[j];
+                            }
+                        }
+                    }
+                    for (int i = tid; i < ((n + 7) & ~7) * 8; i += NT) {     // 16 sums per pair of entries (padded entries are all-zero)
+                        const int pp = i >> 4, d1 = i & 3, d2 = (i >> 2) & 3;
+                        ptab[i] = stage[2 * pp].v[d1] + stage[2 * pp + 1].v[d2];
+                    }
+                    if (tid < n) info[tid].nmiss_g |= (mo1 - mo0) << 4;
+                }
+                __syncthreads();
+                // this entry group's share of the round, in groups of 8 entries (4 pair tables each)
+                const int ng8 = (n + 7) >> 3, per = (ng8 + EG - 1) / EG;
+                for (int g8 = eg * per; g8 < min(ng8, (eg + 1) * per); g8++) {
+                    const int g0 = g8 * 8;
+                    uint32_t by[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) by[j] = (have && g0 + j < n) ? bytes[(size_t)(g0 + j) * W + tq] : 0u;
+                    const uint32_t pbase = ptab_u32 + (uint32_t)g0 * 64u;
+#define GMRM_SHARD_PAIR(J)                                                                                         \
+    {                                                                                                             \
+        uint32_t o1, o2;                                                                                          \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o1) : "r"(lut_u32 + by[2 * J] * 4u));                       \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o2) : "r"(lut_u32 + by[2 * J + 1] * 4u));                   \
+        const uint32_t off = (o2 * 4u + o1) | nmask;                                                              \
+        d[0] += lds_f64_imm<J * 128>(byte_into<0>(off, pbase));                                                   \
+        d[1] += lds_f64_imm<J * 128>(byte_into<1>(off, pbase));                                                   \
+        d[2] += lds_f64_imm<J * 128>(byte_into<2>(off, pbase));                                                   \
+        d[3] += lds_f64_imm<J * 128>(byte_into<3>(off, pbase));                                                   \
+    }
+                    GMRM_SHARD_PAIR(0) GMRM_SHARD_PAIR(1) GMRM_SHARD_PAIR(2) GMRM_SHARD_PAIR(3)
+#undef GMRM_SHARD_PAIR
+                }
+                // missing genotypes were stored as dosage 0 and have just received v[0]: take it out again, entry by entry
+                // (the individuals of one entry are distinct; a barrier orders the entries)
+                for (int en = 0; en < n; en++) {
+                    const uint32_t nmiss = info[en].nmiss_g >> 4;
+                    if (nmiss == 0) continue;                    // CTA-uniform
+                    const uint32_t pgpu = info[en].nmiss_g & 15u, mo = p.pmiss_off[pgpu][info[en].col];
+                    const double v0 = stage[en].v[0];
+                    for (uint32_t i = tid; i < nmiss; i += NT) {
+                        const int ind = (int)p.pmiss_idx[pgpu][mo + i], grow = ind >> 8;
+                        for (int qp = 0; qp < pr.npass; qp++)
+                            if (grow >= pr.start[qp] && grow < pr.start[qp] + pr.count[qp]) {
+                                const int lr = pr.base[qp] + grow - pr.start[qp];
+                                if (lr % G == me) {
+                                    const int k = (lr - me) / G - (q0 >> 6);
+                                    if (k >= 0 && k < rows_here) corr[(k * kRowBytes + ((ind & 255) >> 2)) * 4 + (ind & 3)] -= v0;
+                                }
+                            }
+                    }
+                    __syncthreads();
+                }
+            }
+            // increments of the entry groups, in order, then the missing-genotype corrections; the rows go to every GPU
+            if (eg > 0) { double* r = redbuf + ((size_t)(eg - 1) * W + tq) * 4; r[0] = d[0]; r[1] = d[1]; r[2] = d[2]; r[3] = d[3]; }
+            __syncthreads();
+            if (eg == 0 && have) {
+                for (int g = 1; g < EG; g++) {
+                    const double* r = redbuf + ((size_t)(g - 1) * W + tq) * 4;
+                    d[0] += r[0]; d[1] += r[1]; d[2] += r[2]; d[3] += r[3];
+                }
+                const int64_t o = (int64_t)tt * p.npad + 4 * (int64_t)gq;
+                const double2 ea = *reinterpret_cast<const double2*>(p.eps + o), eb = *reinterpret_cast<const double2*>(p.eps + o + 2);
+                double2 na_, nb_;                                // unobserved individuals took the zero entry: no correction either
+                na_.x = ea.x + (d[0] + ((na & 1u) ? corr[tq * 4] : 0.0));
+                na_.y = ea.y + (d[1] + ((na & 2u) ? corr[tq * 4 + 1] : 0.0));
+                nb_.x = eb.x + (d[2] + ((na & 4u) ? corr[tq * 4 + 2] : 0.0));
+                nb_.y = eb.y + (d[3] + ((na & 8u) ? corr[tq * 4 + 3] : 0.0));
+                for (int g = 0; g < G; g++) {
+                    *reinterpret_cast<double2*>(p.peps[g] + o) = na_;
+                    *reinterpret_cast<double2*>(p.peps[g] + o + 2) = nb_;
+                }
+            }
+            __syncthreads();                                     // corr / redbuf are reused by the next chunk
+        }
+    }
+    // this CTA's rows are on their way to every GPU: fence, tell the same-index CTAs, wait for theirs
+    __syncthreads();
+    if (tid == 0) __threadfence_system();
+    __syncthreads();
+    if (tid < G) {
+        *reinterpret_cast<volatile unsigned long long*>(p.rflag_peer[tid] + (size_t)me * nsm + cta) = p.wait_seq;
+        const volatile unsigned long long* f = p.rflag_mine + (size_t)tid * nsm + cta;
+        for (uint32_t spins = 0; *f < p.wait_seq; ++spins) {
+            __nanosleep(100);
+            if (spins > (1u << 28)) __trap();                    // a lost peer must surface as an error, not as a hung GPU
+        }
+    }
+    __threadfence();
+    __syncthreads();
 }
 
 // ---- (b) tables of rows [row0, row0 + nrp) for T traits, by the NC consumer threads; es[t] accumulates this
@@ -917,6 +1118,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         }
         __syncthreads();
     }
+    if (p.rs_world > 1 && p.pG * p.pV > 0) apply_pending_sharded<T, NT>(p, pr, stage, info, lut, wcnt, tabs, area);
+    else
     if (p.pG * p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     GMRM_TICK()                                           // [8] prologue + update phase

@@ -68,6 +68,14 @@ struct StepParams {
     const uint8_t* pbed[kMaxGpus];
     const uint32_t* pmiss_off[kMaxGpus];
     const uint32_t* pmiss_idx[kMaxGpus];
+    // Row-sharded application of the pending lists (rs_world > 1: list exchange over several GPUs).  Every GPU holds the same
+    // residuals; instead of every GPU applying every update to every row, GPU g applies ALL lists to 1/rs_world of each CTA's
+    // rows (local row lr with lr % rs_world == rs_rank) and stores the updated rows into every GPU's residual array over
+    // NVLink; same-index CTAs of the GPUs then tell each other through flags that their rows have landed.
+    int32_t rs_world, rs_rank;
+    double* peps[kMaxGpus];              // residual arrays of all GPUs (peer memory; [rs_rank] is this GPU's)
+    unsigned long long* rflag_peer[kMaxGpus];   // GPU g's row-flag array [rs_world][nsm]: this GPU writes entry [rs_rank][cta]
+    const unsigned long long* rflag_mine;       // this GPU's row-flag array: entry [g][cta] = sequence number GPU g's CTA `cta` has reached
     const uint8_t* mask4;    // [Ttot][col_stride] NA nibble of every quad (bit k: individual 4q+k observed)
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     const double* merge_tot; // [Ttot][npad] or nullptr: all-reduced deltas of the last exchange, still to be merged: every CTA first

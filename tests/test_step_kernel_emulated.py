@@ -53,14 +53,22 @@ extern "C" int emu_step(const uint8_t* bed, int N, int nsm, const int32_t* cols,
 
 // update-only launch with the lists of TWO GPUs (world_size 2, list exchange): list g holds columns of shard g, whose
 // bytes and missing lists are read from "GPU g's" buffers (peer memory on hardware); this GPU is shard 0.
+// rs_world > 0: the row-sharded form -- the launch is repeated for every "GPU" rs_rank = 0 .. rs_world-1 in turn on the SAME
+// residual array (each updates only its rows of every CTA and "stores them to every GPU"); the row flags are preset, nothing waits
 extern "C" int emu_update_two_lists(const uint8_t* bed0, const uint8_t* bed1, int N, int nsm, double* eps, const uint8_t* mask4, int T,
                                     int tc, int rpp, int npass, const double* plists /* [2][T][ld] */, int pV,
-                                    const uint32_t* moff0, const uint32_t* midx0, const uint32_t* moff1, const uint32_t* midx1) {
+                                    const uint32_t* moff0, const uint32_t* midx0, const uint32_t* moff1, const uint32_t* midx1, int rs_world) {
     using namespace gmrm;
     const Layout L = make_layout(N, nsm);
     int32_t err = 0;
+    std::vector<unsigned long long> flags_set((size_t)kMaxGpus * nsm, 1000ull), flags_out((size_t)kMaxGpus * nsm, 0ull);
+    for (int rs_rank = 0; rs_rank < std::max(rs_world, 1); rs_rank++)
     for (int t0 = 0; t0 < T; t0 += tc) {
         StepParams q{};
+        if (rs_world > 0) {
+            q.rs_world = rs_world; q.rs_rank = rs_rank; q.wait_seq = 7; q.rflag_mine = flags_set.data();
+            for (int g = 0; g < rs_world; g++) { q.peps[g] = eps; q.rflag_peer[g] = flags_out.data(); }
+        }
         q.bed = bed0; q.col_stride = L.col_stride; q.nrows = L.nrows; q.V = 0; q.eps = eps; q.npad = L.npad;
         q.Ttot = T; q.t0 = t0; q.rows_per_pass = rpp; q.npass = npass; q.mask4 = mask4; q.pV = pV; q.err = &err; q.pf = 1;
         q.pG = 2; q.plist = plists;
@@ -197,7 +205,7 @@ def build_list(pV, entries):
 def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
     """world_size 2, list exchange (bayes.cpp:495-553 replaced by published lists): the update phase applies GPU 0's list, then
     GPU 1's -- global virtual-rank order -- reading every published column from the shard that owns it."""
-    N, M, T, nsm, pV = 1290, 48, 2, 2, 21
+    N, M, T, nsm, pV = 2890, 48, 2, 2, 21
     d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=0.02, missing_rate=0.02, seed=12)
     pp = d["paths"]
     inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
@@ -227,12 +235,16 @@ def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
                 oracle.update_eps(want[t], inp["mask4"][t], inp["bed"][j], db, mave[j], msig[j])
             plists[g, t] = build_list(pV, entries)
     plan = api.step_plan(N, nsm, 0, T, want_ranges=False)
-    rc = emu.emu_update_two_lists(p(shards[0][0]), p(shards[1][0]), N, nsm, p(eps), p(mask4), T, plan["traits_per_launch"],
-                                  plan["rows_per_pass"], plan["npass"], p(plists), pV, p(shards[0][1]), p(shards[0][2]),
-                                  p(shards[1][1]), p(shards[1][2]))
-    assert rc == 0
-    for t in range(T):
-        np.testing.assert_allclose(eps[t, :N], want[t][:N], rtol=0, atol=1e-13)
+    eps0 = eps.copy()
+    for rs_world in (0, 2, 3, 8):        # every GPU applies everything / the rows of each CTA are shared by 2, 3, 8 GPUs (8: some get none)
+        eps[...] = eps0
+        rc = emu.emu_update_two_lists(p(shards[0][0]), p(shards[1][0]), N, nsm, p(eps), p(mask4), T, plan["traits_per_launch"],
+                                      plan["rows_per_pass"], plan["npass"], p(plists), pV, p(shards[0][1]), p(shards[0][2]),
+                                      p(shards[1][1]), p(shards[1][2]), rs_world)
+        assert rc == 0
+        for t in range(T):
+            np.testing.assert_allclose(eps[t, :N], want[t][:N], rtol=0, atol=1e-13)
+            assert not eps[t, N:].any()
 
 
 @pytest.mark.parametrize("N,nsm,T,V", [(1795, 2, 1, 2100), (777, 3, 2, 1100)])
