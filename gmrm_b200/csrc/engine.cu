@@ -152,6 +152,7 @@ struct gmrm_engine {
     double* peer_eps[kMaxGpus] = {};                 // peers' (and own) residual arrays: the row-sharded update stores its rows there
     unsigned long long* peer_rflags[kMaxGpus] = {};  // peers' (and own) row-flag arrays [world][nsm]
     DevBuf<unsigned long long> rflags;
+    unsigned long long row_seq = 0;                  // launches with a row-sharded update so far (identical on every GPU)
     bool row_shard = true;                           // GMRM_ROWSHARD=0: every GPU applies every update to every row (round-1 behaviour)
     void* ipc_opened[kMaxGpus][7] = {};
     bool list_p2p = true;            // lists are pushed into the peers' buffers by the sampler kernel (GMRM_EXCHANGE=nccl: all-gather)
@@ -624,7 +625,7 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
             if (e->list_p2p) p.xflags = e->xflags.p;
             p.wait_seq = e->pend_seq;
             if (e->row_shard) {                                     // update work and column traffic shared by rows (kernels.cu, a')
-                p.rs_world = e->cfg.world_size; p.rs_rank = e->cfg.world_rank; p.rflag_mine = e->rflags.p;
+                p.rs_world = e->cfg.world_size; p.rs_rank = e->cfg.world_rank; p.rflag_mine = e->rflags.p; p.row_seq = ++e->row_seq;
                 for (int g = 0; g < p.pG; g++) { p.peps[g] = e->peer_eps[g]; p.rflag_peer[g] = e->peer_rflags[g]; }
             }
         } else if (pend.any) {                                  // this GPU's own list

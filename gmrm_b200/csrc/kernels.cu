@@ -820,18 +820,18 @@ __device__ void apply_pending_sharded(const StepParams& p, const PassRows& pr, P
                     *reinterpret_cast<double2*>(p.peps[g] + o) = na_;
                     *reinterpret_cast<double2*>(p.peps[g] + o + 2) = nb_;
                 }
+                __threadfence_system();                          // by every warp that stored rows (one MEMBAR per warp), before the flags below
             }
             __syncthreads();                                     // corr / redbuf are reused by the next chunk
         }
     }
     // this CTA's rows are on their way to every GPU: fence, tell the same-index CTAs, wait for theirs
     __syncthreads();
-    if (tid == 0) __threadfence_system();
-    __syncthreads();
     if (tid < G) {
-        *reinterpret_cast<volatile unsigned long long*>(p.rflag_peer[tid] + (size_t)me * nsm + cta) = p.wait_seq;
+        __threadfence_system();          // by the thread that writes the flag: the CTA's row stores (ordered before it by the barrier) first
+        *reinterpret_cast<volatile unsigned long long*>(p.rflag_peer[tid] + (size_t)me * nsm + cta) = p.row_seq;
         const volatile unsigned long long* f = p.rflag_mine + (size_t)tid * nsm + cta;
-        for (uint32_t spins = 0; *f < p.wait_seq; ++spins) {
+        for (uint32_t spins = 0; *f < p.row_seq; ++spins) {
             __nanosleep(100);
             if (spins > (1u << 28)) __trap();                    // a lost peer must surface as an error, not as a hung GPU
         }
@@ -1362,6 +1362,7 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
             if (live) reinterpret_cast<PubItem*>(seg + 2)[pos] = it;
         }
         if (lane == 0 && n) atomicAdd(&s_npub, n);
+        if (push) __threadfence_system();                    // by the warp that stored the segment (one MEMBAR per trait and CTA)
     }
     __syncthreads();                                         // the CTA's segment stores are ordered before thread 0's fence below
     if (tid == 0 && s_npub) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), (unsigned long long)s_npub);

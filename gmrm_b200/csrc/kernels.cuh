@@ -73,6 +73,7 @@ struct StepParams {
     // rows (local row lr with lr % rs_world == rs_rank) and stores the updated rows into every GPU's residual array over
     // NVLink; same-index CTAs of the GPUs then tell each other through flags that their rows have landed.
     int32_t rs_world, rs_rank;
+    unsigned long long row_seq;          // sequence number of this launch among the row-sharded ones (same on every GPU)
     double* peps[kMaxGpus];              // residual arrays of all GPUs (peer memory; [rs_rank] is this GPU's)
     unsigned long long* rflag_peer[kMaxGpus];   // GPU g's row-flag array [rs_world][nsm]: this GPU writes entry [rs_rank][cta]
     const unsigned long long* rflag_mine;       // this GPU's row-flag array: entry [g][cta] = sequence number GPU g's CTA `cta` has reached

@@ -66,7 +66,7 @@ extern "C" int emu_update_two_lists(const uint8_t* bed0, const uint8_t* bed1, in
     for (int t0 = 0; t0 < T; t0 += tc) {
         StepParams q{};
         if (rs_world > 0) {
-            q.rs_world = rs_world; q.rs_rank = rs_rank; q.wait_seq = 7; q.rflag_mine = flags_set.data();
+            q.rs_world = rs_world; q.rs_rank = rs_rank; q.row_seq = 7; q.rflag_mine = flags_set.data();
             for (int g = 0; g < rs_world; g++) { q.peps[g] = eps; q.rflag_peer[g] = flags_out.data(); }
         }
         q.bed = bed0; q.col_stride = L.col_stride; q.nrows = L.nrows; q.V = 0; q.eps = eps; q.npad = L.npad;
@@ -202,10 +202,11 @@ def build_list(pV, entries):
     return out
 
 
-def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path):
+@pytest.mark.parametrize("nsm", [2, 7])
+def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path, nsm):
     """world_size 2, list exchange (bayes.cpp:495-553 replaced by published lists): the update phase applies GPU 0's list, then
     GPU 1's -- global virtual-rank order -- reading every published column from the shard that owns it."""
-    N, M, T, nsm, pV = 2890, 48, 2, 2, 21
+    N, M, T, pV = 2890, 48, 2, 21                              # 12 rows: 6 per CTA, or 1-2 (nsm = 7)
     d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=0.02, missing_rate=0.02, seed=12)
     pp = d["paths"]
     inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
