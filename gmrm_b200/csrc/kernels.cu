@@ -396,9 +396,10 @@ __device__ __forceinline__ int global_row(const PassRows& pr, int local_row) {
 // bytes of the table area; an update-only launch (V == 0) sizes it for staging kPubCap published columns
 __host__ __device__ inline int step_area_bytes(int V, int T, int rows_per_pass, int npass) {
     if (V > 0) return rows_per_pass * T * kSlotBytes;
-    // column bytes of kPubCap entries + their pair tables + the prefix of the lists' segment counts
-    const long long want = (long long)kPubCap * npass * rows_per_pass * kRowBytes + kPubCap * 64 + 8192;
-    return (int)(want < 180224 ? want : 180224);
+    // update-only launch: room for the staged column bytes, the pair tables, the prefix of the segment counts and, in the
+    // row-sharded form, the entry groups' increments -- every launch asks for the full 227 KB anyway, so take a fixed 176 KB
+    (void)npass; (void)rows_per_pass;
+    return 180224;
 }
 
 // Exclusive prefix of the segment counts of all pending lists of trait tt (GPU-major = global virtual-rank order) into

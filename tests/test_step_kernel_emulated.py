@@ -202,7 +202,7 @@ def build_list(pV, entries):
     return out
 
 
-@pytest.mark.parametrize("nsm", [2, 7])
+@pytest.mark.parametrize("nsm", [2, 7, 40])
 def test_emulated_update_with_the_lists_of_two_gpus(emu, oracle, tmp_path, nsm):
     """world_size 2, list exchange (bayes.cpp:495-553 replaced by published lists): the update phase applies GPU 0's list, then
     GPU 1's -- global virtual-rank order -- reading every published column from the shard that owns it."""
