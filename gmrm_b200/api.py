@@ -315,12 +315,12 @@ class Engine:
         _check(lib().gmrm_set_timing_detail(self._h, int(level)))
 
     def export_buffers(self) -> bytes:
-        buf = (C.c_uint8 * 448)()
+        buf = (C.c_uint8 * 384)()
         _check(lib().gmrm_comm_export_buffers(self._h, buf))
         return bytes(buf)
 
     def import_buffers(self, rank: int, handles: bytes):
-        buf = (C.c_uint8 * 448).from_buffer_copy(handles)
+        buf = (C.c_uint8 * 384).from_buffer_copy(handles)
         _check(lib().gmrm_comm_import_buffers(self._h, int(rank), buf))
 
     def exchange_buffers(self, all_gather_object):

@@ -148,21 +148,18 @@ struct gmrm_engine {
     const uint32_t* peer_moff[kMaxGpus] = {};
     const uint32_t* peer_midx[kMaxGpus] = {};
     double* peer_plist[kMaxGpus] = {};               // peers' (and own) list buffers [2][world][T][ld]
-    unsigned long long* peer_xflags[kMaxGpus] = {};  // peers' (and own) flag arrays [world]
     double* peer_eps[kMaxGpus] = {};                 // peers' (and own) residual arrays: the row-sharded update stores its rows there
     unsigned long long* peer_rflags[kMaxGpus] = {};  // peers' (and own) row-flag arrays [world][nsm]
     DevBuf<unsigned long long> rflags;
     unsigned long long row_seq = 0;                  // launches with a row-sharded update so far (identical on every GPU)
     bool row_shard = true;                           // GMRM_ROWSHARD=0: every GPU applies every update to every row (round-1 behaviour)
-    void* ipc_opened[kMaxGpus][7] = {};
+    void* ipc_opened[kMaxGpus][6] = {};
     bool list_p2p = true;            // lists are pushed into the peers' buffers by the sampler kernel (GMRM_EXCHANGE=nccl: all-gather)
     bool merge_pending = false;      // delta exchange: the all-reduced deltas wait to be merged by the next step kernel (fused merge)
     unsigned long long xseq = 0;     // exchange sequence number: one per sampled step, identical on all GPUs
     unsigned long long pend_seq = 0; // sequence number of the step whose lists are pending
-    DevBuf<unsigned long long> xflags;
     int peers_set = 0;
     DevBuf<double> plist;            // [world or 1][T][publist_doubles(Vl)] compacted published lists; the sampler writes this GPU's block
-    DevBuf<unsigned int> ticket;
     int step_tc = 1, step_rpp = 1;   // traits per step launch, rows per pass (step_plan)
     bool force_flush = false;        // GMRM_FORCE_FLUSH=1: update-only launch after every step (timing aid)
     int step_pf = 1;                 // GMRM_STEP_PF=0 turns the L2 prefetch of the streaming loads off
@@ -295,14 +292,14 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
     if (const char* v = getenv("GMRM_EXCHANGE")) e->list_p2p = strcmp(v, "nccl") != 0;
     A(e->plist.alloc((size_t)(e->list_exchange ? 2 * c->world_size : 1) * T * publist_doubles(e->Vl)));   // 2: parity of the exchange sequence
-    A(e->ticket.alloc(1)); A(e->xflags.alloc(kMaxGpus)); A(e->rflags.alloc((size_t)kMaxGpus * L.nsm));
+    A(e->rflags.alloc((size_t)kMaxGpus * L.nsm));
     if (const char* v = getenv("GMRM_ROWSHARD")) e->row_shard = atoi(v) != 0;
     if (rc != 0) { delete e; return rc; }
     // everything starts zeroed: genotype tiles (dosage 0), residuals, chain state, missing lists
     for (auto* b : {&e->eps, &e->mave, &e->msig, &e->betas, &e->spart, &e->bsq, &e->esq, &e->sigmag, &e->sigmae, &e->pi, &e->mu,
                     &e->mu_old, &e->partial, &e->delta, &e->delta_tot})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
-    if (e->plist.zero(e->stream) != 0 || e->ticket.zero(e->stream) != 0 || e->xflags.zero(e->stream) != 0 || e->rflags.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->plist.zero(e->stream) != 0 || e->rflags.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
@@ -622,14 +619,13 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         if (pend.any && e->list_exchange && !pend.own_only) {   // the lists of all GPUs (after the all-gather)
             p.pG = e->cfg.world_size; p.plist = lists_of(e, e->pend_seq);
             for (int g = 0; g < p.pG; g++) { p.pbed[g] = e->peer_bed[g]; p.pmiss_off[g] = e->peer_moff[g]; p.pmiss_idx[g] = e->peer_midx[g]; }
-            if (e->list_p2p) p.xflags = e->xflags.p;
             p.wait_seq = e->pend_seq;
             if (e->row_shard) {                                     // update work and column traffic shared by rows (kernels.cu, a')
                 p.rs_world = e->cfg.world_size; p.rs_rank = e->cfg.world_rank; p.rflag_mine = e->rflags.p; p.row_seq = ++e->row_seq;
                 for (int g = 0; g < p.pG; g++) { p.peps[g] = e->peer_eps[g]; p.rflag_peer[g] = e->peer_rflags[g]; }
             }
         } else if (pend.any) {                                  // this GPU's own list
-            p.pG = 1; p.plist = own_list(e, e->pend_seq);
+            p.pG = 1; p.plist = own_list(e, e->pend_seq); p.wait_seq = e->pend_seq;
             p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
         }
         p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
@@ -653,7 +649,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
-    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e, e->xseq); p.ticket = e->ticket.p; p.err = e->err.p; p.npublished = e->npub.p;
+    p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e, e->xseq); p.seq = e->xseq; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }
 
@@ -734,10 +730,14 @@ int gmrm_apply_update(gmrm_engine* e, int32_t trait, int32_t local_id, double db
     // a one-item published list for `trait`, empty lists for the others (Phenotype::update_epsilon's dbeta[3], phenotype.cpp:328)
     const size_t ld = publist_doubles(e->Vl);
     std::vector<double> lists((size_t)T * ld, 0.0);
-    *reinterpret_cast<int32_t*>(&lists[(size_t)trait * ld]) = 1;
+    e->pend_seq = e->xseq;
+    for (int t = 0; t < T; t++)                                  // every segment header carries the sequence number the kernel waits for
+        for (int sg = 0; sg < publist_segments(e->Vl); sg++) {
+            const unsigned long long h = seg_header(t == trait && sg == 0 ? 1 : 0, e->pend_seq);
+            memcpy(&lists[(size_t)t * ld + (size_t)sg * kSegDoubles], &h, 8);
+        }
     PubItem it{dbeta * sg, av, local_id, 0};
     memcpy(&lists[(size_t)trait * ld + 2], &it, sizeof it);
-    e->pend_seq = e->xseq;
     CU(cudaMemcpyAsync(own_list(e, e->pend_seq), lists.data(), lists.size() * 8, cudaMemcpyHostToDevice, e->stream));
     Pending one; one.any = true; one.own_only = true;
     int rc = launch_step_all(e, nullptr, 0, one, nullptr, nullptr); if (rc) return rc;
@@ -1020,10 +1020,8 @@ int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) 
         sp.it = it; sp.step = st; sp.rep_u = d_u; sp.rep_z = d_z; sp.pdl = e->pdl;
         if (e->list_exchange && e->list_p2p) {               // the sampler pushes the list into every peer's buffer and raises our flag there
             sp.world = c.world_size; sp.rank = c.world_rank; sp.seq = e->xseq;
-            for (int g = 0; g < c.world_size; g++) {
+            for (int g = 0; g < c.world_size; g++)
                 sp.peer_list[g] = e->peer_plist[g] + ((size_t)(e->xseq & 1) * c.world_size + c.world_rank) * list_block(e);
-                sp.peer_flag[g] = e->peer_xflags[g] + c.world_rank;
-            }
         }
         launch_sample(sp, s);
         if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
@@ -1301,7 +1299,7 @@ void gmrm_host_free(void* p) {
 // Buffers the other GPUs read in the list exchange: genotypes, missing-list offsets and indices.  Call after
 // gmrm_finalize_bed.  Across processes they travel as CUDA IPC handles (3 x 64 bytes); inside one process as plain
 // pointers (+ peer access).
-int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[448]) {
+int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[384]) {
     if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     CU(cudaSetDevice(e->cfg.device));
@@ -1311,31 +1309,30 @@ int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[448]) {
     CU(cudaIpcGetMemHandle(&h, e->miss_off.p)); memcpy(handles + 64, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->miss_idx.p)); memcpy(handles + 128, &h, 64);
     CU(cudaIpcGetMemHandle(&h, e->plist.p)); memcpy(handles + 192, &h, 64);
-    CU(cudaIpcGetMemHandle(&h, e->xflags.p)); memcpy(handles + 256, &h, 64);
-    CU(cudaIpcGetMemHandle(&h, e->eps.p)); memcpy(handles + 320, &h, 64);
-    CU(cudaIpcGetMemHandle(&h, e->rflags.p)); memcpy(handles + 384, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->eps.p)); memcpy(handles + 256, &h, 64);
+    CU(cudaIpcGetMemHandle(&h, e->rflags.p)); memcpy(handles + 320, &h, 64);
     e->buffers_exported = true;
     return GMRM_OK;
 }
-static int set_peer(gmrm_engine* e, int rank, void* const p[7]) {
+static int set_peer(gmrm_engine* e, int rank, void* const p[6]) {
     if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
     if (!e->peer_bed[rank]) e->peers_set++;
     e->peer_bed[rank] = (const uint8_t*)p[0]; e->peer_moff[rank] = (const uint32_t*)p[1]; e->peer_midx[rank] = (const uint32_t*)p[2];
-    e->peer_plist[rank] = (double*)p[3]; e->peer_xflags[rank] = (unsigned long long*)p[4];
-    e->peer_eps[rank] = (double*)p[5]; e->peer_rflags[rank] = (unsigned long long*)p[6];
+    e->peer_plist[rank] = (double*)p[3];
+    e->peer_eps[rank] = (double*)p[4]; e->peer_rflags[rank] = (unsigned long long*)p[5];
     const int me = e->cfg.world_rank;
     e->peer_bed[me] = e->bed.p; e->peer_moff[me] = e->miss_off.p; e->peer_midx[me] = e->miss_idx.p;
-    e->peer_plist[me] = e->plist.p; e->peer_xflags[me] = e->xflags.p;
+    e->peer_plist[me] = e->plist.p;
     e->peer_eps[me] = e->eps.p; e->peer_rflags[me] = e->rflags.p;
     return GMRM_OK;
 }
-int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[448]) {
+int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[384]) {
     if (!e || !handles) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
     CU(cudaSetDevice(e->cfg.device));
     if (rank < 0 || rank >= e->cfg.world_size || rank == e->cfg.world_rank) return fail(GMRM_EINVAL, "bad peer rank %d", rank);
-    void* p[7];
-    for (int i = 0; i < 7; i++) {
+    void* p[6];
+    for (int i = 0; i < 6; i++) {
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * i, 64);
         CU(cudaIpcOpenMemHandle(&p[i], h, cudaIpcMemLazyEnablePeerAccess));
@@ -1343,15 +1340,15 @@ int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles
     }
     return set_peer(e, rank, p);
 }
-int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[7]) {
+int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[6]) {
     if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
     if (!e->bed_final) return fail(GMRM_EINVAL, "call gmrm_finalize_bed first");
-    ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p; ptrs[3] = e->plist.p; ptrs[4] = e->xflags.p;
-    ptrs[5] = e->eps.p; ptrs[6] = e->rflags.p;
+    ptrs[0] = e->bed.p; ptrs[1] = e->miss_off.p; ptrs[2] = e->miss_idx.p; ptrs[3] = e->plist.p;
+    ptrs[4] = e->eps.p; ptrs[5] = e->rflags.p;
     e->buffers_exported = true;
     return GMRM_OK;
 }
-int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[7]) {
+int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[6]) {
     if (!e || !ptrs) return fail(GMRM_EINVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
     const cudaError_t pe = cudaDeviceEnablePeerAccess(peer_device, 0);

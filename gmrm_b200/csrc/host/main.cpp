@@ -49,7 +49,7 @@ struct Shared {
     std::vector<host::Phen> phens;
     std::vector<int32_t> group_index;
     uint8_t nccl_id[128];
-    void* peer_ptrs[8][7] = {};
+    void* peer_ptrs[8][6] = {};
     int vranks = 0;
     host::Replay replay;                       // --replay-file (empty: production Philox streams)
     // --predict

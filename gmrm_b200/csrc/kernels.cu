@@ -414,9 +414,19 @@ __device__ __forceinline__ void seg_prefix(const StepParams& p, int tt, int S, i
     for (int j = 0; j < kPer; j++) {
         const int i = tid * per + j;
         loc[j] = 0;
-        if (j < per && i < nseg) {                      // .cg: peers rewrite these buffers between launches
+        if (j < per && i < nseg) {                      // wait for the segment: its header carries the expected sequence number
             const int g = i / S, sg = i - g * S;
-            loc[j] = __ldcg(reinterpret_cast<const int32_t*>(p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles));
+            const volatile unsigned long long* h = reinterpret_cast<const volatile unsigned long long*>(
+                p.plist + ((size_t)g * p.Ttot + tt) * publist_doubles(p.pV) + (size_t)sg * kSegDoubles);
+            unsigned long long w = *h;
+            for (uint32_t spins = 0; (w >> 8) != p.wait_seq; ++spins) {
+                __nanosleep(100);
+                // a lost peer must surface as an error, not as a hung GPU; the bound (>= 27 s) has to cover honest skew
+                // between the processes (first-launch module loading, a rank writing output files)
+                if (spins > (1u << 28)) __trap();
+                w = *h;
+            }
+            loc[j] = (int)(w & 0xffu);
         }
         sum += loc[j];
     }
@@ -426,6 +436,7 @@ __device__ __forceinline__ void seg_prefix(const StepParams& p, int tt, int S, i
         const int y = __shfl_up_sync(0xffffffffu, incl, o);
         if ((tid & 31) >= o) incl += y;
     }
+    __threadfence();                                    // the items behind the headers (written before them) are read after this point
     __syncthreads();                                    // wcnt / segpre of the previous trait are consumed
     if ((tid & 31) == 31) wcnt[tid >> 5] = incl;
     __syncthreads();
@@ -1090,19 +1101,6 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     // the genotypes): it may run while the sampler kernel of the previous step is still finishing
     pdl_wait();
     pdl_trigger();                                        // the sampler's CTAs may be scheduled as soon as SMs free up; they wait likewise
-    if (p.xflags != nullptr) {                            // peer-memory exchange: every GPU's list of the previous step has landed
-        if (tid < p.pG) {
-            const volatile unsigned long long* f = p.xflags + tid;
-            for (uint32_t spins = 0; *f < p.wait_seq; ++spins) {
-                __nanosleep(100);
-                // a lost peer must surface as an error, not as a hung GPU; the bound (>= 27 s) has to cover honest skew
-                // between the processes (first-launch module loading, a rank writing output files)
-                if (spins > (1u << 28)) __trap();
-            }
-        }
-        __threadfence();
-        __syncthreads();
-    }
     if (p.merge_tot != nullptr && nr > 0) {               // residual deltas of the last exchange (all-reduced): what the OTHER shards changed
         for (int t = 0; t < T; t++) {
             const int64_t tb = (int64_t)(p.t0 + t) * p.npad;
@@ -1357,31 +1355,20 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
         const size_t off = ((size_t)t * S + blockIdx.x) * kSegDoubles;
         PubItem it;
         if (live) { it.lam = s_lam[t][lane]; it.mave = s_mave[t][lane]; it.col = s_col[lane]; it.v = blockIdx.x * kSegCap + lane; }
-        for (int g = 0; g < (push ? p.world : 1); g++) {     // own list first (g == rank when pushing: peer_list[rank] is the own block)
+        for (int g = 0; g < (push ? p.world : 1); g++) {     // every GPU's copy of this list (own one included)
             double* seg = (push ? p.peer_list[g] : p.plist) + off;
-            if (lane == 0) *reinterpret_cast<int32_t*>(seg) = n;
             if (live) reinterpret_cast<PubItem*>(seg + 2)[pos] = it;
         }
-        if (lane == 0 && n) atomicAdd(&s_npub, n);
-        if (push) __threadfence_system();                    // by the warp that stored the segment (one MEMBAR per trait and CTA)
-    }
-    __syncthreads();                                         // the CTA's segment stores are ordered before thread 0's fence below
-    if (tid == 0 && s_npub) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), (unsigned long long)s_npub);
-    if (!push) return;
-    // ONE system-scope fence per CTA (a fence by every thread -- 2,048 warps per step -- costs ~10 us of sampler time):
-    // barrier + thread 0's fence make this CTA's segments visible to the peers before it takes its ticket
-    __shared__ bool last;
-    if (tid == 0) {
-        __threadfence_system();
-        last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+        if (push) __threadfence_system();                    // one MEMBAR for the warp: the items first ...
+        __syncwarp();
+        if (lane == 0) {                                     // ... the header last: count | sequence
+            for (int g = 0; g < (push ? p.world : 1); g++)
+                *reinterpret_cast<volatile unsigned long long*>((push ? p.peer_list[g] : p.plist) + off) = seg_header(n, p.seq);
+            if (n) atomicAdd(&s_npub, n);
+        }
     }
     __syncthreads();
-    if (!last) return;
-    if (tid < p.world) {                                     // every CTA's segments (ticket order) before the flags
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long*>(p.peer_flag[tid]) = p.seq;
-    }
-    if (tid == 0) *p.ticket = 0u;
+    if (tid == 0 && s_npub) atomicAdd(reinterpret_cast<unsigned long long*>(p.npublished), (unsigned long long)s_npub);
 }
 // [sample-end]
 

@@ -34,14 +34,17 @@ struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3
 };
 // The step's published updates of one GPU and trait: a SEGMENTED list in virtual-rank order.  Every CTA of the sampler
 // kernel samples kSegCap consecutive virtual ranks and writes their published items, compacted and in order, into its own
-// segment -- a 16-byte header (int32 count) followed by up to kSegCap items -- with no dependency on any other CTA (and,
-// across GPUs, straight into the peers' copies of the list).  The consumer (step kernel) turns the segment counts into a
+// segment -- a 16-byte header followed by up to kSegCap items -- with no dependency on any other CTA (and, across GPUs,
+// straight into the peers' copies of the list).  The header's first word is  count | sequence << 8  (the sequence number of
+// the sampled step, written last, after a system-scope fence): the consumer (step kernel) waits until every header carries
+// the sequence number it expects -- that is the whole hand-shake, no flags, no last CTA -- then turns the counts into a
 // prefix and walks the items of all segments of all GPUs in global virtual-rank order.
 struct PubItem { double lam, mave; int32_t col, v; };     // col: column local to the publishing GPU
 constexpr int kSegCap = 16;                                // virtual ranks per sampler CTA == items a segment can hold
 constexpr int kSegDoubles = 2 + 3 * kSegCap;               // header + items, in doubles
 __host__ __device__ constexpr int publist_segments(int V) { return (V + kSegCap - 1) / kSegCap; }
 __host__ __device__ constexpr size_t publist_doubles(int V) { return (size_t)publist_segments(V) * kSegDoubles; }
+__host__ __device__ constexpr unsigned long long seg_header(int count, unsigned long long seq) { return (unsigned long long)count | (seq << 8); }
 
 // One marker-step on one GPU: (a) apply the updates published by the previous step to this CTA's rows of
 // the residuals, (b) build the look-up tables of those rows, (c) stream the step's V columns through them.
@@ -63,8 +66,7 @@ struct StepParams {
     // (peer memory over NVLink when g is not this GPU)
     int32_t pG, pV;                      // lists, virtual ranks behind a list (0 lists: nothing pending)
     const double* plist;                 // [pG][Ttot][publist_doubles(pV)]: publist_segments(pV) segments each
-    const unsigned long long* xflags;    // [pG] or nullptr: wait until every list's flag has reached wait_seq
-    unsigned long long wait_seq;
+    unsigned long long wait_seq;         // sequence number every segment header of the pending lists must carry
     const uint8_t* pbed[kMaxGpus];
     const uint32_t* pmiss_off[kMaxGpus];
     const uint32_t* pmiss_idx[kMaxGpus];
@@ -114,13 +116,10 @@ struct SampleParams {
     int32_t* cass;           // [T][G*K]
     PubEntry* pub;           // unused (kept for the layout of older callers)
     double* plist;           // [T][publist_doubles(V)] this GPU's list: CTA c writes segment c of every trait
-    unsigned int* ticket;    // CTA counter of the peer-memory exchange, zero between launches
-    // peer-memory exchange (world > 1): every CTA also stores its segments into every peer's buffer over NVLink; the
-    // last CTA to finish then raises this GPU's flag there to `seq`
+    // peer-memory exchange (world > 1): every CTA also stores its segments into every peer's buffer over NVLink
     int32_t world, rank;
     double* peer_list[kMaxGpus];                 // where GPU g wants THIS GPU's list (nullptr: no exchange)
-    unsigned long long* peer_flag[kMaxGpus];     // this GPU's flag in GPU g's flag array
-    unsigned long long seq;
+    unsigned long long seq;                      // sequence number of this step, written into the segment headers
     const double* rep_u;     // replay: [Mm][R][T] or nullptr
     const double* rep_z;
     int32_t* err;            // device error flag

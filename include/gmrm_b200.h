@@ -203,10 +203,10 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]);
  * shards' columns from peer memory.  After gmrm_finalize_bed each engine exports its buffers (genotypes, missing
  * lists, list buffer, flags) and imports every peer's -- as CUDA IPC handles across processes (5 x 64 bytes), or as
  * pointers inside one process.  GMRM_EXCHANGE=nccl falls back to an NCCL all-gather of the lists. */
-int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[448]);
-int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[448]);
-int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[7]);
-int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[7]);
+int gmrm_comm_export_buffers(gmrm_engine* e, uint8_t handles[384]);
+int gmrm_comm_import_buffers(gmrm_engine* e, int32_t rank, const uint8_t handles[384]);
+int gmrm_comm_local_buffers(gmrm_engine* e, void* ptrs[6]);
+int gmrm_comm_set_peer_buffers(gmrm_engine* e, int32_t rank, int32_t peer_device, void* const ptrs[6]);
 
 #ifdef __cplusplus
 }

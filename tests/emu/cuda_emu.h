@@ -83,6 +83,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
 template <typename T> inline T __ldcg(const T* p) { return *p; }
 inline long long clock64() { return 0; }
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }

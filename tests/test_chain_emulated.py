@@ -77,7 +77,7 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
 
     std::vector<double> partial((size_t)R * T * nsm), spart((size_t)T * nsm), plist((size_t)T * publist_doubles(R), 0.0);
     std::vector<PubEntry> pub((size_t)R * T);
-    unsigned int ticket = 0;
+    unsigned long long last_seq = 0;
     int64_t npub = 0;
     const int32_t* cols = nullptr;
     auto step = [&](int V, bool pending, const int32_t* pl) {
@@ -86,7 +86,7 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
             q.bed = bed.data(); q.col_stride = L.col_stride; q.nrows = L.nrows; q.cols = cols; q.V = V; q.eps = eps.data(); q.npad = L.npad;
             q.Ttot = T; q.t0 = t0; q.rows_per_pass = pl[1]; q.npass = pl[2]; q.partial = partial.data(); q.spart = spart.data();
             q.mask4 = mask4.data(); q.pV = R; q.err = &err; q.pf = 1;
-            if (pending) { q.pG = 1; q.plist = plist.data(); q.pbed[0] = bed.data(); q.pmiss_off[0] = off.data(); q.pmiss_idx[0] = midx.data(); }
+            if (pending) { q.pG = 1; q.plist = plist.data(); q.wait_seq = last_seq; q.pbed[0] = bed.data(); q.pmiss_off[0] = off.data(); q.pmiss_idx[0] = midx.data(); }
             const int Tl = std::min((int)pl[0], T - t0);
             emu_launch(EmuDim3(nsm), EmuDim3(kStepThreads), [&] {
                 switch (Tl) {
@@ -118,9 +118,10 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
             sp.marker_begin = 0; sp.Mloc = Mt; sp.cols = cols; sp.partial = partial.data(); sp.spart = spart.data();
             sp.miss_off = off.data(); sp.miss_idx = midx.data(); sp.eps = eps.data(); sp.npad = L.npad; sp.mave = o_mave; sp.msig = o_msig;
             sp.betas = betas.data(); sp.comp = comp.data(); sp.group = group; sp.sigmag = sigmag.data(); sp.gc = gc.data(); sp.nonas = nonas;
-            sp.cass = cass.data(); sp.pub = pub.data(); sp.plist = plist.data(); sp.ticket = &ticket; sp.world = 1; sp.rank = 0;
+            sp.cass = cass.data(); sp.pub = pub.data(); sp.plist = plist.data(); sp.world = 1; sp.rank = 0;
             sp.seq = (unsigned long long)s + 1; sp.err = &err; sp.npublished = &npub;
             emu_launch(EmuDim3(publist_segments(R)), EmuDim3(kSegCap * 32), [&] { sample_kernel(sp); });
+            last_seq = sp.seq;
         }
         cols = nullptr;
         step(0, true, plan + 3);                             // flush

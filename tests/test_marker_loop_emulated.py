@@ -4,7 +4,7 @@ through tests/emu/cuda_emu.h, against the oracle's restatement of Bayes::process
 same Philox streams (and, second variant, replaying the oracle's logged variates through the kernel's replay inputs).
 
 Covers what the per-kernel emulation tests cannot: the hand-over between the kernels (per-CTA partial sums, ordered
-compaction of the published updates by the last CTA, the ticket, the pending list applied by the next launch), the
+compaction of the published updates into list segments whose headers carry the step's sequence number, the pending list applied by the next launch), the
 sampler's plumbing (missing-genotype correction of sum b*eps, group constants, component counts).  Test infrastructure
 only; shapes are tiny (a CUDA thread is a std::thread here)."""
 import ctypes as C
@@ -38,7 +38,7 @@ extern "C" int emu_marker_loop(const uint8_t* bed, int N, int nsm, int T, int G,
     std::vector<double> gc((size_t)T * G * 4 * K), partial((size_t)R * T * nsm), spart((size_t)T * nsm), plist((size_t)T * publist_doubles(R), 0.0);
     std::vector<PubEntry> pub((size_t)R * T);
     std::vector<int32_t> cols(R);
-    unsigned int ticket = 0;
+    unsigned long long last_seq = 0;                         // sequence number in the segment headers of the pending list
     emu_launch(EmuDim3((T * G + 127) / 128), EmuDim3(128), [&] { group_consts_kernel(T, G, K, N, sigmag, sigmae, pi, cva, cvai, nonas, gc.data()); });
 
     auto step = [&](int V, bool pending, const int32_t* pl) {
@@ -47,7 +47,7 @@ extern "C" int emu_marker_loop(const uint8_t* bed, int N, int nsm, int T, int G,
             q.bed = bed; q.col_stride = L.col_stride; q.nrows = L.nrows; q.cols = cols.data(); q.V = V; q.eps = eps; q.npad = L.npad;
             q.Ttot = T; q.t0 = t0; q.rows_per_pass = pl[1]; q.npass = pl[2]; q.partial = partial.data(); q.spart = spart.data();
             q.mask4 = mask4; q.pV = R; q.err = &err; q.pf = 1;
-            if (pending) { q.pG = 1; q.plist = plist.data(); q.pbed[0] = bed; q.pmiss_off[0] = miss_off; q.pmiss_idx[0] = miss_idx; }
+            if (pending) { q.pG = 1; q.plist = plist.data(); q.wait_seq = last_seq; q.pbed[0] = bed; q.pmiss_off[0] = miss_off; q.pmiss_idx[0] = miss_idx; }
             const int Tl = std::min((int)pl[0], T - t0);
             emu_launch(EmuDim3(nsm), EmuDim3(kStepThreads), [&] {
                 switch (Tl) {
@@ -71,10 +71,10 @@ extern "C" int emu_marker_loop(const uint8_t* bed, int N, int nsm, int T, int G,
         sp.marker_begin = 0; sp.Mloc = Mt; sp.cols = cols.data(); sp.partial = partial.data(); sp.spart = spart.data();
         sp.miss_off = miss_off; sp.miss_idx = miss_idx; sp.eps = eps; sp.npad = L.npad; sp.mave = mave; sp.msig = msig;
         sp.betas = betas; sp.comp = comp; sp.group = group; sp.sigmag = sigmag; sp.gc = gc.data(); sp.nonas = nonas; sp.cass = cass;
-        sp.pub = pub.data(); sp.plist = plist.data(); sp.ticket = &ticket; sp.world = 1; sp.rank = 0; sp.seq = (unsigned long long)s + 1;
+        sp.pub = pub.data(); sp.plist = plist.data(); sp.world = 1; sp.rank = 0; sp.seq = (unsigned long long)s + 1;
         sp.rep_u = rep_u; sp.rep_z = rep_z; sp.err = &err; sp.npublished = npublished;
         emu_launch(EmuDim3(publist_segments(R)), EmuDim3(kSegCap * 32), [&] { sample_kernel(sp); });
-        if (ticket != 0) return -100;                        // the last CTA hands the ticket back
+        last_seq = sp.seq;
     }
     step(0, true, plan + 3);                                 // flush: the last step's updates
     return err;
