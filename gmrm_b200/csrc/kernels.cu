@@ -436,7 +436,7 @@ __device__ __forceinline__ void seg_prefix(const StepParams& p, int tt, int S, i
         const int y = __shfl_up_sync(0xffffffffu, incl, o);
         if ((tid & 31) >= o) incl += y;
     }
-    __threadfence();                                    // the items behind the headers (written before them) are read after this point
+    if (p.pG > 1) __threadfence();                      // lists from other GPUs: the items behind the headers (written before them) are read after this point
     __syncthreads();                                    // wcnt / segpre of the previous trait are consumed
     if ((tid & 31) == 31) wcnt[tid >> 5] = incl;
     __syncthreads();
