@@ -364,7 +364,7 @@ def run_ours(args):
                                     f"with {ncausal} causal markers, h2 = 0.5, genetic values computed on device)",
             "config": {"workload": f"{args.workload}: N={N} M={M} T={T} G={G} K={K}", "vranks_per_gpu": args.vranks_per_gpu,
                        "vranks_total": R, "sync_rate": args.sync_rate, "marker_steps_per_iter": steps_per_it,
-                       "exchange": None if world == 1 else (os.environ.get("GMRM_EXCHANGE") or "lists") if args.sync_rate == 1 else "delta",
+                       "exchange": None if world == 1 else (os.environ.get("GMRM_EXCHANGE") or "xdelta") if args.sync_rate == 1 else "delta",
                        "causal_markers": ncausal, "h2": 0.5,
                        "layout": f"base-3 quads (1 byte = 4 genotypes), {e.tiles} CTAs, {e.column_stride} B/column",
                        "l2": "inputs >> L2 (no flush needed)",

@@ -144,6 +144,11 @@ struct gmrm_engine {
     // exchange by published lists (world_size > 1, sync_rate == 1): every GPU applies every GPU's published updates
     // itself, reading the other shards' columns over NVLink peer memory; the lists travel by one small all-gather
     bool list_exchange = false;
+    // fused increment exchange (the default at sync_rate 1 on several GPUs; GMRM_EXCHANGE=lists|nccl|delta select the others):
+    // every GPU applies its own list, the increments are reduced and the new residuals broadcast inside the step kernel over
+    // NVLink peer memory (StepParams::xd_world).  Its receive and landing buffers sit behind this GPU's list block in `plist`,
+    // so the six exported buffers stay what they were.
+    bool xdelta = false;
     const uint8_t* peer_bed[kMaxGpus] = {};
     const uint32_t* peer_moff[kMaxGpus] = {};
     const uint32_t* peer_midx[kMaxGpus] = {};
@@ -287,11 +292,14 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     // the other shards' columns over NVLink; "delta" -- every GPU applies its own updates and the residual deltas are all-reduced
     // (what sync_rate > 1 always does); "nccl" -- lists, gathered by NCCL instead of pushed by the sampler kernel
     const char* xmode = getenv("GMRM_EXCHANGE");
-    e->list_exchange = c->world_size > 1 && c->sync_rate == 1 && !(xmode && strcmp(xmode, "delta") == 0);
+    const bool x1 = c->world_size > 1 && c->sync_rate == 1;
+    e->list_exchange = x1 && xmode && (strcmp(xmode, "lists") == 0 || strcmp(xmode, "nccl") == 0);
+    e->xdelta = x1 && !e->list_exchange && !(xmode && strcmp(xmode, "delta") == 0);
     if (c->world_size > kMaxGpus) { delete e; return fail(GMRM_EINVAL, "world_size %d > %d", c->world_size, kMaxGpus); }
-    if (c->world_size > 1 && !e->list_exchange) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
+    if (c->world_size > 1 && !e->list_exchange && !e->xdelta) { A(e->delta.alloc((size_t)T * L.npad)); A(e->delta_tot.alloc((size_t)T * L.npad)); }
     if (const char* v = getenv("GMRM_EXCHANGE")) e->list_p2p = strcmp(v, "nccl") != 0;
-    A(e->plist.alloc((size_t)(e->list_exchange ? 2 * c->world_size : 1) * T * publist_doubles(e->Vl)));   // 2: parity of the exchange sequence
+    A(e->plist.alloc((size_t)(e->list_exchange ? 2 * c->world_size : 1) * T * publist_doubles(e->Vl) +   // 2: parity of the exchange sequence
+                     (e->xdelta ? 4 + (size_t)2 * (c->world_size + 1) * T * L.npad : 0)));               // receive + landing buffers of the increment exchange
     A(e->rflags.alloc((size_t)kMaxGpus * L.nsm));
     if (const char* v = getenv("GMRM_ROWSHARD")) e->row_shard = atoi(v) != 0;
     if (rc != 0) { delete e; return rc; }
@@ -300,6 +308,9 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
                     &e->mu_old, &e->partial, &e->delta, &e->delta_tot})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     if (e->plist.zero(e->stream) != 0 || e->rflags.zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->xdelta)   // exchange buffers (behind the list block, see xrecv_offset below): "nothing here yet"
+        launch_fill_u64(reinterpret_cast<unsigned long long*>(e->plist.p + (((size_t)T * publist_doubles(e->Vl) + 3) & ~(size_t)3)),
+                        (size_t)2 * (c->world_size + 1) * T * L.npad, kXdSentinel, e->stream);
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
     if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
@@ -601,6 +612,8 @@ struct Pending { bool any = false; bool own_only = false; };
 static size_t list_block(const gmrm_engine* e) { return (size_t)e->cfg.T * publist_doubles(e->Vl); }
 static double* lists_of(gmrm_engine* e, unsigned long long seq) { return e->plist.p + (e->list_exchange ? (size_t)(seq & 1) * e->cfg.world_size * list_block(e) : 0); }
 static double* own_list(gmrm_engine* e, unsigned long long seq) { return lists_of(e, seq) + (e->list_exchange ? (size_t)e->cfg.world_rank * list_block(e) : 0); }
+static size_t xrecv_offset(const gmrm_engine* e) { return (list_block(e) + 3) & ~(size_t)3; }   // in doubles; 32-byte aligned
+static size_t xland_offset(const gmrm_engine* e) { return xrecv_offset(e) + (size_t)2 * e->cfg.world_size * e->cfg.T * e->L.npad; }
 
 static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pending& pend, double* partial, int* nlaunch, bool in_loop = false) {
     const int T = e->cfg.T;
@@ -627,8 +640,13 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         } else if (pend.any) {                                  // this GPU's own list
             p.pG = 1; p.plist = own_list(e, e->pend_seq); p.wait_seq = e->pend_seq;
             p.pbed[0] = e->bed.p; p.pmiss_off[0] = e->miss_off.p; p.pmiss_idx[0] = e->miss_idx.p;
+            if (e->xdelta && !pend.own_only) {                  // ... as increments, reduced and broadcast inside the kernel
+                const int W = e->cfg.world_size;
+                p.xd_world = W; p.xd_rank = e->cfg.world_rank; p.row_seq = ++e->row_seq;
+                for (int g = 0; g < W; g++) { p.xrecv[g] = e->peer_plist[g] + xrecv_offset(e); p.xland[g] = e->peer_plist[g] + xland_offset(e); }
+            }
         }
-        p.delta = (e->cfg.world_size > 1 && !e->list_exchange) ? e->delta.p : nullptr;
+        p.delta = (e->cfg.world_size > 1 && !e->list_exchange && !e->xdelta) ? e->delta.p : nullptr;
         p.merge_tot = (e->merge_pending && in_loop) ? e->delta_tot.p : nullptr;   // only launches of the marker loop take the fused merge
         p.err = e->err.p;
         p.prof = e->prof.p;
@@ -1005,7 +1023,7 @@ int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) 
     //                   residual deltas are all-reduced and merged
     CU(cudaEventRecord(e->ev[1], s));
     const bool multi = c.world_size > 1;
-    if (e->list_exchange) {
+    if (e->list_exchange || e->xdelta) {
         if (e->peers_set != c.world_size - 1) return fail(GMRM_EINVAL, "world_size > 1 with sync_rate 1 needs the peers' buffers (gmrm_comm_import_buffers / gmrm_comm_set_peer_buffers)");
     }
     Pending pend;                             // published updates of the previous step still to be applied?
@@ -1027,7 +1045,7 @@ int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) 
         if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 2], s));
         pend.any = true;
         e->pend_seq = e->xseq;
-        const bool delta_exchange = multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
+        const bool delta_exchange = multi && !e->list_exchange && !e->xdelta && ((st + 1) % c.sync_rate == 0 || st == Mm - 1);
         if (e->list_exchange && !e->list_p2p) {
             NC(g_nccl.AllGather(own_list(e, e->xseq), lists_of(e, e->xseq), (size_t)T * publist_doubles(Vl), kNcclFloat64, e->comm, s));
             if (e->timing_detail > 1) CU(cudaEventRecord(e->dot_ev[6 * st + 5], s));
@@ -1114,7 +1132,7 @@ int gmrm_wait_iteration(gmrm_engine* e) {
             if (e->list_exchange && !e->list_p2p) {
                 CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 2], e->dot_ev[6 * st + 5]));
                 e->last.allreduce_ms += ms;
-            } else if (multi && !e->list_exchange && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
+            } else if (multi && !e->list_exchange && !e->xdelta && ((st + 1) % c.sync_rate == 0 || st == Mm - 1)) {
                 CU(cudaEventElapsedTime(&ms, e->dot_ev[6 * st + 3], e->dot_ev[6 * st + 5]));
                 e->last.allreduce_ms += ms;
             }

@@ -1,5 +1,6 @@
 // sm_100a kernels of the Gibbs marker loop (see kernels.cuh, layout.h).
 #include <atomic>
+#include <type_traits>
 
 #include "kernels.cuh"
 
@@ -34,6 +35,13 @@ __device__ __forceinline__ double block_sum_fixed(double v, double* red) {
 // Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization attribute may start while
 // its predecessor in the stream is still draining; pdl_wait() returns once the predecessor has completed and its writes
 // are visible, pdl_trigger() lets the successor's CTAs be scheduled from here on.  Both are no-ops in a plain launch.
+// 32-byte accesses of the multi-GPU exchange: full-sector stores (peer memory over NVLink), polling loads that bypass L1
+__device__ __forceinline__ void st_v4_f64(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void ld_poll_v4(const double* p, unsigned long long (&w)[4]) {
+    asm volatile("ld.volatile.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // [helpers-end]
@@ -465,14 +473,20 @@ __device__ __forceinline__ const double* seg_item(const StepParams& p, int tt, i
 
 // ---- (a) pending updates: Phenotype::update_epsilon (phenotype.cpp:326-329,375-390) for every published marker
 // of the previous step, in virtual-rank order, restricted to this CTA's rows.  All NT threads of the CTA work.
+// With the fused increment exchange (p.xd_world > 1) the sums start from zero and go, instead of into the residuals, into the
+// receive buffers of the GPUs that own the sub-slices of this CTA's rows (exchange_increments below finishes the job); the
+// return value is the mask of the launch's traits whose list held anything.
 template <int T, int NT>
-__device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage* stage, PubInfo* info, uint32_t* lut,
-                              uint32_t* bitmap, int* wcnt, uint8_t* bytes, int bytes_cap, bool profme) {
+__device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* stage, PubInfo* info, uint32_t* lut,
+                             uint32_t* bitmap, int* wcnt, uint8_t* bytes, int bytes_cap, bool profme) {
     long long tk = profme ? clock64() : 0;
     int nk = 40;
 #define GMRM_ATICK() if (profme && nk < 60) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     const int tid = threadIdx.x;
     const int nr = pr.total, nq = nr * kRowBytes;       // quads of my rows
+    const bool xd = p.xd_world > 1;
+    const int xsub = (nq + max(p.xd_world, 1) - 1) / max(p.xd_world, 1);   // quads per sub-slice (fused increment exchange)
+    int tmask = 0;
     // base-3 byte -> byte offsets (8 * dosage) of its four individuals into a PubStage
     for (int e = tid; e < kTabEntries; e += NT) {
         const uint32_t f = tri_to_fields(e);
@@ -499,6 +513,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
         const uint8_t* mask_t = p.mask4 + (int64_t)tt * p.col_stride;
         seg_prefix<NT>(p, tt, S, nseg, segpre, wcnt);
         const int total = segpre[nseg];
+        if (total > 0) tmask |= 1 << t;
         for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
             double e[2][4], e0[2][4];
             uint32_t nmask[2];                          // 0x78 in byte k: individual k is not observed -> zero entry (15 of a pair table, 3 of a single one)
@@ -512,7 +527,7 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                 const uint32_t na = have[qq] ? mask_t[gq[qq]] : 0u;
                 nmask[qq] = ((na & 1u) ? 0u : 0x78u) | ((na & 2u) ? 0u : 0x7800u) | ((na & 4u) ? 0u : 0x780000u) | ((na & 8u) ? 0u : 0x78000000u);
 #pragma unroll
-                for (int k = 0; k < 4; k++) { e[qq][k] = have[qq] ? eps_t[4 * (int64_t)gq[qq] + k] : 0.0; e0[qq][k] = e[qq][k]; }
+                for (int k = 0; k < 4; k++) { e[qq][k] = (have[qq] && !xd) ? eps_t[4 * (int64_t)gq[qq] + k] : 0.0; e0[qq][k] = e[qq][k]; }
             }
             GMRM_ATICK()   // [40] lut + eps/mask loads
             bool touched = false;
@@ -646,7 +661,14 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
                 }
             }
             GMRM_ATICK()   // [43] apply
-            if (touched) {
+            if (xd) {                                   // hop 1: the increments of quad q (zeros if nothing was published) go to the GPU that owns q's sub-slice
+#pragma unroll
+                for (int qq = 0; qq < 2; qq++) {
+                    if (!have[qq]) continue;
+                    double* dst = p.xrecv[(q0 + qq * NT + tid) / xsub] + (((size_t)(p.row_seq & 1) * p.xd_world + p.xd_rank) * p.Ttot + tt) * p.npad + 4 * (int64_t)gq[qq];
+                    st_v4_f64(dst, e[qq][0], e[qq][1], e[qq][2], e[qq][3]);
+                }
+            } else if (touched) {
 #pragma unroll
                 for (int qq = 0; qq < 2; qq++) {
                     if (!have[qq]) continue;
@@ -661,6 +683,88 @@ __device__ void apply_pending(const StepParams& p, const PassRows& pr, PubStage*
             }
         }
     }
+    return tmask;
+}
+
+// ---- fused increment exchange, second half (see StepParams::xd_world): reduction of this GPU's sub-slice of the CTA's rows in
+// GPU order, hop 2 (new residuals into every GPU's landing buffer), then the CTA's rows from its own landing buffer into the
+// residual array.  Data-driven: every wait is a poll of the payload itself.  Whole CTA; ends with a barrier.  `red` is scratch
+// (the staging area: xd_world * quads of a sub-slice * 32 bytes).
+__device__ __forceinline__ bool xd_ready(const unsigned long long (&w)[4]) {
+    return w[0] != kXdSentinel && w[1] != kXdSentinel && w[2] != kXdSentinel && w[3] != kXdSentinel;
+}
+__device__ __forceinline__ void xd_wait(const double* src, unsigned long long (&w)[4]) {
+    ld_poll_v4(src, w);
+    for (uint32_t spins = 0; !xd_ready(w); ++spins) {
+        __nanosleep(40);
+        if (spins > (1u << 28)) __trap();                // a lost peer must surface as an error, not as a hung GPU
+        ld_poll_v4(src, w);
+    }
+}
+template <int T, int NT>
+__device__ void exchange_increments(const StepParams& p, const PassRows& pr, double* red, int red_bytes) {
+    const int tid = threadIdx.x;
+    const int G = p.xd_world, me = p.xd_rank, par = (int)(p.row_seq & 1);
+    const int nq = pr.total * kRowBytes, xsub = (nq + G - 1) / G;
+    const int q_lo = min(nq, me * xsub), q_hi = min(nq, q_lo + xsub), nmine = q_hi - q_lo;
+    const double sent = __longlong_as_double((long long)kXdSentinel);
+    const int cap = max(1, red_bytes / (G * 32));        // quads of the sub-slice per round of the scratch area
+    __syncthreads();                                     // the staging area is free
+    for (int t = 0; t < T; t++)
+    for (int c0 = 0; c0 < nmine; c0 += cap) {
+        const int64_t tb = (int64_t)(p.t0 + t) * p.npad;
+        const int nc = min(cap, nmine - c0), qc = q_lo + c0;
+        // my sub-slice: one thread per (source GPU, quad) fetches, a barrier, one thread per quad adds in GPU order and sends
+        for (int i = tid; i < nc * G; i += NT) {
+            const int g = i / nc, q = qc + (i - g * nc);
+            const int64_t o = tb + 4 * ((int64_t)global_row(pr, q >> 6) * kRowBytes + (q & 63));
+            double* src = p.xrecv[me] + ((size_t)(par * G + g) * p.Ttot) * p.npad + o;
+            unsigned long long w[4];
+            xd_wait(src, w);
+            st_v4_f64(src, sent, sent, sent, sent);      // consumed: the slot is rewritten two launches from now
+            double* r = red + (size_t)i * 4;
+            r[0] = __longlong_as_double((long long)w[0]); r[1] = __longlong_as_double((long long)w[1]);
+            r[2] = __longlong_as_double((long long)w[2]); r[3] = __longlong_as_double((long long)w[3]);
+        }
+        __syncthreads();
+        for (int i = tid; i < nc; i += NT) {
+            const int q = qc + i;
+            const int64_t o = tb + 4 * ((int64_t)global_row(pr, q >> 6) * kRowBytes + (q & 63));
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            for (int g = 0; g < G; g++) {                // fixed order: every replica receives the same bits
+                const double* r = red + ((size_t)g * nc + i) * 4;
+                s0 += r[0]; s1 += r[1]; s2 += r[2]; s3 += r[3];
+            }
+            const double2 ea = __ldcg(reinterpret_cast<const double2*>(p.eps + o)), eb = __ldcg(reinterpret_cast<const double2*>(p.eps + o + 2));
+            const double n0 = ea.x + s0, n1 = ea.y + s1, n2 = eb.x + s2, n3 = eb.y + s3;
+            for (int g = 0; g < G; g++) st_v4_f64(p.xland[g] + ((size_t)par * p.Ttot) * p.npad + o, n0, n1, n2, n3);
+        }
+        __syncthreads();                                 // `red` is reused by the next round
+    }
+    // every quad of my rows, from whichever GPU reduced it
+    for (int t = 0; t < T; t++) {
+        const int64_t tb = (int64_t)(p.t0 + t) * p.npad;
+        for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
+            int64_t o[2]; unsigned long long w[2][4]; bool have[2];
+#pragma unroll
+            for (int qq = 0; qq < 2; qq++) {
+                const int q = q0 + qq * NT + tid;
+                have[qq] = q < nq;
+                o[qq] = have[qq] ? tb + 4 * ((int64_t)global_row(pr, q >> 6) * kRowBytes + (q & 63)) : 0;
+                if (have[qq]) ld_poll_v4(p.xland[me] + ((size_t)par * p.Ttot) * p.npad + o[qq], w[qq]);
+            }
+#pragma unroll
+            for (int qq = 0; qq < 2; qq++) {
+                if (!have[qq]) continue;
+                double* src = p.xland[me] + ((size_t)par * p.Ttot) * p.npad + o[qq];
+                if (!xd_ready(w[qq])) xd_wait(src, w[qq]);
+                st_v4_f64(src, sent, sent, sent, sent);
+                st_v4_f64(p.eps + o[qq], __longlong_as_double((long long)w[qq][0]), __longlong_as_double((long long)w[qq][1]),
+                          __longlong_as_double((long long)w[qq][2]), __longlong_as_double((long long)w[qq][3]));
+            }
+        }
+    }
+    __syncthreads();
 }
 
 // ---- (a') the same updates with several GPUs in the list exchange, ROW-SHARDED: every GPU would otherwise apply every GPU's
@@ -852,6 +956,22 @@ __device__ void apply_pending_sharded(const StepParams& p, const PassRows& pr, P
     __syncthreads();
 }
 
+// Byte offset, inside the nr * 64 contiguous bytes a CTA owns of every column in a pass, of byte k of the word that lane l16
+// (of the 16 lanes serving a marker) holds for table slot s.  Slots are grouped for vector loads: four slots are 16 contiguous
+// bytes per lane, two are 8, one is 4 -- nr = 5: [16 lanes x 16 B][16 lanes x 4 B], nr = 3: [16 x 8 B][16 x 4 B].
+__host__ __device__ __forceinline__ int chunk_offset(int nr, int s, int l16, int k) {
+    int base = 0;
+    if (nr >= 4) {
+        if (s < 4) return 16 * l16 + 4 * s + k;
+        base = 256; nr -= 4; s -= 4;
+    }
+    if (nr >= 2) {
+        if (s < 2) return base + 8 * l16 + 4 * s + k;
+        base += 128; s -= 2;
+    }
+    return base + 4 * l16 + k;
+}
+
 // ---- (b) tables of rows [row0, row0 + nrp) for T traits, by the NC consumer threads; es[t] accumulates this
 // thread's share of sum eps
 template <int T, int NC>
@@ -860,8 +980,9 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
     const int nunits = nrp * T * 4 * 3;
     for (int u = hw; u < nunits; u += NC / 16) {
         const int d3 = u % 3, line = u / 3, k = line & 3, slot = line >> 2, rr = slot / T, t = slot - rr * T;
-        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + ((int64_t)(row0 + rr) * kRowBytes + 4 * l16 + k) * 4;
-        const double2 e01 = *reinterpret_cast<const double2*>(e), e23 = *reinterpret_cast<const double2*>(e + 2);
+        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + ((int64_t)row0 * kRowBytes + chunk_offset(nrp, rr, l16, k)) * 4;
+        // .cg: in the multi-GPU exchanges these rows were just stored by other GPUs (they land in this GPU's L2)
+        const double2 e01 = __ldcg(reinterpret_cast<const double2*>(e)), e23 = __ldcg(reinterpret_cast<const double2*>(e + 2));
         if (d3 == 0) {
             const double s4 = (e01.x + e01.y) + (e23.x + e23.y);
 #pragma unroll
@@ -888,7 +1009,6 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
 
 constexpr int kStepWarps = GMRM_STEP_WARPS, kStepThreads = kStepWarps * 32;
 constexpr int kPairs = kBatch / 2;
-constexpr int kDepth = GMRM_STEP_DEPTH;      // batches of register prefetch
 
 // L2 prefetch of this warp's first two batches of a pass (rows [row0, row0+nr) of their 16 columns each): issued
 // before the pass's tables are built (and at kernel start for pass 0), it takes the HBM round trip of the first
@@ -911,6 +1031,24 @@ __device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0
 
 // ---- (c) stream the V columns through the tables of NR rows
 // Markers [v0, v0 + Vc) of the step (a chunk whose Vc * T partial sums fit the shared-memory array `part`).
+// A CTA's share of a column in a pass is one contiguous chunk of NR * 64 bytes.  Lane l (of the 16 that serve a marker) takes
+// its words for the NR table slots with as few, as wide loads as the chunk allows -- four slots: 16 contiguous bytes (one
+// LDG.128), two: 8 bytes, one: 4 bytes (chunk_offset below; build_tables uses the same map) -- so that a warp's load
+// instruction covers whole 128-byte lines (the 4-byte form touched two half-used lines per instruction and cost twice the
+// L1 wavefronts per byte).  Two register buffers take turns (A: in use, B: being loaded for the warp's next batch).
+template <int NR>
+__device__ __forceinline__ void load_words(const uint8_t* pa, const uint8_t* pb, uint32_t (&w)[NR]) {
+    if constexpr (NR >= 4) {
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(pa));
+        if constexpr (NR == 5) w[4] = ldg_stream_u32(pb);
+    } else if constexpr (NR >= 2) {
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(pa));
+        if constexpr (NR == 3) w[2] = ldg_stream_u32(pb);
+    } else {
+        w[0] = ldg_stream_u32(pa);
+    }
+}
+
 template <int NR, int T>
 __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -919,7 +1057,14 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
     const int nb = (Vc + kBatch - 1) / kBatch;
     int b = warp;
     if (b >= nb) return;
-    const uint8_t* base = p.bed + (int64_t)row0 * kRowBytes + l16 * 4;
+    // Addresses: (column * nrows + row0) is a 32-bit ROW index (columns are whole rows: < 2^32 rows for any shard that fits a
+    // GPU), so a lane's address is ONE multiply-add  lane_a + row * 64  on top of its 64-bit lane base.  The base is passed
+    // through an empty asm statement: the compiler otherwise re-derives it from the kernel parameters in front of every load
+    // (a dozen integer instructions per marker pair) to save two registers.
+    const uint8_t* lane_a = p.bed + chunk_offset(NR, 0, l16, 0);
+    asm volatile("" : "+l"(lane_a));
+    const int d_b = chunk_offset(NR, NR - 1, l16, 0) - chunk_offset(NR, 0, l16, 0);    // the odd slot (NR 3, 5) behind the wide group
+    const uint32_t nrows = (uint32_t)p.nrows, row0u = (uint32_t)row0;
     const int32_t* ccols = p.cols + v0;
 
     // raw column index (may be -1: no marker); the clamp is applied where the value is USED -- clamping here would make
@@ -928,69 +1073,39 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         const int v = bb * kBatch + (l16 & (kBatch - 1));
         return (bb < nb && v < Vc) ? ccols[v] : 0;
     };
-    // register prefetch: Wn holds the next batch, Wn2 (GMRM_STEP_DEPTH == 2) the one after
-    uint32_t Wn[kPairs][NR];
-    [[maybe_unused]] uint32_t Wn2[kDepth == 2 ? kPairs : 1][NR];
-    auto issue = [&](int c, uint32_t (&dst)[kPairs][NR]) {
-#pragma unroll
-        for (int i = 0; i < kPairs; i++) {
-            const int col = max(__shfl_sync(0xffffffffu, c, 2 * i + h), 0);
-            const uint8_t* ptr = base + (int64_t)col * p.col_stride;
-#pragma unroll
-            for (int rr = 0; rr < NR; rr++) dst[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
-        }
+    uint32_t WA[kPairs][NR], WB[kPairs][NR];
+    auto load_pair = [&](int col, int i, uint32_t (&dst)[kPairs][NR]) {      // col: the pair's column for this half-warp (raw)
+        const uint32_t r = (uint32_t)max(col, 0) * nrows + row0u;
+        const uint8_t* pa = lane_a + (uint64_t)r * kRowBytes;
+        load_words<NR>(pa, pa + d_b, dst[i]);
     };
-    issue(loadcols(b), Wn);
-    if constexpr (kDepth == 2) issue(loadcols(b + kStepWarps), reinterpret_cast<uint32_t(&)[kPairs][NR]>(Wn2));
-    int cn = loadcols(b + kDepth * kStepWarps);
+    {
+        const int c0 = loadcols(b);
+#pragma unroll
+        for (int i = 0; i < kPairs; i++) load_pair(__shfl_sync(0xffffffffu, c0, 2 * i + h), i, WA);
+    }
+    int cn = loadcols(b + kStepWarps);
     // L2 prefetch kPfAhead batches ahead of the register loads (which run one batch ahead): the 16 warps then keep
     // ~192 KB per SM in flight towards HBM instead of 64 KB
     constexpr int kPfAhead = 4;
     int pcol = p.pf ? loadcols(b + kPfAhead * kStepWarps) : 0;
-    const uint8_t* pf_base = p.bed + (int64_t)row0 * kRowBytes;
-    // lane -> (marker of the batch, 128-byte line of its chunk); the last lane group also touches the chunk's last byte
-    constexpr int kLG = 32 / kBatch;
-    const int pf_g = lane / kBatch;
-    const int pf_off_a = (kLG == 4 && pf_g == 3) ? NR * kRowBytes - 1 : pf_g * 128, pf_off_b = kLG == 4 ? 1 << 20 : (pf_g ? NR * kRowBytes - 1 : 256);
+    // lane -> (marker of the batch, 128-byte line of its chunk): one prefetch per lane covers the chunk's (at most four) lines
+    const int d_pf = min((lane / kBatch) * 128 * (kBatch / 8), NR * kRowBytes - 1) - chunk_offset(NR, 0, l16, 0);
     [[maybe_unused]] const bool hi8 = l16 & 8, hi4 = l16 & 4, hi2 = l16 & 2;
     // pair whose total this lane ends up with
     const int own = kPairs == 8 ? ((l16 >> 3) & 1) * 4 + ((l16 >> 2) & 1) * 2 + ((l16 >> 1) & 1)
-                  : kPairs == 4 ? ((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1) : ((l16 >> 3) & 1);
+                  : kPairs == 4 ? ((l16 >> 3) & 1) * 2 + ((l16 >> 2) & 1) : ((l16 >> 1) & 1);
 
-    for (; b < nb; b += kStepWarps) {
-        uint32_t W[kPairs][NR];
-#pragma unroll
-        for (int i = 0; i < kPairs; i++)
-#pragma unroll
-            for (int rr = 0; rr < NR; rr++) {
-                W[i][rr] = Wn[i][rr];
-                if constexpr (kDepth == 2) Wn[i][rr] = Wn2[i][rr];
-            }
-        const bool more = b + kDepth * kStepWarps < nb;          // warp-uniform
+    // one batch: look-ups on W while the warp's next batch (if there is one: `more`, a compile-time flag -- predicated loads
+    // into Wn cost a register copy each) is loaded into Wn
+    auto batch = [&](int bb, uint32_t (&W)[kPairs][NR], uint32_t (&Wn)[kPairs][NR], auto more_c) {
+        constexpr bool more = decltype(more_c)::value;
         const int cnow = cn;
-        if (more) cn = loadcols(b + (kDepth + 1) * kStepWarps);
-        // the loads of the next batch are spread over the look-up groups below (a burst of 8*NR loads per warp at the
-        // top of a batch filled the load/store queue in front of the other warps' look-ups)
-        auto issue_pair = [&](int i) {
-            const int col = max(__shfl_sync(0xffffffffu, cnow, 2 * i + h), 0);
-            if (more) {
-                const uint8_t* ptr = base + (int64_t)col * p.col_stride;
-#pragma unroll
-                for (int rr = 0; rr < NR; rr++) {
-                    if constexpr (kDepth == 2) Wn2[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
-                    else Wn[i][rr] = ldg_stream_u32(ptr + rr * kRowBytes);
-                }
-            }
-        };
-        if (p.pf && b + kPfAhead * kStepWarps < nb) {
-            const uint8_t* a = pf_base + (int64_t)max(pcol, 0) * p.col_stride;
-            if (p.pf == 2) {                              // bulk (TMA) L2 prefetch: one instruction per marker chunk
-                if (lane < kBatch) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(NR * kRowBytes) : "memory");
-            } else {
-                if (pf_off_a < NR * kRowBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_a));
-                if (pf_off_b < NR * kRowBytes && NR > 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + pf_off_b));
-            }
-            pcol = loadcols(b + (kPfAhead + 1) * kStepWarps);
+        if constexpr (more) cn = loadcols(bb + 2 * kStepWarps);
+        if (p.pf && bb + kPfAhead * kStepWarps < nb) {
+            const uint32_t r = (uint32_t)max(pcol, 0) * nrows + row0u;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(lane_a + (uint64_t)r * kRowBytes + d_pf));
+            pcol = loadcols(bb + (kPfAhead + 1) * kStepWarps);
         }
         double acc[kPairs][T];
 #pragma unroll
@@ -998,19 +1113,30 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
 #pragma unroll
             for (int t = 0; t < T; t++) acc[i][t] = 0.0;
 
+        // the loads of the next batch are spread over the first look-up groups (a burst of loads at the top of a batch
+        // filled the load/store queue in front of the other warps' look-ups)
 #define GMRM_LOOKUP(RR, K)                                                    \
     _Pragma("unroll") for (int i = 0; i < kPairs; i++)                             \
         lookup_traits<RR * T, K, T>(acc[i], tab_addr<K>(W[i][RR], low));      \
     {                                                                         \
-        constexpr int PPG = (kPairs + NR * 4 - 1) / (NR * 4), G = RR * 4 + K; \
-        _Pragma("unroll") for (int i = G * PPG; i < (G + 1) * PPG; i++)       \
-            if (i < kPairs) issue_pair(i);                                    \
+        constexpr int G = RR * 4 + K;                                         \
+        if constexpr (G < kPairs) {                                           \
+            const int c_ = __shfl_sync(0xffffffffu, cnow, 2 * G + h);         \
+            if constexpr (more) load_pair(c_, G, Wn);                         \
+        }                                                                     \
     }
 #define GMRM_ROW(RR)                                                          \
     if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_LOOKUP(RR, 1) GMRM_LOOKUP(RR, 2) GMRM_LOOKUP(RR, 3) }
         GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3) GMRM_ROW(4)
 #undef GMRM_ROW
 #undef GMRM_LOOKUP
+        if constexpr (NR * 4 < kPairs) {                  // fewer look-up groups than pairs (NR == 1, batches of 16)
+#pragma unroll
+            for (int i = NR * 4; i < kPairs; i++) {
+                const int c_ = __shfl_sync(0xffffffffu, cnow, 2 * i + h);
+                if constexpr (more) load_pair(c_, i, Wn);
+            }
+        }
 
         // 16-lane transposed butterfly: the pair accumulators -> the total of pair `own` (fixed order: reproducible)
 #pragma unroll
@@ -1047,9 +1173,17 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
                 b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-            const int v = b * kBatch + 2 * own + h;
+            const int v = bb * kBatch + 2 * own + h;
             if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < Vc) part[v * T + t] += b1;
         }
+    };
+    for (;;) {
+        if (b + kStepWarps >= nb) { batch(b, WA, WB, std::false_type{}); break; }
+        batch(b, WA, WB, std::true_type{});
+        b += kStepWarps;
+        if (b + kStepWarps >= nb) { batch(b, WB, WA, std::false_type{}); break; }
+        batch(b, WB, WA, std::true_type{});
+        b += kStepWarps;
     }
 }
 
@@ -1119,7 +1253,10 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     if (p.rs_world > 1 && p.pG * p.pV > 0) apply_pending_sharded<T, NT>(p, pr, stage, info, lut, wcnt, tabs, area);
     else
-    if (p.pG * p.pV > 0 && nr > 0) apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
+    if (p.pG * p.pV > 0 && nr > 0) {
+        apply_pending<T, NT>(p, pr, stage, info, lut, bitmap, wcnt, tabs, area, p.prof && tid == 0 && (cta == 0 || cta == nsm / 2));
+        if (p.xd_world > 1) exchange_increments<T, NT>(p, pr, reinterpret_cast<double*>(tabs), area);   // every GPU's CTA `cta` owns the same rows: all of them get here
+    }
     __syncthreads();                                      // residual writes of (a) are visible to the whole CTA
     GMRM_TICK()                                           // [8] prologue + update phase
     if (p.V == 0) return;
@@ -1529,6 +1666,12 @@ void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s) {
     const int64_t n = (int64_t)T * L.npad;
     eps_merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(eps, loc, tot, n);
+}
+__global__ void fill_u64_kernel(unsigned long long* dst, size_t n, unsigned long long value) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = value;
+}
+void launch_fill_u64(unsigned long long* dst, size_t n, unsigned long long value, cudaStream_t s) {
+    if (n) fill_u64_kernel<<<1184, 256, 0, s>>>(dst, n, value);
 }
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s) {
     eps_sumsq_kernel<<<T, 1024, 0, s>>>(eps, npad, n, out);

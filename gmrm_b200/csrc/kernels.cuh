@@ -27,6 +27,7 @@ constexpr int kPartSmemDoubles = 2048;
 constexpr int kBatch = GMRM_STEP_BATCH;   // markers per warp batch (one marker per half-warp: kBatch/2 pairs)
 constexpr int kMaxGpus = 8;
 constexpr int kPubCap = 128;           // published updates staged per round of the update phase
+constexpr unsigned long long kXdSentinel = 0xFFF8DEADFFF8DEADull;   // "nothing here yet" in the exchange buffers (a NaN bit pattern)
 
 struct PubEntry {   // one published update: Phenotype::update_epsilon's dbeta[3], phenotype.cpp:326-329
     double lam;     // dbeta * msig   (0 == nothing to apply)
@@ -79,6 +80,19 @@ struct StepParams {
     double* peps[kMaxGpus];              // residual arrays of all GPUs (peer memory; [rs_rank] is this GPU's)
     unsigned long long* rflag_peer[kMaxGpus];   // GPU g's row-flag array [rs_world][nsm]: this GPU writes entry [rs_rank][cta]
     const unsigned long long* rflag_mine;       // this GPU's row-flag array: entry [g][cta] = sequence number GPU g's CTA `cta` has reached
+    // Fused two-hop exchange of residual INCREMENTS (xd_world > 1; the default at sync_rate 1 on several GPUs).  Every GPU applies
+    // only its OWN published list (local columns), as increments d_g of its CTAs' rows.  CTA c of every GPU owns the same rows;
+    // they are cut into xd_world sub-slices.  Hop 1: CTA c of GPU g stores sub-slice o of d_g into GPU o's receive buffer over
+    // NVLink.  GPU o's CTA c adds the xd_world increments of its sub-slice in GPU order to the old residuals (identical on every
+    // GPU) and -- hop 2 -- stores the new residuals into every GPU's landing buffer, from where every CTA moves its rows into its
+    // residual array: all replicas stay bit-identical, 2 x 7/8 of the residual array crosses NVLink per GPU and step.
+    // There are NO flags and NO fences: both buffers are pre-filled with a sentinel (a NaN no increment or residual can equal),
+    // the receiver polls the payload words themselves, 8 bytes at a time, and puts the sentinel back once it has them
+    // (tools/p2p_micro.cu: 2 us per hop instead of 8-15 us with a system-scope fence per CTA).  Two copies of each buffer take
+    // turns (parity of row_seq): a slot is rewritten two launches after it was consumed, with kernel boundaries in between.
+    int32_t xd_world, xd_rank;
+    double* xrecv[kMaxGpus];                     // GPU g's receive buffer [2][xd_world (source)][Ttot][npad]
+    double* xland[kMaxGpus];                     // GPU g's landing buffer [2][Ttot][npad]
     const uint8_t* mask4;    // [Ttot][col_stride] NA nibble of every quad (bit k: individual 4q+k observed)
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     const double* merge_tot; // [Ttot][npad] or nullptr: all-reduced deltas of the last exchange, still to be merged: every CTA first
@@ -143,6 +157,7 @@ void launch_stats(const uint8_t* bed, int nmark, const Layout& L, const uint8_t*
 void launch_eps_offset(double* eps, const uint8_t* mask4, const Layout& L, int T, const double* mu_old, const double* mu_new, cudaStream_t s);
 void launch_eps_merge(double* eps, double* loc, const double* tot, const Layout& L, int T, cudaStream_t s);
 void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double* out, cudaStream_t s);
+void launch_fill_u64(unsigned long long* dst, size_t n, unsigned long long value, cudaStream_t s);
 // dynamic shared memory the step kernel needs, or -1 if (V, T, rows_per_pass, rows per CTA) do not fit
 int step_npass(const Layout& L, int rows_per_pass);
 void host_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count);   // the kernel's row ownership [npass], for tests

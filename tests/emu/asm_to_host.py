@@ -64,11 +64,22 @@ def _operands(section):
 
 def _translate(instr, outs, ins):
     i = instr.strip()
+    if i == "":                                              # empty statement: an optimisation barrier for the compiler only
+        return "(void)0;"
     if i.startswith("ld.global.nc.L1::no_allocate.u32"):
         return f"{outs[0]} = *reinterpret_cast<const uint32_t*>({ins[0]});"
     if i.startswith("ld.global.nc.L1::no_allocate.v4.u32"):
         return ("{ const uint4 emu_t_ = *reinterpret_cast<const uint4*>(" + ins[0] + "); "
                 f"{outs[0]} = emu_t_.x; {outs[1]} = emu_t_.y; {outs[2]} = emu_t_.z; {outs[3]} = emu_t_.w; }}")
+    if i.startswith("ld.global.nc.L1::no_allocate.v2.u32"):
+        return ("{ const uint32_t* emu_t_ = reinterpret_cast<const uint32_t*>(" + ins[0] + "); "
+                f"{outs[0]} = emu_t_[0]; {outs[1]} = emu_t_[1]; }}")
+    if i.startswith("st.global.v4.f64"):                     # 32-byte store, word by word (no atomicity of the whole is assumed)
+        return ("{ volatile double* emu_t_ = reinterpret_cast<volatile double*>(" + ins[0] + "); "
+                f"emu_t_[0] = {ins[1]}; emu_t_[1] = {ins[2]}; emu_t_[2] = {ins[3]}; emu_t_[3] = {ins[4]}; }}")
+    if i.startswith("ld.volatile.global.v4.u64"):
+        return ("{ const volatile unsigned long long* emu_t_ = reinterpret_cast<const volatile unsigned long long*>(" + ins[0] + "); "
+                f"{outs[0]} = emu_t_[0]; {outs[1]} = emu_t_[1]; {outs[2]} = emu_t_[2]; {outs[3]} = emu_t_[3]; }}")
     if i.startswith("ld.shared.f64 %0, [%1+%2]"):
         return f"{outs[0]} = emu_lds<double>(({ins[0]}) + (uint32_t)({ins[1]}));"
     if i.startswith("ld.shared.u32 %0, [%1+%2]"):

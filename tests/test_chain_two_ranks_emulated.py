@@ -43,7 +43,7 @@ def p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def worker(rank, world, port, so, data_dir, out):
+def worker(rank, world, port, so, data_dir, out, xd=False):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -72,12 +72,21 @@ def worker(rank, world, port, so, data_dir, out):
     lib.emu_mg_info(h, C.byref(mb), C.byref(ml), C.byref(mm), C.byref(ld))
     lo, n, Mm, ld = mb.value, ml.value, mm.value, ld.value
     ok = True
+    if xd:       # fused increment exchange: residuals, receive buffers and flags of both "GPUs" in one shared mapping
+        lib.emu_mg_xd_block_bytes.restype = C.c_size_t
+        blk = lib.emu_mg_xd_block_bytes(h)
+        shm = np.memmap(os.path.join(data_dir, "xd_shared.bin"), dtype=np.uint8, mode="r+", shape=(world * blk,))
+        lib.emu_mg_enable_xd(h, p(shm))
+        dist.barrier()
     for it in range(1, iters + 1):
         lib.emu_mg_begin_iteration(h, it)
         lists = None
         for s in range(Mm):
             own = np.zeros(ld)
             ok &= lib.emu_mg_step(h, it, s, p(lists), p(own)) == 0
+            if xd:                                                          # the kernels exchange increments themselves: own list only
+                lists = own
+                continue
             got = [torch.zeros(ld, dtype=torch.float64) for _ in range(world)]
             dist.all_gather(got, torch.from_numpy(own))                     # the exchange: every GPU's list to every GPU
             lists = np.ascontiguousarray(np.stack([g.numpy() for g in got]))
@@ -96,6 +105,10 @@ def worker(rank, world, port, so, data_dir, out):
         ok &= bool(np.allclose(sigmag, res["sigmag"][i], rtol=1e-8)) and bool(np.allclose(sigmae, res["sigmae"][i], rtol=1e-8))
         ok &= bool(np.allclose(pi, np.asarray(res["pi"][i]).reshape(T, G * K), rtol=1e-8)) and bool(np.array_equal(m0, res["m0"][i]))
     ok &= bool(np.allclose(eps, res["eps_final"][:, :N], rtol=0, atol=1e-10))  # the residuals are replicated: every rank holds the chain's
+    if xd:                                                                   # one chain: the replicas are bit-identical
+        reps = [None] * world
+        dist.all_gather_object(reps, eps.tobytes())
+        ok &= all(r == reps[0] for r in reps)
     spans = [None] * world
     dist.all_gather_object(spans, (lo, n))                                   # the shards tile the markers in rank order
     ok &= spans[0][0] == 0 and all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1)) and sum(x[1] for x in spans) == M
@@ -105,7 +118,14 @@ def worker(rank, world, port, so, data_dir, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path):
+def test_two_rank_chain_with_increment_exchange_matches_oracle(tmp_path):
+    """The default multi-GPU exchange (StepParams::xd_world): each rank applies its own list as increments, the step kernel's
+    source reduces them sub-slice by sub-slice and stores the new residuals into both ranks' arrays (shared memory stands for
+    NVLink peer memory; CTA c of both processes runs concurrently, flags and all)."""
+    test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=True)
+
+
+def test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=False):
     sys.path.insert(0, ROOT)
     from gmrm_b200 import synth
     c = CASE
@@ -115,7 +135,10 @@ def test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path):
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
     port = 29000 + os.getpid() % 2000
-    procs = [ctx.Process(target=worker, args=(r, world, port, so, str(tmp_path), out)) for r in range(world)]
+    if xd:
+        with open(os.path.join(str(tmp_path), "xd_shared.bin"), "wb") as f:
+            f.write(b"\0" * (64 << 20))
+    procs = [ctx.Process(target=worker, args=(r, world, port, so, str(tmp_path), out, xd)) for r in range(world)]
     for q in procs:
         q.start()
     for q in procs:
