@@ -120,6 +120,10 @@ struct gmrm_engine {
     std::vector<int32_t> h_nonas;
 
     DevBuf<uint8_t> bed, mask4, stage, stage2;     // stage/stage2: double-buffered PLINK staging of gmrm_upload_bed
+    // hybrid plan of the step kernel (one trait; GMRM_HYBRID=0 switches it off): second copy of the direct rows, 2-bit fields
+    DevBuf<uint8_t> bed2;
+    bool hybrid = false;
+    int hyb_npass = 0;
     cudaStream_t copy_stream = nullptr;
     // output staging: betas/components of an iteration are snapshotted on the device and copied to
     // pinned host memory on the copy stream while the next iteration runs
@@ -261,6 +265,11 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
         delete e;
         return fail(GMRM_EINVAL, "%d virtual ranks per GPU do not fit the step kernel's shared memory (partials + one table slot)", vl);
     }
+    {
+        const char* hv = getenv("GMRM_HYBRID");
+        e->hybrid = c->T == 1 && GMRM_STEP_DIRECT >= 1 && !(hv && atoi(hv) == 0);
+        e->hyb_npass = step_npass(e->L, e->step_rpp);
+    }
     e->phen_set.assign(c->T, 0);
     e->h_na.assign(c->T, {});
     e->h_nonas.assign(c->T, 0);
@@ -272,6 +281,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     const Layout& L = e->L;
     const int T = c->T, G = c->G, K = c->K;
     A(e->bed.alloc((size_t)e->Mloc * L.col_stride));
+    if (e->hybrid) A(e->bed2.alloc((size_t)e->Mloc * e->hyb_npass * L.nsm * kRowBytes));
     A(e->mask4.alloc((size_t)T * L.col_stride));
     A(e->eps.alloc((size_t)T * L.npad));
     A(e->mave.alloc((size_t)T * e->Mloc)); A(e->msig.alloc((size_t)T * e->Mloc));
@@ -313,6 +323,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
                         (size_t)2 * (c->world_size + 1) * T * L.npad, kXdSentinel, e->stream);
     for (auto* b : {&e->comp, &e->cass, &e->m0, &e->err, &e->steptab, &e->nonas, &e->group_loc, &e->mtotgrp})
         if (b->zero(e->stream) != 0) { delete e; return GMRM_ECUDA; }
+    if (e->hybrid && e->bed2.zero(e->stream)) { delete e; return GMRM_ECUDA; }
     if (e->bed.zero(e->stream) || e->mask4.zero(e->stream) || e->miss_off.zero(e->stream) || e->npub.zero(e->stream)) { delete e; return GMRM_ECUDA; }
     if (cudaMemsetAsync(e->pub.p, 0, e->pub.n * sizeof(PubEntry), e->stream) != cudaSuccess || cudaStreamSynchronize(e->stream) != cudaSuccess) {
         delete e;
@@ -368,6 +379,7 @@ static int ingest_staged(gmrm_engine* e, const uint8_t* staged, int lb, int n) {
     if (e->miss_cnt.n < (size_t)n + 1) { int rc = e->miss_cnt.alloc((size_t)n + 1); if (rc) return rc; }
     CU(cudaMemsetAsync(e->miss_cnt.p, 0, ((size_t)n + 1) * 4, e->stream));
     launch_transcode(staged, n, e->L, e->bed.p + (size_t)lb * e->L.col_stride, e->miss_cnt.p, e->stream);
+    if (e->hybrid) launch_direct_plane(staged, n, e->L, e->hyb_npass, e->bed2.p + (size_t)lb * e->hyb_npass * e->L.nsm * kRowBytes, e->stream);
     CU(cudaGetLastError());
     gmrm_engine::MissChunk ch;
     ch.begin = lb; ch.count = n; ch.cnt.resize(n);
@@ -652,6 +664,9 @@ static int launch_step_all(gmrm_engine* e, const int32_t* cols, int V, const Pen
         p.prof = e->prof.p;
         p.pf = e->step_pf;
         p.pdl = e->pdl && in_loop;
+        if (e->hybrid && V > 0 && T == 1 && rpp == e->step_rpp && p.npass == e->hyb_npass) {   // the plan the second copy was laid out for
+            p.bed2 = e->bed2.p; p.drows = e->hyb_npass * e->L.nsm; p.ndir = 1;
+        }
         const int rc = launch_step(e->L, std::min(tc, T - t0), p, e->stream);
         if (rc != 0) return fail(GMRM_ECUDA, "step kernel launch failed (%d): %s", rc, cudaGetErrorString(cudaGetLastError()));
         if (nlaunch) (*nlaunch)++;
@@ -667,6 +682,7 @@ static SampleParams sample_params(gmrm_engine* e, const int32_t* cols, int V, co
     p.cols = cols; p.partial = partial; p.spart = e->spart.p; p.miss_off = e->miss_off.p; p.miss_idx = e->miss_idx.p;
     p.eps = e->eps.p; p.npad = e->L.npad; p.mave = e->mave.p; p.msig = e->msig.p; p.betas = e->betas.p; p.comp = e->comp.p;
     p.group = e->group_loc.p; p.sigmag = e->sigmag.p;
+    if (e->step_pf) { p.pf_bed = e->bed.p; p.pf_col_stride = e->L.col_stride; }
     p.gc = e->gc.p; p.nonas = e->nonas.p; p.cass = e->cass.p; p.pub = e->pub.p; p.plist = own_list(e, e->xseq); p.seq = e->xseq; p.err = e->err.p; p.npublished = e->npub.p;
     return p;
 }

@@ -1,4 +1,5 @@
 // sm_100a kernels of the Gibbs marker loop (see kernels.cuh, layout.h).
+#include <algorithm>
 #include <atomic>
 #include <type_traits>
 
@@ -484,6 +485,7 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
 #define GMRM_ATICK() if (profme && nk < 60) { const long long t_ = clock64(); atomicAdd(&p.prof[nk++], (unsigned long long)(t_ - tk)); tk = t_; }
     const int tid = threadIdx.x;
     const int nr = pr.total, nq = nr * kRowBytes;       // quads of my rows
+    constexpr int kQ = NT >= 512 ? 2 : 3;               // quads a thread owns per round: 13 rows (832 quads) in ONE round for 12 warps too
     const bool xd = p.xd_world > 1;
     const int xsub = (nq + max(p.xd_world, 1) - 1) / max(p.xd_world, 1);   // quads per sub-slice (fused increment exchange)
     int tmask = 0;
@@ -514,13 +516,13 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
         seg_prefix<NT>(p, tt, S, nseg, segpre, wcnt);
         const int total = segpre[nseg];
         if (total > 0) tmask |= 1 << t;
-        for (int q0 = 0; q0 < nq; q0 += 2 * NT) {
-            double e[2][4], e0[2][4];
-            uint32_t nmask[2];                          // 0x78 in byte k: individual k is not observed -> zero entry (15 of a pair table, 3 of a single one)
-            int gq[2];                                  // global quad (byte of the column) of local quad q
-            bool have[2];
+        for (int q0 = 0; q0 < nq; q0 += kQ * NT) {
+            double e[kQ][4], e0[kQ][4];
+            uint32_t nmask[kQ];                          // 0x78 in byte k: individual k is not observed -> zero entry (15 of a pair table, 3 of a single one)
+            int gq[kQ];                                 // global quad (byte of the column) of local quad q
+            bool have[kQ];
 #pragma unroll
-            for (int qq = 0; qq < 2; qq++) {
+            for (int qq = 0; qq < kQ; qq++) {
                 const int q = q0 + qq * NT + tid;
                 have[qq] = q < nq;
                 gq[qq] = have[qq] ? global_row(pr, q >> 6) * kRowBytes + (q & 63) : 0;
@@ -557,7 +559,7 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
                     }
                     __syncthreads();
                     touched = true;
-                    if (q0 == 0 || nq > 2 * NT) {            // (re)stage: once per round unless the rows need several quad chunks
+                    if (q0 == 0 || nq > kQ * NT) {            // (re)stage: once per round unless the rows need several quad chunks
                         uint32_t mo0 = 0, mo1 = 0;           // missing-list bounds of entry `tid`, in flight with the bytes
                         if (tid < n) { const uint32_t* mo = p.pmiss_off[info[tid].nmiss_g & 15u]; mo0 = mo[info[tid].col]; mo1 = mo[info[tid].col + 1]; }
                         const int npiece = n * nr * 4;       // 16-byte pieces: entry x local row x 4
@@ -587,11 +589,11 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
                     }
                     GMRM_ATICK()   // [42] stage fill + column bytes
                     for (int g0 = 0; g0 < n; g0 += 8) {
-                        uint32_t by[8][2];
+                        uint32_t by[8][kQ];
 #pragma unroll
                         for (int j = 0; j < 8; j++)
 #pragma unroll
-                            for (int qq = 0; qq < 2; qq++) {
+                            for (int qq = 0; qq < kQ; qq++) {
                                 by[j][qq] = 0;
                                 if (g0 + j < n && have[qq]) by[j][qq] = bytes[(size_t)(g0 + j) * nq + q0 + qq * NT + tid];
                             }
@@ -604,7 +606,7 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
                         for (int j = 0; j < 8; j++) anymiss |= info[g0 + j].nmiss_g >> 4;
                         if (!anymiss) {
 #define GMRM_APPLY_PAIR(J)                                                                                          \
-    _Pragma("unroll") for (int qq = 0; qq < 2; qq++) {                                                            \
+    _Pragma("unroll") for (int qq = 0; qq < kQ; qq++) {                                                            \
         uint32_t o1, o2;                                                                                          \
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o1) : "r"(lut_u32 + by[2 * J][qq] * 4u));                   \
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(o2) : "r"(lut_u32 + by[2 * J + 1][qq] * 4u));               \
@@ -637,7 +639,7 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
             }                                                                                                     \
             __syncthreads();                                                                                      \
         }                                                                                                         \
-        _Pragma("unroll") for (int qq = 0; qq < 2; qq++) {                                                        \
+        _Pragma("unroll") for (int qq = 0; qq < kQ; qq++) {                                                        \
             if (have[qq]) {                                                                                       \
                 uint32_t off;                                                                                     \
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(off) : "r"(lut_u32 + by[J][qq] * 4u));              \
@@ -663,14 +665,14 @@ __device__ int apply_pending(const StepParams& p, const PassRows& pr, PubStage* 
             GMRM_ATICK()   // [43] apply
             if (xd) {                                   // hop 1: the increments of quad q (zeros if nothing was published) go to the GPU that owns q's sub-slice
 #pragma unroll
-                for (int qq = 0; qq < 2; qq++) {
+                for (int qq = 0; qq < kQ; qq++) {
                     if (!have[qq]) continue;
                     double* dst = p.xrecv[(q0 + qq * NT + tid) / xsub] + (((size_t)(p.row_seq & 1) * p.xd_world + p.xd_rank) * p.Ttot + tt) * p.npad + 4 * (int64_t)gq[qq];
                     st_v4_f64(dst, e[qq][0], e[qq][1], e[qq][2], e[qq][3]);
                 }
             } else if (touched) {
 #pragma unroll
-                for (int qq = 0; qq < 2; qq++) {
+                for (int qq = 0; qq < kQ; qq++) {
                     if (!have[qq]) continue;
 #pragma unroll
                     for (int k = 0; k < 4; k++) eps_t[4 * (int64_t)gq[qq] + k] = e[qq][k];
@@ -1008,6 +1010,7 @@ __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int 
 }
 
 constexpr int kStepWarps = GMRM_STEP_WARPS, kStepThreads = kStepWarps * 32;
+constexpr int kDirectMax = GMRM_STEP_DIRECT;   // direct rows per pass the kernel is built for (registers: 32 per row and thread)
 constexpr int kPairs = kBatch / 2;
 
 // L2 prefetch of this warp's first two batches of a pass (rows [row0, row0+nr) of their 16 columns each): issued
@@ -1049,8 +1052,32 @@ __device__ __forceinline__ void load_words(const uint8_t* pa, const uint8_t* pb,
     }
 }
 
-template <int NR, int T>
-__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc) {
+// DIRECT rows (ND > 0, one trait): rows of the pass that get no table.  Their genotypes come from a second copy kept in plain
+// 2-bit dosage fields (StepParams::bed2), their residuals sit in registers -- lane l holds the 16 individuals of word l,
+// pre-scaled -- and every genotype costs one byte permute plus one fp64 multiply-add on pipes the look-ups leave idle:
+//   m_f = word & (0x03030303 << 2f)   isolates the fields f, f+4, f+8, f+12 in the four bytes (value d << 2f),
+//   PRMT moves byte b of m_f into the low word of a double whose high word is 0: the denormal  d * 2^(2f) * 2^-1074,
+//   DFMA with the weight  eps * 2^(kDirScale - 2f)  adds  d * eps * 2^(kDirScale - 1074)  exactly as  acc += d * eps  would
+// (power-of-two scalings only), and the batch's direct sums are scaled back by 2^(1074 - kDirScale) when they join the
+// look-up sums.  Missing genotypes are dosage 0 in both copies, residuals of unobserved individuals are 0.
+constexpr int kDirScale = 960;
+// D keeps its (zero) high word; its low word becomes byte B of m: the permute writes straight into the register pair
+template <int B>
+__device__ __forceinline__ void dir_operand(double& D, uint32_t m) {
+    asm("{\n\t.reg .b32 lo, hi;\n\tmov.b64 {lo, hi}, %0;\n\tprmt.b32 lo, %1, 0, %2;\n\tmov.b64 %0, {lo, hi};\n\t}" : "+d"(D) : "r"(m), "n"(0x4440 | B));
+}
+template <int F>
+__device__ __forceinline__ void dir_fields(uint32_t w, const double (&wt)[16], double (&D)[4], double& acc) {   // fields F, F+4, F+8, F+12 of the word
+    const uint32_t m = w & (0x03030303u << (2 * F));
+    dir_operand<0>(D[0], m); acc = fma(D[0], wt[F], acc);
+    dir_operand<1>(D[1], m); acc = fma(D[1], wt[4 + F], acc);
+    dir_operand<2>(D[2], m); acc = fma(D[2], wt[8 + F], acc);
+    dir_operand<3>(D[3], m); acc = fma(D[3], wt[12 + F], acc);
+}
+
+template <int NR, int T, int ND = 0>
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc, int dslot = 0) {
+    static_assert(ND == 0 || T == 1, "direct rows: one trait");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
     const uint32_t low = (uint32_t)l16 * 8u;
@@ -1066,6 +1093,26 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
     const int d_b = chunk_offset(NR, NR - 1, l16, 0) - chunk_offset(NR, 0, l16, 0);    // the odd slot (NR 3, 5) behind the wide group
     const uint32_t nrows = (uint32_t)p.nrows, row0u = (uint32_t)row0;
     const int32_t* ccols = p.cols + v0;
+    // direct rows: word l16 of row d of the second copy, weights of its 16 individuals
+    // a zero neither compiler stage can fold (a launch parameter): the operands' high words live in registers instead of
+    // being re-created by a move in front of every multiply-add
+    [[maybe_unused]] const double dzero = __hiloint2double((int)p.zero, (int)p.zero);
+    [[maybe_unused]] const uint8_t* lane_d = nullptr;
+    [[maybe_unused]] double wt[ND > 0 ? ND : 1][16];
+    if constexpr (ND > 0) {
+        lane_d = p.bed2 + (int64_t)dslot * kRowBytes + l16 * 4;
+        asm volatile("" : "+l"(lane_d));
+#pragma unroll
+        for (int d = 0; d < ND; d++) {
+            const double* e = p.eps + (int64_t)p.t0 * p.npad + ((int64_t)(row0 + NR + d) * kRowInd + 16 * l16);
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(e + j));
+                wt[d][j] = scalbn(v.x, kDirScale - 2 * (j & 3));
+                wt[d][j + 1] = scalbn(v.y, kDirScale - 2 * ((j + 1) & 3));
+            }
+        }
+    }
 
     // raw column index (may be -1: no marker); the clamp is applied where the value is USED -- clamping here would make
     // the warp wait for this load at once instead of a batch later (measured: 17 % of the stream's stall samples)
@@ -1073,11 +1120,16 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         const int v = bb * kBatch + (l16 & (kBatch - 1));
         return (bb < nb && v < Vc) ? ccols[v] : 0;
     };
-    uint32_t WA[kPairs][NR], WB[kPairs][NR];
-    auto load_pair = [&](int col, int i, uint32_t (&dst)[kPairs][NR]) {      // col: the pair's column for this half-warp (raw)
+    uint32_t WA[kPairs][NR + ND], WB[kPairs][NR + ND];
+    auto load_pair = [&](int col, int i, uint32_t (&dst)[kPairs][NR + ND]) {      // col: the pair's column for this half-warp (raw)
         const uint32_t r = (uint32_t)max(col, 0) * nrows + row0u;
         const uint8_t* pa = lane_a + (uint64_t)r * kRowBytes;
-        load_words<NR>(pa, pa + d_b, dst[i]);
+        load_words<NR>(pa, pa + d_b, reinterpret_cast<uint32_t(&)[NR]>(dst[i]));
+        if constexpr (ND > 0) {
+            const uint8_t* pd = lane_d + (uint64_t)((uint32_t)max(col, 0) * (uint32_t)p.drows) * kRowBytes;
+#pragma unroll
+            for (int d = 0; d < ND; d++) dst[i][NR + d] = ldg_stream_u32(pd + d * kRowBytes);
+        }
     };
     {
         const int c0 = loadcols(b);
@@ -1098,7 +1150,7 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
 
     // one batch: look-ups on W while the warp's next batch (if there is one: `more`, a compile-time flag -- predicated loads
     // into Wn cost a register copy each) is loaded into Wn
-    auto batch = [&](int bb, uint32_t (&W)[kPairs][NR], uint32_t (&Wn)[kPairs][NR], auto more_c) {
+    auto batch = [&](int bb, uint32_t (&W)[kPairs][NR + ND], uint32_t (&Wn)[kPairs][NR + ND], auto more_c) {
         constexpr bool more = decltype(more_c)::value;
         const int cnow = cn;
         if constexpr (more) cn = loadcols(bb + 2 * kStepWarps);
@@ -1108,10 +1160,14 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
             pcol = loadcols(bb + (kPfAhead + 1) * kStepWarps);
         }
         double acc[kPairs][T];
+        [[maybe_unused]] double accd[kPairs];
+        [[maybe_unused]] double Dop[4] = {dzero, dzero, dzero, dzero};   // multiplier operands: high words stay 0
 #pragma unroll
-        for (int i = 0; i < kPairs; i++)
+        for (int i = 0; i < kPairs; i++) {
+            accd[i] = 0.0;
 #pragma unroll
             for (int t = 0; t < T; t++) acc[i][t] = 0.0;
+        }
 
         // the loads of the next batch are spread over the first look-up groups (a burst of loads at the top of a batch
         // filled the load/store queue in front of the other warps' look-ups)
@@ -1125,9 +1181,25 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
             if constexpr (more) load_pair(c_, G, Wn);                         \
         }                                                                     \
     }
+        // direct work is dealt out between the look-up groups: every (NR / ND)-th group is followed by one of the ND * 4 field
+        // groups of the direct rows (4 per row: fields F, F+4, F+8, F+12 of every pair's word)
+#define GMRM_DIRECT(G_)                                                                           \
+    if constexpr (ND > 0) {                                                                       \
+        constexpr int kEvery = NR / ND > 0 ? NR / ND : 1, D_ = (G_) / kEvery;                     \
+        if constexpr ((G_) % kEvery == 0 && D_ < ND * 4) {                                        \
+            _Pragma("unroll") for (int i = 0; i < kPairs; i++)                                    \
+                dir_fields<D_ & 3>(W[i][NR + (D_ >> 2)], wt[D_ >> 2], Dop, accd[i]);              \
+        }                                                                                         \
+    }
 #define GMRM_ROW(RR)                                                          \
-    if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_LOOKUP(RR, 1) GMRM_LOOKUP(RR, 2) GMRM_LOOKUP(RR, 3) }
+    if constexpr (RR < NR) { GMRM_LOOKUP(RR, 0) GMRM_DIRECT(RR * 4 + 0) GMRM_LOOKUP(RR, 1) GMRM_DIRECT(RR * 4 + 1) \
+                             GMRM_LOOKUP(RR, 2) GMRM_DIRECT(RR * 4 + 2) GMRM_LOOKUP(RR, 3) GMRM_DIRECT(RR * 4 + 3) }
         GMRM_ROW(0) GMRM_ROW(1) GMRM_ROW(2) GMRM_ROW(3) GMRM_ROW(4)
+#undef GMRM_DIRECT
+        if constexpr (ND > 0) {
+#pragma unroll
+            for (int i = 0; i < kPairs; i++) acc[i][0] = fma(accd[i], 0x1p114, acc[i][0]);       // 2^(1074 - kDirScale)
+        }
 #undef GMRM_ROW
 #undef GMRM_LOOKUP
         if constexpr (NR * 4 < kPairs) {                  // fewer look-up groups than pairs (NR == 1, batches of 16)
@@ -1266,12 +1338,34 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     for (int t = 0; t < T; t++) es[t] = 0.0;
     bool flushed = false;                                 // chunked steps: the global slots hold the sums of earlier passes
     for (int pass = 0; pass < npass; pass++) {
-        const int r_lo = pr.start[pass], nrp = pr.count[pass];
+        // rows of the pass beyond the table slots are DIRECT rows (hybrid plan, one trait): no table, genotypes from bed2
+        // hybrid plan (one trait): the LAST row of a pass of two or more rows is a DIRECT row: no table, genotypes from bed2
+        const int r_lo = pr.start[pass], nall = pr.count[pass], ndp = (kDirectMax >= 1 && T == 1 && p.ndir > 0 && nall >= 2) ? 1 : 0, nrp = nall - ndp;
+        const int dslot = pass * nsm + cta;
         build_tables<T, NT>(p, r_lo, nrp, es);
+        if (ndp > 0) {                                    // the direct rows' share of sum eps (their tables would have added it)
+            for (int i = tid; i < ndp * kRowBytes; i += NT) {
+                const double* e = p.eps + (int64_t)p.t0 * p.npad + ((int64_t)(r_lo + nrp) * kRowBytes + i) * 4;
+                const double2 a = __ldcg(reinterpret_cast<const double2*>(e)), b = __ldcg(reinterpret_cast<const double2*>(e + 2));
+                es[0] += (a.x + a.y) + (b.x + b.y);
+            }
+        }
         __syncthreads();
         GMRM_TICK()                                       // [9 + 3*pass] sync + build
         for (int v0 = 0; v0 < p.V; v0 += Vc_max) {
             const int Vc = min(Vc_max, p.V - v0);
+            if constexpr (T == 1 && kDirectMax >= 1) {
+                if (ndp == 1) {
+                    switch (nrp) {
+                    case 1: stream_rows<1, 1, 1>(p, r_lo, part, v0, Vc, dslot); break;
+                    case 2: stream_rows<2, 1, 1>(p, r_lo, part, v0, Vc, dslot); break;
+                    case 3: stream_rows<3, 1, 1>(p, r_lo, part, v0, Vc, dslot); break;
+                    case 4: stream_rows<4, 1, 1>(p, r_lo, part, v0, Vc, dslot); break;
+                    default: break;
+                    }
+                }
+            }
+            if (ndp == 0)
             switch (nrp) {
             case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc); break;
             case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc); break;
@@ -1280,7 +1374,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
             case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc); break;
             default: break;
             }
-            if (chunked && nrp > 0) {                     // this chunk's sums of this pass -> the CTA's global slots
+            if (chunked && nall > 0) {                    // this chunk's sums of this pass -> the CTA's global slots
                 __syncthreads();
                 for (int i = tid; i < Vc * T; i += NT) {
                     const int v = v0 + i / T, t = i % T;
@@ -1291,7 +1385,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
                 __syncthreads();
             }
         }
-        if (chunked && nrp > 0) flushed = true;
+        if (chunked && nall > 0) flushed = true;
         GMRM_TICK()                                       // [10 + 3*pass] this warp's streaming
         if (p.pf && pass + 1 < npass && pr.count[pass + 1] > 0) prefetch_pass_head(p, pr.start[pass + 1], pr.count[pass + 1]);
         if (pass + 1 < npass) __syncthreads();            // everyone is done with these tables
@@ -1320,6 +1414,33 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 #undef GMRM_TICK
 }
 // [step-end]
+
+// [direct-begin]
+// Second copy of the DIRECT rows (hybrid plan of the step kernel, StepParams::bed2): the row that closes the range of (pass,
+// cta) in plain 2-bit dosage fields (missing = 0, as in the base-3 copy), [marker][npass * nsm slots][64 bytes].
+__global__ void direct_plane_kernel(const uint8_t* __restrict__ plink, int nmark, Layout L, int npass, uint8_t* __restrict__ dst) {
+    const int slot = blockIdx.x, q = slot / L.nsm, c = slot - q * L.nsm;
+    __shared__ int srow;
+    if (threadIdx.x == 0) {
+        int start[kMaxPasses], count[kMaxPasses];
+        all_pass_rows(L.nrows, npass, L.nsm, c, start, count);
+        srow = count[q] >= 2 ? start[q] + count[q] - 1 : -1;
+    }
+    __syncthreads();
+    const int row = srow;
+    if (row < 0) return;                                       // a pass of fewer than two rows has no direct row
+    const int64_t drows = (int64_t)npass * L.nsm;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < (int64_t)nmark * kRowBytes; i += (int64_t)gridDim.y * blockDim.x) {
+        const int64_t j = i >> 6, o = (int64_t)row * kRowBytes + (i & 63);
+        uint8_t v = 0;
+        if (o < L.mbytes) {
+            uint32_t mm;
+            v = (uint8_t)tri_to_fields(plink_to_tri(plink[j * L.mbytes + o], &mm));
+        }
+        dst[(j * drows + slot) * kRowBytes + (i & 63)] = v;
+    }
+}
+// [direct-end]
 
 // =====================================================================================
 // K2: one warp per virtual rank: finish the dot product, sample, publish.
@@ -1480,6 +1601,8 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
     pdl_wait();                                              // the step kernel's partial sums are complete and visible
     double lam = 0.0, mave = 0.0;
     if (v < p.V) sample_one(p, v, lane, col, lam, mave);
+    if (p.pf_bed != nullptr && __ballot_sync(0xffffffffu, lam != 0.0) != 0u && lane == 0 && col >= 0)   // published: its column is needed again in a few microseconds
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_bed + (int64_t)col * p.pf_col_stride), "r"((uint32_t)p.pf_col_stride) : "memory");
     if (lane < p.T) { s_lam[lane][warp] = lam; s_mave[lane][warp] = mave; }
     if (lane == 0) s_col[warp] = col;
     __syncthreads();
@@ -1627,6 +1750,11 @@ void launch_transcode(const uint8_t* plink, int nmark, const Layout& L, uint8_t*
     if (nmark <= 0) return;
     dim3 grid((unsigned)((L.col_stride + 255) / 256), (unsigned)nmark);
     transcode_kernel<<<grid, 256, 0, s>>>(plink, nmark, L, dst, miss_counts);
+}
+void launch_direct_plane(const uint8_t* plink, int nmark, const Layout& L, int npass, uint8_t* dst, cudaStream_t s) {
+    if (nmark <= 0 || npass <= 0) return;
+    dim3 grid((unsigned)(npass * L.nsm), (unsigned)std::min(64, (nmark * kRowBytes + 255) / 256));
+    direct_plane_kernel<<<grid, 256, 0, s>>>(plink, nmark, L, npass, dst);
 }
 void launch_fill_missing(const uint8_t* plink, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s) {
     if (nmark <= 0) return;

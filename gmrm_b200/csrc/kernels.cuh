@@ -10,15 +10,19 @@
 
 namespace gmrm {
 
-// Step-kernel shape: (32 warps, batches of 8 markers, 64 registers) or (16 warps, batches of 16, 128 registers)
+// Step-kernel shape: 16 warps of 128 registers, batches of 8 markers.  (Measured alternatives, tools/build_variant.sh: 12 and 14
+// warps with more registers run the stream at the same speed; the hybrid plan below needs <= 12 warps for its registers.)
 #ifndef GMRM_STEP_WARPS
 #define GMRM_STEP_WARPS 16
 #endif
 #ifndef GMRM_STEP_BATCH
 #define GMRM_STEP_BATCH 8
 #endif
-#ifndef GMRM_STEP_DEPTH
-#define GMRM_STEP_DEPTH 1
+// Direct rows per pass the step kernel is built for (0: look-ups only -- the product build; 1: the hybrid plan, see
+// StepParams::bed2 -- parity-tested on the GPU but 14 % SLOWER than look-ups alone at N = 458,000 (profiles/README.md), kept as
+// a build variant: tools/build_variant.sh h12 -DGMRM_STEP_WARPS=12 -DGMRM_STEP_DIRECT=1)
+#ifndef GMRM_STEP_DIRECT
+#define GMRM_STEP_DIRECT 0
 #endif
 // Per-marker partial sums of a step live in shared memory, kPartSmemDoubles of them (16 KB next to the full set of table
 // slots); a step of more (marker, trait) pairs is streamed in chunks of that size per pass, each chunk's sums being added to
@@ -97,6 +101,12 @@ struct StepParams {
     double* delta;           // [Ttot][npad] or nullptr: increments applied since the last exchange (multi-GPU)
     const double* merge_tot; // [Ttot][npad] or nullptr: all-reduced deltas of the last exchange, still to be merged: every CTA first
                              // adds (merge_tot - delta) to its rows of eps and clears delta (the merge kernel, fused)
+    // Hybrid plan (ndir = 1, one trait): the LAST row of every pass of two or more rows is a DIRECT row -- no table; its
+    // genotypes are read from a second copy in plain 2-bit dosage fields, bed2 [column][drows = npass * nsm][64 bytes], row
+    // slot pass * nsm + cta, and decoded on the fp64 / integer pipes while the look-ups keep the shared-memory pipe busy.
+    const uint8_t* bed2;
+    int32_t drows, ndir;
+    uint32_t zero;           // 0 (see stream_rows)
     int32_t* err;
     int32_t pf;              // 1: L2 prefetch ahead of the streaming loads
     int32_t pdl;             // host side: launch with the programmatic-serialization attribute (the prologue overlaps the previous kernel)
@@ -133,6 +143,10 @@ struct SampleParams {
     // peer-memory exchange (world > 1): every CTA also stores its segments into every peer's buffer over NVLink
     int32_t world, rank;
     double* peer_list[kMaxGpus];                 // where GPU g wants THIS GPU's list (nullptr: no exchange)
+    // L2 prefetch of a published marker's column (it was streamed a step ago and has mostly left L2): the next step kernel's
+    // update phase then finds its bytes in L2 instead of waiting for HBM.  nullptr: off
+    const uint8_t* pf_bed;
+    int64_t pf_col_stride;
     unsigned long long seq;                      // sequence number of this step, written into the segment headers
     const double* rep_u;     // replay: [Mm][R][T] or nullptr
     const double* rep_z;
@@ -144,6 +158,8 @@ struct SampleParams {
 // launchers (kernels.cu)
 void launch_transcode(const uint8_t* plink, int nmark, const Layout& L, uint8_t* dst, uint32_t* miss_counts, cudaStream_t s);
 void launch_fill_missing(const uint8_t* plink, int nmark, const Layout& L, const uint32_t* off, uint32_t* idx, cudaStream_t s);
+// hybrid plan: the second (2-bit) copy of the direct rows of `nmark` staged PLINK columns, dst [nmark][npass * nsm][64]
+void launch_direct_plane(const uint8_t* plink, int nmark, const Layout& L, int npass, uint8_t* dst, cudaStream_t s);
 void launch_untranscode(const uint8_t* bed, int nmark, const Layout& L, const uint32_t* miss_off, const uint32_t* miss_idx,
                         uint8_t* plink_out, cudaStream_t s);
 void launch_decode_column(const uint8_t* col, const Layout& L, const uint32_t* miss_idx, uint32_t nmiss, double* a, double* b, cudaStream_t s);

@@ -74,6 +74,9 @@ def _translate(instr, outs, ins):
     if i.startswith("ld.global.nc.L1::no_allocate.v2.u32"):
         return ("{ const uint32_t* emu_t_ = reinterpret_cast<const uint32_t*>(" + ins[0] + "); "
                 f"{outs[0]} = emu_t_[0]; {outs[1]} = emu_t_[1]; }}")
+    if i.startswith("{") and "prmt.b32 lo, %1, 0, %2" in i:    # direct rows: low word of the double <- one byte of m, high word kept
+        return ("{ uint64_t emu_r_; memcpy(&emu_r_, &(" + outs[0] + "), 8); "
+                f"emu_r_ = (emu_r_ & 0xffffffff00000000ull) | emu_prmt({ins[0]}, 0u, {ins[1]}); memcpy(&({outs[0]}), &emu_r_, 8); }}")
     if i.startswith("st.global.v4.f64"):                     # 32-byte store, word by word (no atomicity of the whole is assumed)
         return ("{ volatile double* emu_t_ = reinterpret_cast<volatile double*>(" + ins[0] + "); "
                 f"emu_t_[0] = {ins[1]}; emu_t_[1] = {ins[2]}; emu_t_[2] = {ins[3]}; emu_t_[3] = {ins[4]}; }}")

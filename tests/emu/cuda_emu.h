@@ -40,6 +40,7 @@ inline double2 make_double2(double x, double y) { return double2{x, y}; }
 inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 inline double __longlong_as_double(long long v) { double d; memcpy(&d, &v, 8); return d; }
+inline double __hiloint2double(int hi, int lo) { const uint64_t r = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; memcpy(&d, &r, 8); return d; }
 inline double __shfl_xor_sync(unsigned, double v, int o) {
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     emu_warp_buf[warp * 32 + lane] = v;

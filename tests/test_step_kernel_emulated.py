@@ -28,12 +28,13 @@ EMU = os.path.join(ROOT, "tests", "emu")
 TAIL = r'''
 extern "C" int emu_step(const uint8_t* bed, int N, int nsm, const int32_t* cols, int V, double* eps, const uint8_t* mask4, int T,
                         int tc, int rpp, int npass, double* partial, double* spart, const double* plist, int pV,
-                        const uint32_t* miss_off, const uint32_t* miss_idx) {
+                        const uint32_t* miss_off, const uint32_t* miss_idx, const uint8_t* bed2) {
     using namespace gmrm;
     const Layout L = make_layout(N, nsm);
     int32_t err = 0;
     for (int t0 = 0; t0 < T; t0 += tc) {
         StepParams q{};
+        if (bed2 && T == 1) { q.bed2 = bed2; q.drows = npass * nsm; q.ndir = 1; }   // hybrid plan: last row of a pass is a direct row
         q.bed = bed; q.col_stride = L.col_stride; q.nrows = L.nrows; q.cols = cols; q.V = V; q.eps = eps; q.npad = L.npad;
         q.Ttot = T; q.t0 = t0; q.rows_per_pass = rpp; q.npass = npass; q.partial = partial; q.spart = spart;
         q.mask4 = mask4; q.pV = pV; q.err = &err; q.pf = 1;
@@ -106,7 +107,10 @@ def emu(tmp_path_factory):
     so = d / "libstep_emu.so"
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-shared", "-Wall", "-Wno-unknown-pragmas",
                     "-Wno-unused-variable", "-Wno-unused-but-set-variable", "-I", os.path.join(EMU, "fake_cuda"), "-I", EMU,
-                    "-I", os.path.join(ROOT, "gmrm_b200", "csrc"), str(cpp), "-o", str(so)], check=True)
+                    "-I", os.path.join(ROOT, "gmrm_b200", "csrc"),
+                    # the build variant with the hybrid plan compiled in (12 warps, one direct row per pass); the cases without a
+                    # second genotype copy run the look-up-only path of the same source, as the product build (16 warps) does
+                    "-DGMRM_STEP_WARPS=12", "-DGMRM_STEP_DIRECT=1", str(cpp), "-o", str(so)], check=True)
     return C.CDLL(str(so))
 
 
@@ -115,9 +119,10 @@ def dosages(bed, N):
     return np.where(codes == 0, 2.0, np.where(codes == 2, 1.0, 0.0)).reshape(bed.shape[0], -1)[:, :N]
 
 
-@pytest.mark.parametrize("N,nsm,T,M,na,miss", [(777, 1, 3, 33, 0.02, 0.01), (1795, 2, 2, 40, 0.0, 0.02), (5119, 1, 1, 50, 0.01, 0.0),
-                                               (3000, 3, 1, 21, 0.03, 0.03), (1024, 1, 4, 18, 0.0, 0.0)])
-def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M, na, miss):
+@pytest.mark.parametrize("N,nsm,T,M,na,miss,hybrid", [(777, 1, 3, 33, 0.02, 0.01, False), (1795, 2, 2, 40, 0.0, 0.02, False), (5119, 1, 1, 50, 0.01, 0.0, False),
+                                                      (3000, 3, 1, 21, 0.03, 0.03, False), (1024, 1, 4, 18, 0.0, 0.0, False),
+                                                      (5119, 1, 1, 50, 0.01, 0.0, True), (3000, 3, 1, 21, 0.03, 0.03, True), (8000, 2, 1, 19, 0.02, 0.01, True)])
+def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M, na, miss, hybrid):
     d = synth.write_dataset(str(tmp_path), N=N, M=M, n_traits=T, n_groups=1, na_rate=na, missing_rate=miss, seed=N % 71)
     pp = d["paths"]
     inp = oracle.load_inputs(pp["bed"], pp["dim"], pp["phen"], pp["gri"], pp["grm"])
@@ -132,13 +137,26 @@ def test_emulated_step_kernel_matches_oracle(emu, oracle, tmp_path, N, nsm, T, M
 
     def launch(cols, plist=None, pV=0):
         V = len(cols)
-        plan = api.step_plan(N, nsm, V, T, want_ranges=False)
+        plan = api.step_plan(N, nsm, V, T, want_ranges=hybrid)
         assert plan is not None
+        bed2 = None
+        if hybrid and V:             # second copy of the direct rows (engine: direct_plane_kernel): 2-bit dosage fields, missing = 0
+            codes = (inp["bed"][:, :, None] >> (2 * np.arange(4))) & 3
+            fields = (np.where(codes == 0, 2, np.where(codes == 2, 1, 0)) << (2 * np.arange(4))).sum(axis=2).astype(np.uint8)
+            padded = np.zeros((M, stride), dtype=np.uint8)
+            padded[:, : fields.shape[1]] = fields
+            npass = plan["npass"]
+            bed2 = np.zeros((M, npass * nsm, 64), dtype=np.uint8)
+            for q in range(npass):
+                for c in range(nsm):
+                    start, count = plan["ranges"][q][c]
+                    if count >= 2:
+                        bed2[:, q * nsm + c, :] = padded[:, (start + count - 1) * 64: (start + count) * 64]
         cols_a = np.ascontiguousarray(cols, dtype=np.int32) if V else np.zeros(1, np.int32)
         partial = np.full((max(V, 1), T, nsm), np.nan)
         spart = np.full((T, nsm), np.nan)
         rc = emu.emu_step(p(tri), N, nsm, p(cols_a), V, p(eps), p(mask4), T, plan["traits_per_launch"], plan["rows_per_pass"],
-                          plan["npass"], p(partial), p(spart), p(plist), pV, p(miss_off), p(miss_idx))
+                          plan["npass"], p(partial), p(spart), p(plist), pV, p(miss_off), p(miss_idx), p(bed2))
         assert rc == 0
         return partial, spart
 
@@ -272,7 +290,7 @@ def test_emulated_step_kernel_with_partial_sums_in_global_memory(emu, oracle, tm
     partial = np.full((V, T, nsm), np.nan)
     spart = np.full((T, nsm), np.nan)
     rc = emu.emu_step(p(tri), N, nsm, p(cols), V, p(eps), p(mask4), T, plan["traits_per_launch"], plan["rows_per_pass"],
-                      plan["npass"], p(partial), p(spart), None, 0, p(miss_off), p(miss_idx))
+                      plan["npass"], p(partial), p(spart), None, 0, p(miss_off), p(miss_idx), None)
     assert rc == 0
     ok = cols >= 0
     for t in range(T):
