@@ -299,27 +299,19 @@ def run_ours(args):
         dev_ms.append(tm["iteration_ms"])
         launches += tm["launches"]; pub_timed.append(tm["published"])
     barrier()
-    # K further iterations with 2 CUDA events per step around the step kernel: the live launch duration behind `roofline`
-    # (events between the launches switch the programmatic overlap of consecutive kernels off, hence not the K above)
-    e.set_timing_detail(1)
-    for _ in range(args.steps):
-        it += 1
-        e.run_iteration(it)
-        tm = e.timing()
-        dot_ms.append(tm["dot_kernel_ms"]); dev1_ms.append(tm["iteration_ms"])
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    # diagnostic pass (not part of the K timed steps): one iteration with every phase bracketed by events and the
-    # residual update of every step as its own launch, so that dot-only and update-only times are seen
-    e.set_timing_detail(2)
-    it += 1
-    e.run_iteration(it)
-    tm2 = e.timing()
-    e.set_timing_detail(0)
     ms_per_step = maxreduce(sum(dev_ms) / len(dev_ms))
     # ---- e2e: the call a user makes per iteration -- run it, then read the iteration's outputs back to the
     # host (what the reference writes to .bet/.cpn/.csv, bayes.cpp:659-669); host wall clock, max over ranks.
     # Everything is read through the staged path: device snapshot, pinned D2H on a second stream, fetched one iteration later.
+    # one untimed pass of the same call sequence first: the staging buffers (pinned host memory, device snapshots, copy
+    # stream) are allocated on first use -- set-up, like the chain's own warm-up iterations
+    it += 1
+    e.run_iteration_async(it)
+    e.wait_iteration()
+    e.stage_outputs()
+    for t in range(T):
+        e.fetch_outputs(t)
+    e.fetch_state()
     barrier()
     t1 = time.perf_counter()
     d2h = 0
@@ -342,6 +334,24 @@ def run_ours(args):
     d2h += sum(v.nbytes for v in st.values())
     barrier()
     e2e_s = maxreduce((time.perf_counter() - t1) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    # (the diagnostic passes below come after both timed regions, so that the two see the chain at neighbouring iterations)
+    # K further iterations with 2 CUDA events per step around the step kernel: the live launch duration behind `roofline`
+    # (events between the launches switch the programmatic overlap of consecutive kernels off, hence not the K above)
+    e.set_timing_detail(1)
+    for _ in range(args.steps):
+        it += 1
+        e.run_iteration(it)
+        tm = e.timing()
+        dot_ms.append(tm["dot_kernel_ms"]); dev1_ms.append(tm["iteration_ms"])
+    barrier()
+    # diagnostic pass (not part of the K timed steps): one iteration with every phase bracketed by events and the
+    # residual update of every step as its own launch, so that dot-only and update-only times are seen
+    e.set_timing_detail(2)
+    it += 1
+    e.run_iteration(it)
+    tm2 = e.timing()
+    e.set_timing_detail(0)
     pub_warm = [sumreduce(x) for x in pub_warm]
     pub_timed = [sumreduce(x) for x in pub_timed]
 

@@ -134,7 +134,7 @@ struct gmrm_engine {
     bool out_pending = false;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
     DevBuf<double> eps, mave, msig, betas, cva, cvai, partial, spart, bsq, esq, sigmag, sigmae, pi, mu, mu_old;
-    DevBuf<double> delta, delta_tot, gc;
+    DevBuf<double> delta, delta_tot, gc, bsq_part;
     DevBuf<int32_t> comp, group_loc, mtotgrp, steptab, cass, m0, nonas, err, tmp_cols;
     DevBuf<uint32_t> miss_off, miss_idx, miss_cnt;
     // individuals without a phenotype, per trait (what the marker statistics take out of the whole-column dosage counts)
@@ -293,7 +293,7 @@ int gmrm_create(const gmrm_config* c, gmrm_engine** out) {
     A(e->spart.alloc((size_t)T * L.nsm));
     A(e->pub.alloc((size_t)e->Vl * T));
     A(e->cass.alloc((size_t)T * G * K)); A(e->m0.alloc((size_t)T * G));
-    A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T));
+    A(e->bsq.alloc((size_t)T * G)); A(e->esq.alloc(T)); A(e->bsq_part.alloc((size_t)beta_sq_scratch_doubles(T, G)));
     A(e->sigmag.alloc((size_t)T * G)); A(e->sigmae.alloc(T)); A(e->pi.alloc((size_t)T * G * K));
     A(e->mu.alloc(T)); A(e->mu_old.alloc(T)); A(e->nonas.alloc(T)); A(e->gc.alloc((size_t)T * G * 4 * K));
     A(e->err.alloc(1)); A(e->npub.alloc(1));
@@ -1085,7 +1085,7 @@ int gmrm_run_iteration_async(gmrm_engine* e, int32_t it, const gmrm_replay* rp) 
     CU(cudaEventRecord(e->ev[2], s));
 
     // ---- epilogue (bayes.cpp:562-651)
-    launch_beta_sq(e->betas.p, e->group_loc.p, e->Mloc, T, G, e->bsq.p, s);
+    launch_beta_sq(e->betas.p, e->group_loc.p, e->Mloc, T, G, e->bsq.p, e->bsq_part.p, s);
     if (multi) {   // Allreduce of beta_sqn and cass (bayes.cpp:575-588)
         NC(g_nccl.AllReduce(e->bsq.p, e->bsq.p, (size_t)T * G, kNcclFloat64, kNcclSum, e->comm, s));
         NC(g_nccl.AllReduce(e->cass.p, e->cass.p, (size_t)T * G * K, kNcclInt32, kNcclSum, e->comm, s));

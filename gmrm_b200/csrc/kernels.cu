@@ -1687,6 +1687,37 @@ __global__ void __launch_bounds__(256) beta_sq_kernel(const double* __restrict__
     }
 }
 
+// The same sum for large shards in two levels (one CTA per trait took ~1 ms per iteration at 10^6 markers): CTA (t, b) sums
+// slice b of the markers per group, a second launch adds the slices in order.  Fixed slicing: reproducible.
+constexpr int kBsqSlices = 128;
+__global__ void __launch_bounds__(256) beta_sq_part_kernel(const double* __restrict__ betas, const int32_t* __restrict__ group,
+                                                           int Mloc, int G, double* __restrict__ part /* [T][kBsqSlices][G] */) {
+    extern __shared__ double acc[];                  // [G][256]
+    const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    for (int g = 0; g < G; g++) acc[g * 256 + tid] = 0.0;
+    const int per = (Mloc + kBsqSlices - 1) / kBsqSlices, j0 = b * per, j1 = min(Mloc, j0 + per);
+    for (int j = j0 + tid; j < j1; j += 256) {
+        const double x = betas[(int64_t)t * Mloc + j];
+        acc[group[j] * 256 + tid] += x * x;
+    }
+    __syncthreads();
+    for (int g = 0; g < G; g++) {
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) acc[g * 256 + tid] += acc[g * 256 + tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) part[((int64_t)t * kBsqSlices + b) * G + g] = acc[g * 256];
+    }
+}
+__global__ void beta_sq_final_kernel(const double* __restrict__ part, int T, int G, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= T * G) return;
+    const int t = i / G, g = i - t * G;
+    double s = 0.0;
+    for (int b = 0; b < kBsqSlices; b++) s += part[((int64_t)t * kBsqSlices + b) * G + g];
+    out[i] = s;
+}
+
 // sigmaE start value, Phenotype::update_epsilon_sigma (phenotype.cpp:448-457)
 __global__ void init_sigmae_kernel(const double* esq, const int32_t* nonas, int T, double* sigmae) {
     const int t = threadIdx.x;
@@ -1907,8 +1938,16 @@ void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int mar
     if (n <= 0) return;
     steptab_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tab, Mm, Vl, r0, R, Mt, marker_begin, shuffle, seed, it, rep_perm);
 }
-void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, cudaStream_t s) {
+int beta_sq_scratch_doubles(int T, int G) { return T * kBsqSlices * G; }
+void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, double* scratch, cudaStream_t s) {
     const int smem = G * 256 * (int)sizeof(double);
+    if (scratch != nullptr && Mloc >= 4096) {                 // two levels for shards of any size worth it
+        static std::atomic<int> have2[kMaxDevices];
+        if (smem > 48 * 1024) ensure_dyn_smem(beta_sq_part_kernel, have2, smem);
+        beta_sq_part_kernel<<<dim3((unsigned)T, kBsqSlices), 256, smem, s>>>(betas, group, Mloc, G, scratch);
+        beta_sq_final_kernel<<<(T * G + 127) / 128, 128, 0, s>>>(scratch, T, G, out);
+        return;
+    }
     static std::atomic<int> have[kMaxDevices];
     if (smem > 48 * 1024) ensure_dyn_smem(beta_sq_kernel, have, smem);
     beta_sq_kernel<<<T, 256, smem, s>>>(betas, group, Mloc, G, out);

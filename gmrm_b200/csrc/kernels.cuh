@@ -185,7 +185,8 @@ void launch_sample(const SampleParams& p, cudaStream_t s);
 void launch_finish_dots(const SampleParams& p, double* out, cudaStream_t s);
 void launch_steptab(int32_t* tab, int Mm, int Vl, int r0, int R, int Mt, int marker_begin, int shuffle,
                     uint32_t seed, int it, const int32_t* rep_perm, cudaStream_t s);
-void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, cudaStream_t s);
+int beta_sq_scratch_doubles(int T, int G);
+void launch_beta_sq(const double* betas, const int32_t* group, int Mloc, int T, int G, double* out, double* scratch, cudaStream_t s);
 
 struct GlobalDrawParams {
     int32_t T, G, K, N, it;
