@@ -430,9 +430,9 @@ __device__ __forceinline__ void seg_prefix(const StepParams& p, int tt, int S, i
             unsigned long long w = *h;
             for (uint32_t spins = 0; (w >> 8) != p.wait_seq; ++spins) {
                 __nanosleep(100);
-                // a lost peer must surface as an error, not as a hung GPU; the bound (>= 27 s) has to cover honest skew
+                // a lost peer must surface as an error, not as a hung GPU; the bound (some 40 s of polling) has to cover honest skew
                 // between the processes (first-launch module loading, a rank writing output files)
-                if (spins > (1u << 28)) __trap();
+                if (spins > (1u << 26)) __trap();
                 w = *h;
             }
             loc[j] = (int)(w & 0xffu);
@@ -699,7 +699,7 @@ __device__ __forceinline__ void xd_wait(const double* src, unsigned long long (&
     ld_poll_v4(src, w);
     for (uint32_t spins = 0; !xd_ready(w); ++spins) {
         __nanosleep(40);
-        if (spins > (1u << 28)) __trap();                // a lost peer must surface as an error, not as a hung GPU
+        if (spins > (1u << 26)) __trap();                // a lost peer must surface as an error, not as a hung GPU
         ld_poll_v4(src, w);
     }
 }
@@ -951,7 +951,7 @@ __device__ void apply_pending_sharded(const StepParams& p, const PassRows& pr, P
         const volatile unsigned long long* f = p.rflag_mine + (size_t)tid * nsm + cta;
         for (uint32_t spins = 0; *f < p.row_seq; ++spins) {
             __nanosleep(100);
-            if (spins > (1u << 28)) __trap();                    // a lost peer must surface as an error, not as a hung GPU
+            if (spins > (1u << 26)) __trap();                    // a lost peer must surface as an error, not as a hung GPU
         }
     }
     __threadfence();

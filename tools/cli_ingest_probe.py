@@ -51,7 +51,7 @@ def main():
         f.write("0.00000 0.00010 0.00100 0.01000\n")
     y = rng.normal(size=N)
     with open(stem + ".phen", "w") as f:
-        f.write("".join(f"{i + 1} {i + 1} {y[i]!r}\n" for i in range(N)))
+        f.write("".join(f"{i + 1} {i + 1} {float(y[i])!r}\n" for i in range(N)))
     t_write = time.time() - t0
     size = os.path.getsize(stem + ".bed")
     cmd = [os.path.join(ROOT, "gmrm_b200", "gmrm_b200_cli"), "--bed-file", stem + ".bed", "--dim-file", stem + ".dim", "--phen-files", stem + ".phen",
