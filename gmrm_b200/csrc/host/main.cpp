@@ -58,19 +58,38 @@ struct Shared {
     std::vector<std::vector<double>> bet_mean; // [T][Mt]
 };
 
-// this GPU's block of the .bed into the engine (Bayes::load_genotype, bayes.cpp:867-900), in chunks
+// this GPU's block of the .bed into the engine (Bayes::load_genotype, bayes.cpp:867-900), in chunks: two pinned buffers take
+// turns -- chunk k+1 is read from the file (a few threads, disjoint pread ranges) while chunk k is uploaded and transcoded
 void load_block(gmrm_engine* e, const host::Options& o, int N, int S, int M) {
     host::BedReader bed(o.bed_file, N);
-    const int chunk = std::max(1, (int)((256u << 20) / (size_t)bed.mbytes()));
-    // pinned read buffer: the upload is then plain DMA (gmrm_host_alloc, include/gmrm_b200.h)
-    uint8_t* buf = (uint8_t*)gmrm_host_alloc((size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes());
-    if (!buf) ck(-4, "gmrm_host_alloc");
-    for (int done = 0; done < M; done += chunk) {
-        const int n = std::min(chunk, M - done);
-        bed.read(S + done, n, buf);
-        ck(gmrm_upload_bed(e, buf, S + done, n), "gmrm_upload_bed");
+    size_t chunk_bytes = 256u << 20;
+    if (const char* v = getenv("GMRM_CLI_CHUNK_KB")) chunk_bytes = (size_t)std::max(1, atoi(v)) << 10;   // tests: many small chunks
+    const int chunk = std::max(1, (int)(chunk_bytes / (size_t)bed.mbytes()));
+    // pinned read buffers: the upload is then plain DMA (gmrm_host_alloc, include/gmrm_b200.h)
+    const size_t cap = (size_t)std::min(chunk, std::max(M, 1)) * bed.mbytes();
+    uint8_t* buf[2] = {(uint8_t*)gmrm_host_alloc(cap), M > chunk ? (uint8_t*)gmrm_host_alloc(cap) : nullptr};
+    if (!buf[0] || (M > chunk && !buf[1])) ck(-4, "gmrm_host_alloc");
+    const int nreaders = 4;
+    auto read_chunk = [&](int k) {
+        const int done = k * chunk, n = std::min(chunk, M - done);
+        std::vector<std::thread> th;
+        for (int r = 0; r < nreaders; r++) {
+            const int lo = (int)((int64_t)n * r / nreaders), hi = (int)((int64_t)n * (r + 1) / nreaders);
+            if (hi > lo) th.emplace_back([&, lo, hi] { bed.read(S + done + lo, hi - lo, buf[k & 1] + (size_t)lo * bed.mbytes()); });
+        }
+        for (auto& t : th) t.join();
+    };
+    const int nchunks = (M + chunk - 1) / chunk;
+    if (nchunks > 0) read_chunk(0);
+    for (int k = 0; k < nchunks; k++) {
+        const int done = k * chunk, n = std::min(chunk, M - done);
+        std::thread next;
+        if (k + 1 < nchunks) next = std::thread(read_chunk, k + 1);      // the other buffer: its upload (chunk k-1) has returned
+        ck(gmrm_upload_bed(e, buf[k & 1], S + done, n), "gmrm_upload_bed");
+        if (next.joinable()) next.join();
     }
-    gmrm_host_free(buf);
+    gmrm_host_free(buf[0]);
+    if (buf[1]) gmrm_host_free(buf[1]);
     ck(gmrm_finalize_bed(e), "gmrm_finalize_bed");
 }
 

@@ -1039,16 +1039,44 @@ __device__ __forceinline__ void prefetch_pass_head(const StepParams& p, int row0
 // LDG.128), two: 8 bytes, one: 4 bytes (chunk_offset below; build_tables uses the same map) -- so that a warp's load
 // instruction covers whole 128-byte lines (the 4-byte form touched two half-used lines per instruction and cost twice the
 // L1 wavefronts per byte).  Two register buffers take turns (A: in use, B: being loaded for the warp's next batch).
+// The genotype stream is read once per step and never again before it has left L2 anyway: its lines carry the L2
+// evict-first policy, so that what IS reused -- residuals, masks, the per-marker scalars the sampler reads at random, the
+// published columns the sampler prefetched for the update phase -- stays resident next to 238 MB of streamed bytes per step.
+#ifndef GMRM_STREAM_EVICT_FIRST
+#define GMRM_STREAM_EVICT_FIRST 1
+#endif
+__device__ __forceinline__ uint64_t stream_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint8_t* p, uint64_t pol) {
+    uint32_t v;
+#if GMRM_STREAM_EVICT_FIRST
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+#endif
+    return v;
+}
 template <int NR>
-__device__ __forceinline__ void load_words(const uint8_t* pa, const uint8_t* pb, uint32_t (&w)[NR]) {
+__device__ __forceinline__ void load_words(const uint8_t* pa, const uint8_t* pb, uint32_t (&w)[NR], uint64_t pol) {
     if constexpr (NR >= 4) {
+#if GMRM_STREAM_EVICT_FIRST
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(pa), "l"(pol));
+#else
         asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(pa));
-        if constexpr (NR == 5) w[4] = ldg_stream_u32(pb);
+#endif
+        if constexpr (NR == 5) w[4] = ldg_stream_u32(pb, pol);
     } else if constexpr (NR >= 2) {
+#if GMRM_STREAM_EVICT_FIRST
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(w[0]), "=r"(w[1]) : "l"(pa), "l"(pol));
+#else
         asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(w[0]), "=r"(w[1]) : "l"(pa));
-        if constexpr (NR == 3) w[2] = ldg_stream_u32(pb);
+#endif
+        if constexpr (NR == 3) w[2] = ldg_stream_u32(pb, pol);
     } else {
-        w[0] = ldg_stream_u32(pa);
+        w[0] = ldg_stream_u32(pa, pol);
     }
 }
 
@@ -1120,15 +1148,16 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         const int v = bb * kBatch + (l16 & (kBatch - 1));
         return (bb < nb && v < Vc) ? ccols[v] : 0;
     };
+    const uint64_t pol = stream_policy();
     uint32_t WA[kPairs][NR + ND], WB[kPairs][NR + ND];
     auto load_pair = [&](int col, int i, uint32_t (&dst)[kPairs][NR + ND]) {      // col: the pair's column for this half-warp (raw)
         const uint32_t r = (uint32_t)max(col, 0) * nrows + row0u;
         const uint8_t* pa = lane_a + (uint64_t)r * kRowBytes;
-        load_words<NR>(pa, pa + d_b, reinterpret_cast<uint32_t(&)[NR]>(dst[i]));
+        load_words<NR>(pa, pa + d_b, reinterpret_cast<uint32_t(&)[NR]>(dst[i]), pol);
         if constexpr (ND > 0) {
             const uint8_t* pd = lane_d + (uint64_t)((uint32_t)max(col, 0) * (uint32_t)p.drows) * kRowBytes;
 #pragma unroll
-            for (int d = 0; d < ND; d++) dst[i][NR + d] = ldg_stream_u32(pd + d * kRowBytes);
+            for (int d = 0; d < ND; d++) dst[i][NR + d] = ldg_stream_u32(pd + d * kRowBytes, pol);
         }
     };
     {

@@ -66,6 +66,16 @@ def _translate(instr, outs, ins):
     i = instr.strip()
     if i == "":                                              # empty statement: an optimisation barrier for the compiler only
         return "(void)0;"
+    if i.startswith("createpolicy."):                        # L2 eviction policy of the genotype stream: no meaning on the host
+        return f"{outs[0]} = 0;"
+    if i.startswith("ld.global.nc.L1::no_allocate.L2::cache_hint.u32"):
+        return f"{outs[0]} = *reinterpret_cast<const uint32_t*>({ins[0]});"
+    if i.startswith("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32"):
+        return ("{ const uint4 emu_t_ = *reinterpret_cast<const uint4*>(" + ins[0] + "); "
+                f"{outs[0]} = emu_t_.x; {outs[1]} = emu_t_.y; {outs[2]} = emu_t_.z; {outs[3]} = emu_t_.w; }}")
+    if i.startswith("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32"):
+        return ("{ const uint32_t* emu_t_ = reinterpret_cast<const uint32_t*>(" + ins[0] + "); "
+                f"{outs[0]} = emu_t_[0]; {outs[1]} = emu_t_[1]; }}")
     if i.startswith("ld.global.nc.L1::no_allocate.u32"):
         return f"{outs[0]} = *reinterpret_cast<const uint32_t*>({ins[0]});"
     if i.startswith("ld.global.nc.L1::no_allocate.v4.u32"):

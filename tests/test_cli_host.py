@@ -119,8 +119,10 @@ def test_cli_rejects_unsorted_mixtures(data, tmp_path):
 def test_cli_outputs_match_oracle(data, oracle, vranks, thin):
     out = os.path.join(data["tmp"], f"out_{vranks}_{thin}")
     iters, seed = 6, 4242
+    # the second case loads the .bed in many small chunks: both pinned buffers of the pipelined reader take turns
+    env = dict(os.environ, GMRM_CLI_CHUNK_KB="8") if vranks == 16 else None
     r = run(base_args(data, out) + ["--iterations", str(iters), "--seed", str(seed), "--vranks", str(vranks), "--output-thin-rate", str(thin),
-                                     "--burn-in", "2"])
+                                     "--burn-in", "2"], env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("total proc time") == iters                                      # bayes.cpp:655
     p = data["paths"]
