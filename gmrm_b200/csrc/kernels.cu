@@ -976,15 +976,37 @@ __host__ __device__ __forceinline__ int chunk_offset(int nr, int s, int l16, int
 
 // ---- (b) tables of rows [row0, row0 + nrp) for T traits, by the NC consumer threads; es[t] accumulates this
 // thread's share of sum eps
+#ifndef GMRM_BUILD_PIPE
+#define GMRM_BUILD_PIPE 1
+#endif
 template <int T, int NC>
 __device__ __forceinline__ void build_tables(const StepParams& p, int row0, int nrp, double (&es)[T]) {
     const int hw = threadIdx.x >> 4, l16 = threadIdx.x & 15;
     const int nunits = nrp * T * 4 * 3;
-    for (int u = hw; u < nunits; u += NC / 16) {
+    constexpr int kStride = NC / 16;
+    // a unit's four residuals: the loads of this half-warp's NEXT unit are issued before the current one's 27 entries are
+    // computed and stored (a pass of 5 rows is two units per half-warp: without this the second L2 round trip is exposed)
+    auto unit_ptr = [&](int u) -> const double* {
+        const int line = u / 3, k = line & 3, slot = line >> 2, rr = slot / T, t = slot - rr * T;
+        return p.eps + (int64_t)(p.t0 + t) * p.npad + ((int64_t)row0 * kRowBytes + chunk_offset(nrp, rr, l16, k)) * 4;
+    };
+    double2 n01 = make_double2(0.0, 0.0), n23 = make_double2(0.0, 0.0);
+    if (hw < nunits) {   // .cg: in the multi-GPU exchanges these rows were just stored by other GPUs (they land in this GPU's L2)
+        const double* e = unit_ptr(hw);
+        n01 = __ldcg(reinterpret_cast<const double2*>(e)); n23 = __ldcg(reinterpret_cast<const double2*>(e + 2));
+    }
+    for (int u = hw; u < nunits; u += kStride) {
         const int d3 = u % 3, line = u / 3, k = line & 3, slot = line >> 2, rr = slot / T, t = slot - rr * T;
-        const double* e = p.eps + (int64_t)(p.t0 + t) * p.npad + ((int64_t)row0 * kRowBytes + chunk_offset(nrp, rr, l16, k)) * 4;
-        // .cg: in the multi-GPU exchanges these rows were just stored by other GPUs (they land in this GPU's L2)
-        const double2 e01 = __ldcg(reinterpret_cast<const double2*>(e)), e23 = __ldcg(reinterpret_cast<const double2*>(e + 2));
+#if GMRM_BUILD_PIPE
+        const double2 e01 = n01, e23 = n23;
+        if (u + kStride < nunits) {
+            const double* e = unit_ptr(u + kStride);
+            n01 = __ldcg(reinterpret_cast<const double2*>(e)); n23 = __ldcg(reinterpret_cast<const double2*>(e + 2));
+        }
+#else       // measured alternative: every unit loads its own residuals when its turn comes
+        const double* e_ = unit_ptr(u);
+        const double2 e01 = __ldcg(reinterpret_cast<const double2*>(e_)), e23 = __ldcg(reinterpret_cast<const double2*>(e_ + 2));
+#endif
         if (d3 == 0) {
             const double s4 = (e01.x + e01.y) + (e23.x + e23.y);
 #pragma unroll
@@ -1103,15 +1125,25 @@ __device__ __forceinline__ void dir_fields(uint32_t w, const double (&wt)[16], d
     dir_operand<3>(D[3], m); acc = fma(D[3], wt[12 + F], acc);
 }
 
+// `es` non-null (GMRM_BUILD_FUSED=1, a measured alternative): the pass's tables are built HERE, by all threads, after the loads
+// of every warp's first batch have been issued, so that their latency runs under the build -- followed by the barrier that
+// publishes the tables.  A/B on one box at the UKB size: 61.1 ms per iteration against 60.4 with the build in front
+// (profiles/r2_small_ab_summary.txt): off.
+#ifndef GMRM_BUILD_FUSED
+#define GMRM_BUILD_FUSED 0
+#endif
 template <int NR, int T, int ND = 0>
-__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc, int dslot = 0) {
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc, int dslot = 0, double (*es)[T] = nullptr) {
     static_assert(ND == 0 || T == 1, "direct rows: one trait");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
     const uint32_t low = (uint32_t)l16 * 8u;
     const int nb = (Vc + kBatch - 1) / kBatch;
     int b = warp;
-    if (b >= nb) return;
+    if (b >= nb) {                                           // a warp without batches still builds and meets the barrier
+        if (es != nullptr) { build_tables<T, kStepThreads>(p, row0, NR, *es); __syncthreads(); }
+        return;
+    }
     // Addresses: (column * nrows + row0) is a 32-bit ROW index (columns are whole rows: < 2^32 rows for any shard that fits a
     // GPU), so a lane's address is ONE multiply-add  lane_a + row * 64  on top of its 64-bit lane base.  The base is passed
     // through an empty asm statement: the compiler otherwise re-derives it from the kernel parameters in front of every load
@@ -1166,6 +1198,7 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
         for (int i = 0; i < kPairs; i++) load_pair(__shfl_sync(0xffffffffu, c0, 2 * i + h), i, WA);
     }
     int cn = loadcols(b + kStepWarps);
+    if (es != nullptr) { build_tables<T, kStepThreads>(p, row0, NR, *es); __syncthreads(); }
     // L2 prefetch kPfAhead batches ahead of the register loads (which run one batch ahead): the 16 warps then keep
     // ~192 KB per SM in flight towards HBM instead of 64 KB
     constexpr int kPfAhead = 4;
@@ -1371,7 +1404,8 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         // hybrid plan (one trait): the LAST row of a pass of two or more rows is a DIRECT row: no table, genotypes from bed2
         const int r_lo = pr.start[pass], nall = pr.count[pass], ndp = (kDirectMax >= 1 && T == 1 && p.ndir > 0 && nall >= 2) ? 1 : 0, nrp = nall - ndp;
         const int dslot = pass * nsm + cta;
-        build_tables<T, NT>(p, r_lo, nrp, es);
+        const bool fused = GMRM_BUILD_FUSED && ndp == 0 && nrp > 0;   // the stream builds the tables itself (see stream_rows)
+        if (!fused) build_tables<T, NT>(p, r_lo, nrp, es);
         if (ndp > 0) {                                    // the direct rows' share of sum eps (their tables would have added it)
             for (int i = tid; i < ndp * kRowBytes; i += NT) {
                 const double* e = p.eps + (int64_t)p.t0 * p.npad + ((int64_t)(r_lo + nrp) * kRowBytes + i) * 4;
@@ -1379,10 +1413,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
                 es[0] += (a.x + a.y) + (b.x + b.y);
             }
         }
-        __syncthreads();
+        if (!fused) __syncthreads();
         GMRM_TICK()                                       // [9 + 3*pass] sync + build
         for (int v0 = 0; v0 < p.V; v0 += Vc_max) {
             const int Vc = min(Vc_max, p.V - v0);
+            double (*esb)[T] = (fused && v0 == 0) ? &es : nullptr;
             if constexpr (T == 1 && kDirectMax >= 1) {
                 if (ndp == 1) {
                     switch (nrp) {
@@ -1396,11 +1431,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
             }
             if (ndp == 0)
             switch (nrp) {
-            case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc); break;
-            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc); break;
-            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part, v0, Vc); break;
-            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part, v0, Vc); break;
-            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc); break;
+            case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc, 0, esb); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc, 0, esb); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part, v0, Vc, 0, esb); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part, v0, Vc, 0, esb); break;
+            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc, 0, esb); break;
             default: break;
             }
             if (chunked && nall > 0) {                    // this chunk's sums of this pass -> the CTA's global slots
@@ -1541,9 +1576,33 @@ __global__ void group_consts_kernel(int T, int G, int K, int N, const double* __
 // round 1: column index, the marker's partial sums and the residual sums (none depends on the column);
 // round 2 (needs the column): missing-list bounds, group, mave, msig, beta;  round 3: sigmaG, sampler constants.
 // The published item of lane t < T (trait t) is returned in (lam, mave); lam == 0: nothing to publish.
+#ifndef GMRM_SAMPLE_EARLY
+#define GMRM_SAMPLE_EARLY 1
+#endif
 __device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lane, int col, double& out_lam, double& out_mave) {
     out_lam = 0.0; out_mave = 0.0;
-    // ---- round 1: sum a*eps partials and sum eps, trait by trait (fixed order), while `col` is in flight
+#if !GMRM_SAMPLE_EARLY
+    pdl_wait();
+#endif
+    // ---- before the grid dependency: everything about the marker that the step kernel still running does not write --
+    // missing-list bounds, group, mave, msig, beta, the group's variance and sampler constants.  Their (often HBM) round
+    // trips then run under the tail of the step kernel instead of behind the partial sums.
+    const int cc = max(col, 0);
+    const uint32_t m0 = p.miss_off[cc], m1 = p.miss_off[cc + 1];
+    const int grp = p.group[cc];
+    const int tl = lane < p.T ? lane : 0;
+    const int64_t mi = (int64_t)tl * p.Mloc + cc;
+    const double mave = p.mave[mi], msig = p.msig[mi], beta_old = p.betas[mi];
+    const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + tl;
+    const double rep_u = p.rep_u ? p.rep_u[ri] : 0.0;
+    const int nonas = p.nonas[tl];
+    const double sigg = p.sigmag[tl * p.G + grp];
+    const double* gc = p.gc + ((int64_t)tl * p.G + grp) * 4 * p.K;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(gc + (lane & 15)));
+#if GMRM_SAMPLE_EARLY
+    pdl_wait();                                              // the step kernel's partial sums are complete and visible
+#endif
+    // ---- sum a*eps partials and sum eps, trait by trait (fixed order)
     double my_coded = 0.0, my_sall = 0.0;
     for (int t = 0; t < p.T; t++) {
         const double* part = p.partial + ((int64_t)v * p.T + t) * p.nsm;
@@ -1563,18 +1622,6 @@ __device__ __forceinline__ void sample_one(const SampleParams& p, int v, int lan
         if (lane == t) { my_coded = coded; my_sall = sall; }
     }
     if (col < 0) return;
-    // ---- round 2
-    const uint32_t m0 = p.miss_off[col], m1 = p.miss_off[col + 1];
-    const int grp = p.group[col];
-    const int tl = lane < p.T ? lane : 0;
-    const int64_t mi = (int64_t)tl * p.Mloc + col;
-    const double mave = p.mave[mi], msig = p.msig[mi], beta_old = p.betas[mi];
-    const int64_t ri = ((int64_t)p.step * p.R + (p.r0 + v)) * p.T + tl;
-    const double rep_u = p.rep_u ? p.rep_u[ri] : 0.0;
-    const int nonas = p.nonas[tl];
-    // ---- round 3
-    const double sigg = p.sigmag[tl * p.G + grp];
-    const double* gc = p.gc + ((int64_t)tl * p.G + grp) * 4 * p.K;
     double my_smiss = 0.0;
     if (m1 > m0)                                              // warp-uniform: sum of eps over the missing genotypes
         for (int t = 0; t < p.T; t++) {
@@ -1627,9 +1674,9 @@ __global__ void __launch_bounds__(kSegCap * 32) sample_kernel(const SampleParams
     if (tid == 0) s_npub = 0;
     pdl_trigger();                                           // the next step kernel may start its prologue (shared-memory set-up, L2 prefetch)
     const int col = v < p.V ? p.cols[v] : -1;
-    pdl_wait();                                              // the step kernel's partial sums are complete and visible
     double lam = 0.0, mave = 0.0;
-    if (v < p.V) sample_one(p, v, lane, col, lam, mave);
+    if (v < p.V) sample_one(p, v, lane, col, lam, mave);     // waits for the step kernel (pdl_wait) after its marker-only loads
+    else pdl_wait();
     if (p.pf_bed != nullptr && __ballot_sync(0xffffffffu, lam != 0.0) != 0u && lane == 0 && col >= 0)   // published: its column is needed again in a few microseconds
         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.pf_bed + (int64_t)col * p.pf_col_stride), "r"((uint32_t)p.pf_col_stride) : "memory");
     if (lane < p.T) { s_lam[lane][warp] = lam; s_mave[lane][warp] = mave; }

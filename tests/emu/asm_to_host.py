@@ -103,7 +103,7 @@ def _translate(instr, outs, ins):
         return f"emu_sts<double>({ins[0]}, {ins[1]});"
     if i.startswith("prmt.b32"):
         return f"{outs[0]} = emu_prmt({ins[0]}, {ins[1]}, {ins[2]});"
-    if i.startswith("prefetch.global.L2") or i.startswith("cp.async.bulk.prefetch.L2"):
+    if i.startswith("prefetch.global.L2") or i.startswith("prefetch.global.L1") or i.startswith("cp.async.bulk.prefetch.L2"):
         return "(void)0;"
     if i.startswith("griddepcontrol."):                      # programmatic dependent launch: launches are serial on the host
         return "(void)0;"
