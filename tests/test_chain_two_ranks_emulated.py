@@ -125,13 +125,17 @@ def test_two_rank_chain_with_increment_exchange_matches_oracle(tmp_path):
     test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=True)
 
 
-def test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=False):
+def test_three_rank_chain_with_increment_exchange_matches_oracle(tmp_path):
+    """The same with three ranks: sub-slices that do not divide the CTA's quads evenly, three increments added in rank order."""
+    test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=True, world=3)
+
+
+def test_two_rank_chain_with_list_exchange_matches_oracle(tmp_path, xd=False, world=2):
     sys.path.insert(0, ROOT)
     from gmrm_b200 import synth
     c = CASE
     synth.write_dataset(str(tmp_path), N=c["N"], M=c["M"], n_traits=c["T"], n_groups=c["G"], na_rate=0.02, missing_rate=0.015, seed=19)
     so = build(str(tmp_path))
-    world = 2
     ctx = mp.get_context("spawn")
     out = ctx.Manager().dict()
     port = 29000 + os.getpid() % 2000
