@@ -315,19 +315,20 @@ __global__ void __launch_bounds__(1024) eps_sumsq_kernel(const double* __restric
 // each pass (all_pass_rows below), at most rows_per_pass rows (as many (row, trait) table slots as shared memory
 // holds).  Per CTA:
 //   update: every thread owns up to 2 quads of the CTA's rows per round; for each published marker of the
-//           previous step (rank order) it adds  v[dosage]  to its 4 residuals -- one PRMT + LDS.64 + DADD per
-//           individual, NA / missing individuals are routed to a zero entry
-//   build : half-warp <-> (slot, byte k, third d3 of the 81 entries); lane l owns the quad 4l+k of the row:
+//           previous step (rank order) it adds  v[dosage]  to its 4 residuals -- pair tables: one PRMT + LDS.64 + DADD
+//           per individual serves TWO published markers; NA / missing individuals are routed to a zero entry.  On
+//           several GPUs (sync rate 1) the sums start from zero and are exchanged as increments (exchange_increments)
+//   build : half-warp <-> (slot, byte k, third d3 of the 81 entries); lane l owns one quad of the slot (chunk_offset):
 //           reads its 4 residuals, writes 27 entries  sum_k d_k eps_k  (conflict-free 8-byte stores)
-//   stream: warp w takes batches w, w+16, ... of 16 markers; in a batch, half-warp h works on marker 2i+h of
-//           pair i = 0..7; lane l loads word l of each of the pass's rows straight from HBM/L2 into registers,
-//           one batch ahead of its use (and prefetches into L2 further ahead), and per byte does
-//           PRMT -> LDS.64 -> DADD  into the pair's accumulator; a 16-lane transposed butterfly leaves one total
-//           per marker, added to the marker's partial sum in shared memory (each marker is always served by the
-//           same lane: plain read-modify-write).
+//   stream: warp w takes batches w, w+16, ... of 8 markers; in a batch, half-warp h works on marker 2i+h of
+//           pair i = 0..3; lane l loads its words of the pass's rows with one 16-byte load (+ one 4-byte load for a fifth
+//           row) straight from HBM/L2 into one of two register buffers, one batch ahead of its use (and prefetches into
+//           L2 further ahead), and per byte does  PRMT -> LDS.64 -> DADD  into the pair's accumulator; a 16-lane
+//           transposed butterfly leaves one total per marker, added to the marker's partial sum in shared memory (each
+//           marker is always served by the same lane: plain read-modify-write).
 //   (A shared-memory ring fed by a producer warp -- cp.async.bulk or cp.async -- was measured and dropped: with
 //   227 KB of tables + partials only 32-40 KB are left for it, and the producer hand-off costs more than the
-//   register double-buffer; profiles/README.md.)
+//   register double-buffer; DESIGN.md section 5 lists this and the other measured alternatives.)
 // At the end the CTA writes partial[v][t][cta] and its sum of residuals spart[t][cta]; the sampler kernel
 // adds the nsm partials of a marker in a fixed order.
 // =====================================================================================
