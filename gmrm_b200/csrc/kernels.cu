@@ -1133,8 +1133,15 @@ __device__ __forceinline__ void dir_fields(uint32_t w, const double (&wt)[16], d
 #ifndef GMRM_BUILD_FUSED
 #define GMRM_BUILD_FUSED 0
 #endif
+// 1 (a measured alternative): the CTA's last pass stores every marker's sum straight into its global slot instead of the
+// 2,048-store burst behind the final barrier.  A/B on one box: the step kernel got 1.5 us SLOWER (scattered stores inside the
+// stream loop), profiles/r2_small_ab_summary.txt: off.
+#ifndef GMRM_PARTIAL_DIRECT
+#define GMRM_PARTIAL_DIRECT 0
+#endif
 template <int NR, int T, int ND = 0>
-__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc, int dslot = 0, double (*es)[T] = nullptr) {
+__device__ __forceinline__ void stream_rows(const StepParams& p, int row0, double* part, int v0, int Vc, int dslot = 0, double (*es)[T] = nullptr,
+                                            bool last = false) {
     static_assert(ND == 0 || T == 1, "direct rows: one trait");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = lane >> 4, l16 = lane & 15;
@@ -1309,7 +1316,12 @@ __device__ __forceinline__ void stream_rows(const StepParams& p, int row0, doubl
             }
             b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
             const int v = bb * kBatch + 2 * own + h;
-            if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < Vc) part[v * T + t] += b1;
+            if ((l16 & (kPairs == 8 ? 1 : kPairs == 4 ? 3 : 7)) == 0 && v < Vc) {
+                // the CTA's last pass (GMRM_PARTIAL_DIRECT): the marker's sum goes straight to its global slot -- the stores
+                // spread over the pass instead of a 2,048-store burst behind the final barrier
+                if (GMRM_PARTIAL_DIRECT && last) p.partial[((int64_t)(v0 + v) * p.Ttot + p.t0 + t) * gridDim.x + blockIdx.x] = part[v * T + t] + b1;
+                else part[v * T + t] += b1;
+            }
         }
     };
     for (;;) {
@@ -1400,6 +1412,12 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
 #pragma unroll
     for (int t = 0; t < T; t++) es[t] = 0.0;
     bool flushed = false;                                 // chunked steps: the global slots hold the sums of earlier passes
+    int last_pass = -1;                                   // the CTA's last pass with rows: its stream writes the partial sums out itself
+#if GMRM_PARTIAL_DIRECT
+    if (!chunked)
+        for (int q = 0; q < npass; q++)
+            if (pr.count[q] > 0) last_pass = q;
+#endif
     for (int pass = 0; pass < npass; pass++) {
         // rows of the pass beyond the table slots are DIRECT rows (hybrid plan, one trait): no table, genotypes from bed2
         // hybrid plan (one trait): the LAST row of a pass of two or more rows is a DIRECT row: no table, genotypes from bed2
@@ -1419,6 +1437,7 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
         for (int v0 = 0; v0 < p.V; v0 += Vc_max) {
             const int Vc = min(Vc_max, p.V - v0);
             double (*esb)[T] = (fused && v0 == 0) ? &es : nullptr;
+            const bool lastp = pass == last_pass && ndp == 0;
             if constexpr (T == 1 && kDirectMax >= 1) {
                 if (ndp == 1) {
                     switch (nrp) {
@@ -1432,11 +1451,11 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
             }
             if (ndp == 0)
             switch (nrp) {
-            case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc, 0, esb); break;
-            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc, 0, esb); break;
-            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part, v0, Vc, 0, esb); break;
-            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part, v0, Vc, 0, esb); break;
-            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc, 0, esb); break;
+            case 1: stream_rows<1, T>(p, r_lo, part, v0, Vc, 0, esb, lastp); break;
+            case 2: if constexpr (2 * T <= kMaxSlots) stream_rows<2, T>(p, r_lo, part, v0, Vc, 0, esb, lastp); break;
+            case 3: if constexpr (3 * T <= kMaxSlots) stream_rows<3, T>(p, r_lo, part, v0, Vc, 0, esb, lastp); break;
+            case 4: if constexpr (4 * T <= kMaxSlots) stream_rows<4, T>(p, r_lo, part, v0, Vc, 0, esb, lastp); break;
+            case 5: if constexpr (5 * T <= kMaxSlots) stream_rows<5, T>(p, r_lo, part, v0, Vc, 0, esb, lastp); break;
             default: break;
             }
             if (chunked && nall > 0) {                    // this chunk's sums of this pass -> the CTA's global slots
@@ -1458,12 +1477,14 @@ __global__ void __launch_bounds__(kStepThreads, 1) step_kernel(const StepParams 
     }
     __syncthreads();
     GMRM_TICK()
-    if (!chunked) {
+    // (hybrid plan: a last pass with a direct row keeps the shared-memory sums, written out here)
+    const bool wrote_direct = last_pass >= 0 && !(kDirectMax >= 1 && T == 1 && p.ndir > 0 && pr.count[last_pass] >= 2);
+    if (!chunked && !wrote_direct) {
         for (int i = tid; i < p.V * T; i += NT) {
             const int v = i / T, t = i - v * T;
             p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = part[i];
         }
-    } else if (!flushed) {                                // a CTA that owns no rows at all (more CTAs than rows): its slots are zero
+    } else if (chunked && !flushed) {                                // a CTA that owns no rows at all (more CTAs than rows): its slots are zero
         for (int i = tid; i < p.V * T; i += NT) {
             const int v = i / T, t = i - v * T;
             p.partial[((int64_t)v * p.Ttot + p.t0 + t) * nsm + cta] = 0.0;
