@@ -127,6 +127,13 @@ extern "C" int emu_chain(const uint8_t* plink, int N, int nsm, int Mt, int T, in
         step(0, true, plan + 3);                             // flush
         // ---- epilogue
         emu_launch(EmuDim3(T), EmuDim3(256), [&] { beta_sq_kernel(betas.data(), group, Mt, G, bsq.data()); });
+        if (it == 1) {   // the two-level form the engine uses for shards of 4,096 markers and more: same sums
+            std::vector<double> part((size_t)T * kBsqSlices * G, -1.0), bsq2((size_t)T * G, -1.0);
+            emu_launch(EmuDim3(T, kBsqSlices), EmuDim3(256), [&] { beta_sq_part_kernel(betas.data(), group, Mt, G, part.data()); });
+            emu_launch(EmuDim3((T * G + 127) / 128), EmuDim3(128), [&] { beta_sq_final_kernel(part.data(), T, G, bsq2.data()); });
+            for (int i = 0; i < T * G; i++)
+                if (std::fabs(bsq2[i] - bsq[i]) > 1e-12 * std::max(1.0, std::fabs(bsq[i]))) err = 77;
+        }
         emu_launch(EmuDim3(T), EmuDim3(1024), [&] { eps_sumsq_kernel(eps.data(), L.npad, N, esq.data()); });
         GlobalDrawParams gp{};
         gp.T = T; gp.G = G; gp.K = K; gp.N = N; gp.it = it; gp.seed = seed; gp.mtotgrp = mtotgrp.data(); gp.bsq = bsq.data();
