@@ -1295,6 +1295,11 @@ int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]) {
     return GMRM_OK;
 }
 
+int gmrm_debug_chunk_offset(int32_t rows, int32_t slot, int32_t lane16, int32_t k) {
+    if (rows < 1 || rows > kMaxSlots || slot < 0 || slot >= rows || lane16 < 0 || lane16 > 15 || k < 0 || k > 3) return -1;
+    return host_chunk_offset(rows, slot, lane16, k);
+}
+
 // Test hook, no device needed: the step kernel's launch plan for (N, nsm, V, T) -- traits per launch, rows per pass,
 // passes, dynamic shared memory -- and, if `ranges` is given, the rows [start, start+count) every CTA owns in every pass
 // (ranges[(pass * nsm + cta) * 2 + {0,1}], room for 64 * nsm * 2 ints).

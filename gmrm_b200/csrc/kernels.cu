@@ -1935,6 +1935,7 @@ void launch_eps_sumsq(const double* eps, int64_t npad, int64_t n, int T, double*
 }
 
 void host_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count) { all_pass_rows(nrows, npass, nsm, cta, start, count); }
+int host_chunk_offset(int nr, int slot, int lane16, int k) { return chunk_offset(nr, slot, lane16, k); }
 
 constexpr int kMaxDynSmem = 232448;   // 227 KB: the most one CTA can opt into on sm_100
 

@@ -177,6 +177,7 @@ void launch_fill_u64(unsigned long long* dst, size_t n, unsigned long long value
 // dynamic shared memory the step kernel needs, or -1 if (V, T, rows_per_pass, rows per CTA) do not fit
 int step_npass(const Layout& L, int rows_per_pass);
 void host_pass_rows(int nrows, int npass, int nsm, int cta, int* start, int* count);   // the kernel's row ownership [npass], for tests
+int host_chunk_offset(int nr, int slot, int lane16, int k);                                // the kernel's lane -> byte map inside a pass chunk, for tests
 int step_smem_bytes(const Layout& L, int V, int T, int rows_per_pass);
 // traits per launch and rows per pass for a step of V markers (0 rows = does not fit)
 void step_plan(const Layout& L, int V, int Ttot, int* traits_per_launch, int* rows_per_pass);

@@ -194,6 +194,11 @@ int gmrm_genetic_values(gmrm_engine* e, int32_t trait, const double* beta, doubl
 int gmrm_debug_step_plan(int32_t N, int32_t nsm, int32_t V, int32_t T, int32_t* traits_per_launch, int32_t* rows_per_pass,
                          int32_t* npass, int32_t* smem_bytes, int32_t* nrows, int32_t* ranges);
 
+/* --- test hook without a device: where the step kernel's lanes find their genotype bytes.  A CTA's share of a column in a pass
+ * of `rows` (1..5) rows is one chunk of rows * 64 bytes; the byte at the returned offset is byte k (0..3) of the word that lane
+ * `lane16` (0..15, of the 16 lanes serving a marker) looks up in table slot `slot` (0..rows-1).  Negative: bad argument. */
+int gmrm_debug_chunk_offset(int32_t rows, int32_t slot, int32_t lane16, int32_t k);
+
 /* --- multi-GPU (one process per GPU): rank 0 makes the id, the launcher broadcasts it. */
 int gmrm_comm_unique_id(uint8_t id[128]);
 int gmrm_comm_init(gmrm_engine* e, const uint8_t id[128]);

@@ -73,3 +73,32 @@ def test_bad_arguments_are_refused():
     assert plan(1000, 0, 16, 1) is None
     assert plan(1000, 148, -1, 1) is None
     assert plan(1000, 148, 16, 0) is None
+
+
+def test_lane_byte_map_of_a_pass_chunk_is_a_bijection():
+    """chunk_offset (kernels.cu): (table slot, lane, byte) <-> byte of the CTA's rows * 64-byte chunk of a column.  Every byte
+    exactly once; a lane's words of a 4-slot group are 16 contiguous, 16-byte aligned bytes (one LDG.128), of a 2-slot group
+    8 (LDG.64); the table build and the stream use the same map."""
+    import ctypes as C
+    from gmrm_b200 import api
+    f = api.lib().gmrm_debug_chunk_offset
+    f.restype = C.c_int
+    for rows in range(1, 6):
+        seen = {}
+        for s_ in range(rows):
+            for lane in range(16):
+                for k in range(4):
+                    o = f(rows, s_, lane, k)
+                    assert 0 <= o < rows * 64 and o not in seen
+                    seen[o] = (s_, lane, k)
+        assert len(seen) == rows * 64
+        for lane in range(16):
+            if rows >= 4:
+                base = f(rows, 0, lane, 0)
+                assert base % 16 == 0 and [f(rows, s_, lane, k) for s_ in range(4) for k in range(4)] == list(range(base, base + 16))
+            elif rows >= 2:
+                base = f(rows, 0, lane, 0)
+                assert base % 8 == 0 and [f(rows, s_, lane, k) for s_ in range(2) for k in range(4)] == list(range(base, base + 8))
+            last = f(rows, rows - 1, lane, 0)
+            assert last % 4 == 0 and [f(rows, rows - 1, lane, k) for k in range(4)] == list(range(last, last + 4))
+    assert f(6, 0, 0, 0) < 0 and f(3, 3, 0, 0) < 0 and f(3, 0, 16, 0) < 0
